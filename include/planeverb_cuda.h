@@ -1,0 +1,148 @@
+/*
+ * planeverb_cuda.h -- the thin C-ABI CUDA layer behind Planeverb's hot path.
+ *
+ * This is the internal seam SURVEY.md section 8(b) names: the reference's
+ *     Grid::GenerateResponse(listener)      ProjectPlaneverb/src/FDTD/Grid.h:32-34, FDTD.cpp:244-254
+ *     Grid::GenerateResponseGPU (throws)    ProjectPlaneverb/src/FDTD/FDTD.cpp:238-242   <- the stub this implements
+ *     Analyzer::AnalyzeResponses(listener)  ProjectPlaneverb/src/DSP/Analyzer.h:30, Analyzer.cpp:48-104
+ *     Grid::AddAABB / RemoveAABB            ProjectPlaneverb/src/FDTD/Grid.cpp:229-296
+ *     FreeGrid::SimulateFreeFieldEnergy     ProjectPlaneverb/src/FDTD/FreeGrid.cpp:71-94
+ *     Grid::GetResponse                     ProjectPlaneverb/src/FDTD/FDTD.cpp:74-79
+ * selected when PlaneverbConfig::threadExecutionType == 1 (the commented-out pv_GPU,
+ * ProjectPlaneverb/include/PvTypes.h:13-17).
+ *
+ * Plain C: opaque handle, plain pointers and sizes, int status codes (0 = ok).  All pointers are
+ * HOST pointers unless the name ends in _dev.  Every scalar that the reference derives through a
+ * float->int truncation (grid size, response length, listener cell, AABB cell rectangle, analysis
+ * window lengths) is computed by the HOST caller with the reference's own expressions
+ * (planeverb_b200/csrc/pv_params.h) and handed in here as integers, so the device never re-derives
+ * an index.  Host-side consumers: planeverb_b200/csrc/planeverb_api.cpp (the Planeverb C++ API +
+ * Unity C ABI) and planeverb_b200/pvcuda.py (ctypes, tests and bench).
+ *
+ * Layout contract: a "plane" is (gx+1) rows of (gy+1) floats, row-major, index r*(gy+1)+c -- the
+ * alloc-grid indexing of FDTD.cpp:99.  Results use the analyzer's interior indexing s = r*gx + c
+ * (PvDefinitions.h:23-24, Analyzer.cpp:79), 8 floats per cell in AnalyzerResult order
+ * (Analyzer.h:13-21): occlusion, wetGain, rt60, lowpass, direction.x, direction.y,
+ * sourceDirectivity.x, sourceDirectivity.y.
+ */
+#ifndef PLANEVERB_CUDA_H
+#define PLANEVERB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PVC_API __declspec(dllexport)
+#else
+#define PVC_API __attribute__((visibility("default")))
+#endif
+
+typedef struct pvc_solver pvc_solver;
+
+enum pvc_status
+{
+    PVC_OK = 0,
+    PVC_ERR_INVALID = 1,    /* bad argument            (reference: throw pv_InvalidConfig)   */
+    PVC_ERR_MEMORY = 2,     /* device allocation failed (reference: throw pv_NotEnoughMemory) */
+    PVC_ERR_CUDA = 3,       /* CUDA runtime error, see pvc_last_error()                       */
+    PVC_ERR_NO_DEVICE = 4   /* no usable CUDA device: the product has NO CPU fallback         */
+};
+
+/* Everything Grid's constructor and Analyzer's constructor derive (Grid.cpp:46-55, Analyzer.cpp:20-27,
+ * 170-171,237,284), already evaluated on the host. */
+typedef struct pvc_config
+{
+    int   gx, gy;            /* interior cells (int)m_gridSize.x/.y                               */
+    int   T;                 /* response length in samples (m_responseLength)                     */
+    int   fs;                /* sampling rate (m_samplingRate)                                    */
+    int   resolution;        /* gridResolution                                                    */
+    float dx;                /* metres per cell                                                   */
+    float courant;           /* PV_C*dt/dx as evaluated at FDTD.cpp:90                            */
+    int   flux_samples;      /* (int)(PV_DRY_DIRECTION_ANALYSIS_LENGTH*fs)   Analyzer.cpp:171     */
+    int   dry_samples;       /* (int)(PV_DRY_GAIN_ANALYSIS_LENGTH*fs)        Analyzer.cpp:170     */
+    int   wet_samples;       /* (int)(PV_WET_GAIN_ANALYSIS_LENGTH*fs)        Analyzer.cpp:237     */
+    int   tail_samples;      /* (int)(PV_SCHROEDER_OFFSET_S*fs)              Analyzer.cpp:284     */
+    int   max_sources;       /* listener positions solved per pvc_run call (batched on one GPU)   */
+    int   device;            /* CUDA device ordinal                                               */
+    int   step_kernel;       /* 0 = default (fused, temporally blocked), 1 = two-launch baseline  */
+    int   reserved;          /* fused-kernel tile variant (0 = default); tuning knob, see pvc_step_fused.cu */
+} pvc_config;
+
+/* One queued geometry edit, already voxelised to a half-open cell rectangle rows [r0,r1) x cols
+ * [c0,c1) by the host with the truncations of Grid.cpp:139-142 / 252-255 (clipping to 0..gx / 0..gy
+ * inclusive happens on the device as in Grid.cpp:231,235). add != 0: wall with admittance
+ * Y = (1-R)/(1+R) (FDTD.cpp:153,160); add == 0: back to air (Grid.cpp:260-295). Applied in order. */
+typedef struct pvc_rect
+{
+    int   r0, r1, c0, c1;
+    int   add;
+    float admittance;
+} pvc_rect;
+
+/* One listener ("source" in BASELINE.json): pulse cell (FDTD.cpp:97-99), the analyzer's own listener
+ * cell (Analyzer.cpp:201-202 -- multiply-by-reciprocal, can differ by one) and its world position. */
+typedef struct pvc_listener
+{
+    int   cell_r, cell_c;
+    int   efree_r, efree_c;
+    float x, z;
+} pvc_listener;
+
+PVC_API int  pvc_device_count(void);
+PVC_API const char* pvc_last_error(void);
+
+PVC_API int  pvc_create(const pvc_config* cfg, pvc_solver** out);
+PVC_API void pvc_destroy(pvc_solver* s);
+
+/* bytes of device memory pvc_create would allocate for cfg (pressure history dominates: 4*T*plane per source) */
+PVC_API size_t pvc_memory_requirement(const pvc_config* cfg);
+
+/* Gaussian source pulse, T floats (Grid.cpp:12-27, evaluated by the host) */
+PVC_API int  pvc_set_pulse(pvc_solver* s, const float* pulse, int n);
+
+/* reset the coefficient plane to the empty grid of Grid.cpp:84-108 */
+PVC_API int  pvc_clear_geometry(pvc_solver* s);
+/* apply n queued edits in order on the device (GeometryManager::PushGeometryChanges, GeometryManager.cpp:123-152) */
+PVC_API int  pvc_apply_geometry(pvc_solver* s, const pvc_rect* rects, int n);
+/* read back the coefficient plane as the reference's two fields: b (0/1) and admittance Y (tests) */
+PVC_API int  pvc_fetch_coefficients(pvc_solver* s, int16_t* b, float* admittance);
+
+/* FreeGrid (FreeGrid.cpp:71-110): n-step free-field run on an empty grid from (lr,lc); returns
+ * r * sum_{i<n} p_i^2 at (er,ec). The result is also installed as the solver's EFree. */
+PVC_API int  pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, float r, float* efree);
+PVC_API int  pvc_set_efree(pvc_solver* s, float efree);
+
+/* GenerateResponse + AnalyzeResponses for n listeners (n <= max_sources), asynchronous on the
+ * solver's stream; results stay on the device until fetched. analyze == 0 skips the analyzer. */
+PVC_API int  pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze);
+PVC_API int  pvc_synchronize(pvc_solver* s);
+
+/* zero the persistent results of one source slot (Context's memset, PvContext.cpp:132) */
+PVC_API int  pvc_clear_results(pvc_solver* s, int source);
+/* results: gx*gy*8 floats, delay: gx*gy floats (FLT_MAX = no onset); either may be NULL. Synchronous. */
+PVC_API int  pvc_fetch_results(pvc_solver* s, int source, float* results, float* delay);
+/* the 8 floats of one interior cell (Analyzer::GetResponseResult, Analyzer.cpp:106-116) */
+PVC_API int  pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8);
+/* impulse response of alloc cell (r,c): T x {p, vx, vy} (Grid::GetResponse). vx/vy are rebuilt on the
+ * device from the pressure history with the solver's own update rules. */
+PVC_API int  pvc_fetch_ir(pvc_solver* s, int source, int r, int c, float* out3T);
+/* pressure plane recorded for sample t (tests): (gx+1)*(gy+1) floats */
+PVC_API int  pvc_fetch_pressure(pvc_solver* s, int source, int t, float* plane);
+/* final p/vx/vy planes after the last step, before the last injection (tests) */
+PVC_API int  pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, float* vy);
+
+/* timing of the last pvc_run in milliseconds, measured with CUDA events on the solver's stream:
+ * out[0] = step kernels, out[1] = analyzer kernels, out[2] = total; launches = kernels launched */
+PVC_API int  pvc_last_timing(pvc_solver* s, float* out3, int* launches);
+/* device-resident raw pointers for zero-copy consumers (results_dev: gx*gy*8 floats of a source) */
+PVC_API const float* pvc_results_dev(pvc_solver* s, int source);
+PVC_API void* pvc_stream(pvc_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,65 @@
+/*
+ * planeverb_ext.h -- "scene solver" entry points: the reference's Grid + FreeGrid + Analyzer trio
+ * driven directly (no Context background thread), with HOST buffers in and out.
+ *
+ * Mirrors, call for call, what a host program does with the reference classes
+ *     Grid::Grid / AddAABB / RemoveAABB      ProjectPlaneverb/src/FDTD/Grid.cpp:30-117,136-296
+ *     FreeGrid::FreeGrid                     ProjectPlaneverb/src/FDTD/FreeGrid.cpp:6-34
+ *     Grid::GenerateResponse                 ProjectPlaneverb/src/FDTD/FDTD.cpp:244-254
+ *     Analyzer::AnalyzeResponses             ProjectPlaneverb/src/DSP/Analyzer.cpp:48-104
+ *     Analyzer::GetResponseResult            ProjectPlaneverb/src/DSP/Analyzer.cpp:106-116
+ * plus the two things BASELINE.json's configs need that the reference's Context does not offer:
+ * an explicit response length (500/2000/4000 steps instead of the derived fs*0.3015 s) and several
+ * listener positions ("sources") solved as one batch.  The Planeverb C++ API / Unity C ABI
+ * (include/Planeverb.h, include/PlaneverbUnity.h) sits on the same code for the drop-in path; this
+ * header is what tests/ and bench.py bind (planeverb_b200/pvcuda.py).  Positions are world metres on
+ * the (x, z) plane exactly as in Planeverb::vec3 usage (FDTD.cpp:97-98).
+ */
+#ifndef PLANEVERB_EXT_H
+#define PLANEVERB_EXT_H
+
+#include "planeverb_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pvx_scene pvx_scene;
+
+/* responseLength <= 0: the reference's derived length (Grid.cpp:55). efree < 0: run the free-field
+ * simulation on the device (FreeGrid.cpp:71-94). stepKernel/variant: see pvc_config. */
+PVC_API int  pvx_create(float sizeX, float sizeY, int resolution, int responseLength, float efree,
+                        int maxSources, int device, int stepKernel, int variant, pvx_scene** out);
+PVC_API void pvx_destroy(pvx_scene* sc);
+
+/* ints[10] = gx, gy, T, fs, fluxSamples, drySamples, wetSamples, tailSamples, freeSamples, maxSources
+ * floats[4] = dx, dt, courant, efree */
+PVC_API int  pvx_info(pvx_scene* sc, int* ints, float* floats);
+PVC_API int  pvx_pulse(pvx_scene* sc, float* out, int n);
+
+/* queue an AddAABB / RemoveAABB (Grid.cpp:136,249); flushed in order before the next solve, like
+ * GeometryManager::PushGeometryChanges (GeometryManager.cpp:123-152) */
+PVC_API int  pvx_add_aabb(pvx_scene* sc, float posX, float posY, float width, float height, float absorption);
+PVC_API int  pvx_remove_aabb(pvx_scene* sc, float posX, float posY, float width, float height, float absorption);
+PVC_API int  pvx_flush_geometry(pvx_scene* sc);
+
+/* GenerateResponse + AnalyzeResponses for n listeners given as xyz triples (y ignored).
+ * results (n*gx*gy*8 floats) / delay (n*gx*gy floats) may be NULL to leave them on the device.
+ * Synchronous: returns when the host buffers are filled. */
+PVC_API int  pvx_solve(pvx_scene* sc, const float* listenersXYZ, int n, int analyze, float* results, float* delay);
+/* asynchronous halves for overlapped multi-device use */
+PVC_API int  pvx_solve_async(pvx_scene* sc, const float* listenersXYZ, int n, int analyze);
+PVC_API int  pvx_wait(pvx_scene* sc);
+
+/* Analyzer::GetResponseResult for a world-space emitter position: 0 = ok and out8 filled,
+ * PVC_ERR_INVALID when the reference would return nullptr (outside the grid) */
+PVC_API int  pvx_lookup(pvx_scene* sc, int source, float x, float y, float z, float* out8);
+/* Planeverb::GetImpulseResponse (FDTD.cpp:60-70): T x {p, vx, vy} of the cell containing the position */
+PVC_API int  pvx_impulse_response(pvx_scene* sc, int source, float x, float y, float z, float* out3T);
+
+PVC_API pvc_solver* pvx_solver(pvx_scene* sc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,304 @@
+// pvc_analyze.cu -- per-cell impulse-response analyzer on the device.
+//
+// Restates Analyzer::EncodeResponse (ProjectPlaneverb/src/DSP/Analyzer.cpp:139-328) and
+// Analyzer::EncodeListenerDirection (:340-431) over the pressure history the step kernels record
+// (one fp32 plane per sample instead of the reference's 16-byte Cell per sample per cell).
+//
+// One thread per interior cell.  Every sum runs in the reference's order in fp32 without
+// contraction, so the results equal the CPU reference's up to libm differences in log10f/powf:
+//   * causal part (onset, Edry, flux): ascending t from sample 0 (Analyzer.cpp:146-195).  The flux
+//     needs vx, vy of the cell, which are rebuilt on the fly from the cell's and its up/left
+//     neighbours' recorded pressures with the solver's own velocity rules (FDTD.cpp:144-223) -- an
+//     exact recurrence because a velocity only ever depends on its own previous value and on the
+//     recorded pressures;
+//   * wet energy: ascending t over its window (Analyzer.cpp:235-247);
+//   * RT60: backward Schroeder integral, descending t, with the running log10 and the two regression
+//     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
+// Adjacent threads read adjacent floats of each history plane (coalesced 128-byte lines).
+#include <float.h>
+#include "pvc_internal.h"
+
+namespace pvc
+{
+    __device__ __forceinline__ bool isAirA(float w) { return __float_as_uint(w) == kAirBits; }
+
+    constexpr float kAudibleThreshold = 0.00000316f;   // PvTypes.h:89
+    constexpr float kGainThreshold = 0.891251f;        // PvTypes.h:99
+    constexpr float kDelayClose = 5.f;                 // PvTypes.h:100
+    constexpr float kSpeedOfSoundA = 343.21f;          // PvTypes.h:85
+
+    struct AnalyzeParams
+    {
+        int T, fs;
+        int fluxSamples, drySamples, wetSamples, tailSamples;
+        float dx, courant, efree;
+        int resolution;
+    };
+
+    __global__ void __launch_bounds__(128)
+    encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
+                         const SourceParams* __restrict__ src, float* __restrict__ results,
+                         float* __restrict__ delay, float* __restrict__ walkDelay)
+    {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r = blockIdx.y;
+        const int s = blockIdx.z;
+        if (c >= L.gy) return;
+        const size_t cells = (size_t)L.gx * L.gy;
+        const size_t serial = (size_t)r * L.gx + c;              // INDEX_TO_POS, PvDefinitions.h:24
+        float* out = results + ((size_t)s * cells + serial) * 8;
+        const float* H = hist + (size_t)s * A.T * L.hist_plane + (size_t)r * L.hist_pitch + c;
+        const size_t hp = L.hist_plane;
+        const int T = A.T;
+
+        const size_t wi = cellIndex(L, r, c);
+        const float wSelf = w[wi];
+        if (!isAirA(wSelf))
+        {   // a wall cell's pressure is identically zero: no onset, results left untouched (Analyzer.cpp:161-165)
+            delay[(size_t)s * cells + serial] = FLT_MAX;
+            walkDelay[(size_t)s * cells + serial] = FLT_MAX;
+            return;
+        }
+        const float wUp = w[wi - L.pitch], wLeft = w[wi - 1];
+        const bool topEdge = (r == 0), leftEdge = (c == 0);
+        const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
+
+        // ---- causal pass: onset, Edry over [0, onset+D), flux over [0, onset+Sd) ----
+        int onset = -1;
+        float edry = 0.f, fx = 0.f, fy = 0.f, vx = 0.f, vy = 0.f;
+        int dryEnd = T, fluxEnd = T;
+        for (int t = 0; t < dryEnd; ++t)
+        {
+            const float p = H[(size_t)t * hp];
+            if (onset < 0 && fabsf(p) > kAudibleThreshold)
+            {
+                onset = t;
+                dryEnd = min(t + A.drySamples, T);
+                fluxEnd = min(t + A.fluxSamples, T);
+                if (t >= dryEnd) break;
+            }
+            if (t < fluxEnd)
+            {
+                if (topEdge) vx = -p;
+                else
+                {
+                    const float pu = H[(size_t)t * hp - L.hist_pitch];
+                    vx = upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, pu))) : -__fmul_rn(wUp, p);
+                }
+                if (leftEdge) vy = -p;
+                else
+                {
+                    const float pl = H[(size_t)t * hp - 1];
+                    vy = leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, pl))) : -__fmul_rn(wLeft, p);
+                }
+                fx = __fadd_rn(fx, __fmul_rn(p, vx));
+                fy = __fadd_rn(fy, __fmul_rn(p, vy));
+            }
+            edry = __fadd_rn(edry, __fmul_rn(p, p));
+        }
+        if (onset < 0)
+        {
+            delay[(size_t)s * cells + serial] = FLT_MAX;
+            walkDelay[(size_t)s * cells + serial] = FLT_MAX;
+            return;
+        }
+        const int directEnd = onset + A.drySamples;
+
+        // ---- obstruction gain and source directivity (Analyzer.cpp:199-220, FreeGrid.cpp:41-59) ----
+        const SourceParams sp = src[s];
+        float efreePr;
+        {
+            const float lX = __fmul_rn((float)sp.efree_r, A.dx), lY = __fmul_rn((float)sp.efree_c, A.dx);
+            const float eX = __fmul_rn((float)r, A.dx), eY = __fmul_rn((float)c, A.dx);
+            const float ddx = __fsub_rn(eX, lX), ddy = __fsub_rn(eY, lY);
+            const float rr = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+            efreePr = (rr == 0.f) ? A.efree : __fdiv_rn(A.efree, rr);
+        }
+        const float occ = __fsqrt_rn(__fdiv_rn(edry, efreePr));
+        float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+        norm = __fdiv_rn(-1.0f, (norm > 0.0f ? norm : 1.0f));
+        const float sdx = __fmul_rn(norm, fx), sdy = __fmul_rn(norm, fy);
+
+        // ---- low-pass cutoff (Analyzer.cpp:227-230); powf evaluated in double then rounded, which is
+        //      what a correctly rounded libm powf returns in all but vanishingly rare ties ----
+        const float rinv = __fdiv_rn(1.0f, fmaxf(0.001f, occ));
+        const float pw = (float)pow((double)__fdiv_rn(rinv, 12.f), (double)0.8f);
+        const float lowpass = __fadd_rn(-147.f, __fdiv_rn(18390.f, __fadd_rn(1.f, pw)));
+
+        // ---- wet gain over [directEnd+1, min(directEnd+1+W, T)) (Analyzer.cpp:235-247) ----
+        float wet = 0.f;
+        {
+            const int end = min(directEnd + 1 + A.wetSamples, T);
+            for (int j = directEnd + 1; j < end; ++j)
+            {
+                const float p = H[(size_t)j * hp];
+                wet = __fadd_rn(wet, __fmul_rn(p, p));
+            }
+        }
+        const float wetGain = __fsqrt_rn(__fdiv_rn(wet, A.efree));
+
+        // ---- RT60: backward Schroeder integration + closed-form regression (Analyzer.cpp:282-326) ----
+        const int start = directEnd + 1;
+        const int endPoint = T - A.tailSamples;
+        const int regressN = endPoint - start;
+        const float rn = (float)regressN;
+        const float xmean = __fmul_rn(__fsub_rn(rn, 1.0f), 0.5f);
+        const float xsum = __fmul_rn(rn, xmean);
+        const float denominator = __fmul_rn(__fmul_rn(1.0f / 12.0f, rn), __fsub_rn(__fmul_rn(rn, rn), 1.0f));
+        float edc = 0.f, xysum = 0.f, ysum = 0.f;
+        for (int i = T - 1; i >= endPoint && i >= 0; --i)
+        {
+            const float p = H[(size_t)i * hp];
+            edc = __fadd_rn(edc, __fmul_rn(p, p));
+        }
+        #pragma unroll 8
+        for (int i = endPoint - 1; i >= start; --i)
+        {
+            const float p = H[(size_t)i * hp];
+            edc = __fadd_rn(edc, __fmul_rn(p, p));
+            const float y = __fmul_rn(10.f, log10f(edc));
+            xysum = __fadd_rn(xysum, __fmul_rn(y, (float)(i - start)));
+            ysum = __fadd_rn(ysum, y);
+        }
+        const float ymean = __fdiv_rn(ysum, rn);
+        float numerator = __fsub_rn(xysum, __fmul_rn(ymean, xsum));
+        numerator = __fsub_rn(numerator, __fmul_rn(xmean, ysum));
+        numerator = __fadd_rn(numerator, __fmul_rn(__fmul_rn(rn, xmean), ymean));
+        const float slopePerSample = __fdiv_rn(numerator, denominator);
+        const float slopePerSec = __fmul_rn(slopePerSample, (float)A.fs);
+        const float rt60 = __fdiv_rn(-60.f, slopePerSec);
+
+        out[0] = occ; out[1] = wetGain; out[2] = rt60; out[3] = lowpass;
+        out[6] = sdx; out[7] = sdy;
+        delay[(size_t)s * cells + serial] = (float)onset;
+        walkDelay[(size_t)s * cells + serial] = (occ > 0.f) ? (float)onset : FLT_MAX;
+    }
+
+    // Analyzer.cpp:340-431.  walkDelay holds the onset of every cell a walk may step onto (has an onset
+    // and occlusion > 0, Analyzer.cpp:372-374) and FLT_MAX elsewhere.
+    __global__ void __launch_bounds__(128)
+    listenerDirectionKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src,
+                            float* __restrict__ results, const float* __restrict__ walkDelay)
+    {
+        const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r0 = blockIdx.y;
+        const int s = blockIdx.z;
+        if (c0 >= L.gy) return;
+        const int gx = L.gx, gy = L.gy;
+        const size_t cells = (size_t)gx * gy;
+        float* res = results + (size_t)s * cells * 8;
+        const float* wd = walkDelay + (size_t)s * cells;
+        const SourceParams sp = src[s];
+        const float samplingRate = (float)A.fs;
+        const float thresholdDist = __fmul_rn(0.3f, __fdiv_rn(kSpeedOfSoundA, (float)A.resolution));
+
+        int nextIndex = r0 * gx + c0;
+        float loudness = res[(size_t)nextIndex * 8];
+        float delay = FLT_MAX;
+        while (delay > kDelayClose && loudness < kGainThreshold)
+        {
+            const int r = nextIndex / gx, c = nextIndex % gx;
+            float nextDelay = FLT_MAX;
+            #pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+                const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+                const int nr = r + dr, nc = c + dc;
+                if (nr < 0 || nc < 0 || nr >= gx || nc >= gy) continue;
+                const int ni = nr * gx + nc;
+                const float d = wd[ni];
+                if (d < nextDelay) { nextIndex = ni; nextDelay = d; }
+            }
+            if (nextDelay == FLT_MAX || nextDelay >= delay) break;
+            delay = nextDelay;
+            loudness = res[(size_t)nextIndex * 8];
+            const float geodesic = __fdiv_rn(__fmul_rn(kSpeedOfSoundA, nextDelay), samplingRate);
+            const int r2 = nextIndex / gx, c2 = nextIndex % gx;
+            const float tx = __fsub_rn(__fmul_rn((float)r2, A.dx), sp.x);
+            const float ty = __fsub_rn(__fmul_rn((float)c2, A.dx), sp.z);
+            const float eu = __fsqrt_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
+            if (fabsf(__fsub_rn(geodesic, eu)) < thresholdDist) break;
+        }
+        const int r = nextIndex / gx, c = nextIndex % gx;
+        float ox = __fsub_rn(__fmul_rn((float)r, A.dx), sp.x);
+        float oy = __fsub_rn(__fmul_rn((float)c, A.dx), sp.z);
+        float len = __fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy));
+        if (len != 0.f)
+        {
+            len = __fsqrt_rn(len);
+            ox = __fdiv_rn(ox, len);
+            oy = __fdiv_rn(oy, len);
+        }
+        float* out = res + ((size_t)r0 * gx + c0) * 8;
+        out[4] = ox; out[5] = oy;
+    }
+
+    // Grid::GetResponse for one alloc cell: T x {p, vx, vy}, velocities rebuilt from the history
+    __global__ void rebuildIrKernel(Layout L, int T, float courant, const float* __restrict__ hist,
+                                    const float* __restrict__ w, int r, int c, float* __restrict__ out)
+    {
+        if (blockIdx.x != 0 || threadIdx.x != 0) return;
+        const float* H = hist + (size_t)r * L.hist_pitch + c;
+        const size_t wi = cellIndex(L, r, c);
+        const float wSelf = w[wi], wUp = w[wi - L.pitch], wLeft = w[wi - 1];
+        const bool aSelf = isAirA(wSelf), aUp = isAirA(wUp), aLeft = isAirA(wLeft);
+        float vx = 0.f, vy = 0.f;
+        for (int t = 0; t < T; ++t)
+        {
+            const float p = H[(size_t)t * L.hist_plane];
+            const float pu = (r > 0) ? H[(size_t)t * L.hist_plane - L.hist_pitch] : 0.f;
+            const float pl = (c > 0) ? H[(size_t)t * L.hist_plane - 1] : 0.f;
+            if (c >= L.gy) vx = 0.f;
+            else if (r == 0) vx = -p;
+            else if (r == L.gx) vx = pu;
+            else if (aSelf && aUp) vx = __fsub_rn(vx, __fmul_rn(courant, __fsub_rn(p, pu)));
+            else if (!aSelf && aUp) vx = __fmul_rn(wSelf, pu);
+            else if (aSelf && !aUp) vx = -__fmul_rn(wUp, p);
+            else vx = 0.f;
+            if (r >= L.gx) vy = 0.f;
+            else if (c == 0) vy = -p;
+            else if (c == L.gy) vy = pl;
+            else if (aSelf && aLeft) vy = __fsub_rn(vy, __fmul_rn(courant, __fsub_rn(p, pl)));
+            else if (!aSelf && aLeft) vy = __fmul_rn(wSelf, pl);
+            else if (aSelf && !aLeft) vy = -__fmul_rn(wLeft, p);
+            else vy = 0.f;
+            out[3 * t] = p; out[3 * t + 1] = vx; out[3 * t + 2] = vy;
+        }
+    }
+
+    static AnalyzeParams paramsOf(const pvc_solver* s)
+    {
+        AnalyzeParams A;
+        A.T = s->cfg.T; A.fs = s->cfg.fs;
+        A.fluxSamples = s->cfg.flux_samples; A.drySamples = s->cfg.dry_samples;
+        A.wetSamples = s->cfg.wet_samples; A.tailSamples = s->cfg.tail_samples;
+        A.dx = s->cfg.dx; A.courant = s->cfg.courant; A.efree = s->efree;
+        A.resolution = s->cfg.resolution;
+        return A;
+    }
+
+    int launchAnalyzer(pvc_solver* s, int nsrc, int* launches)
+    {
+        const Layout& L = s->L;
+        const AnalyzeParams A = paramsOf(s);
+        dim3 block(128, 1, 1);
+        dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
+        encodeResponseKernel<<<grid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay);
+        listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
+        *launches += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev)
+    {
+        const Layout& L = s->L;
+        const float* h = s->hist + (size_t)source * s->cfg.T * L.hist_plane;
+        rebuildIrKernel<<<1, 32, 0, s->stream>>>(L, s->cfg.T, s->cfg.courant, h, s->w, r, c, out_dev);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("ir rebuild launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+}

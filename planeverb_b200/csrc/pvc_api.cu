@@ -1,0 +1,460 @@
+// pvc_api.cu -- the C-ABI entry points declared in include/planeverb_cuda.h: device memory, the
+// coefficient-plane voxeliser, the free-field normaliser and the run/fetch calls.  No CPU fallback:
+// every entry point fails with PVC_ERR_NO_DEVICE / PVC_ERR_CUDA when the GPU is not usable.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <float.h>
+#include "pvc_internal.h"
+
+namespace pvc
+{
+    static thread_local char g_error[512] = "";
+
+    void setError(const char* fmt, ...)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_error, sizeof(g_error), fmt, ap);
+        va_end(ap);
+    }
+
+    #define PVC_CUDA(call)                                                                         \
+        do { cudaError_t e_ = (call);                                                               \
+             if (e_ != cudaSuccess) { setError("%s: %s", #call, cudaGetErrorString(e_));            \
+                                      return (e_ == cudaErrorMemoryAllocation) ? PVC_ERR_MEMORY : PVC_ERR_CUDA; } } while (0)
+
+    static int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+    static Layout makeLayout(const pvc_config& c)
+    {
+        Layout L;
+        L.gx = c.gx; L.gy = c.gy;
+        L.rows = c.gx + 1; L.cols = c.gy + 1;
+        L.tile_rows = fusedTileRows(c.reserved);
+        L.valid_rows = L.tile_rows - 2 * kTileK;
+        L.tiles_x = (L.cols + kValidCols - 1) / kValidCols;
+        L.tiles_y = (L.rows + L.valid_rows - 1) / L.valid_rows;
+        L.pitch = roundUp(L.tiles_x * kValidCols + 2 * kGuardCols, 32);
+        L.rows_alloc = L.tiles_y * L.valid_rows + 2 * kGuardRows;
+        if (L.rows_alloc < L.rows + kGuardRows + 1) L.rows_alloc = L.rows + kGuardRows + 1;
+        L.plane = (size_t)L.rows_alloc * L.pitch;
+        L.hist_pitch = roundUp(L.cols, 32);
+        L.hist_plane = (size_t)L.rows * L.hist_pitch;
+        return L;
+    }
+
+    static bool validConfig(const pvc_config* c)
+    {
+        return c && c->gx >= 2 && c->gy >= 2 && c->T >= 1 && c->fs > 0 && c->resolution > 0 && c->dx > 0.f &&
+               c->max_sources >= 1 && c->flux_samples >= 0 && c->dry_samples >= c->flux_samples &&
+               c->wet_samples >= 0 && c->tail_samples >= 0 && (c->step_kernel == 0 || c->step_kernel == 1);
+    }
+
+    // ---- geometry kernels: Grid ctor field init (Grid.cpp:84-108) and AddAABB/RemoveAABB (:229-296) ----
+    __global__ void clearGeometryKernel(Layout L, float* __restrict__ w)
+    {
+        const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= L.plane) return;
+        const int r = (int)(i / L.pitch) - kGuardRows, c = (int)(i % L.pitch) - kGuardCols;
+        float v;
+        if (r < 0 || c < 0 || r > L.gx || c > L.gy) v = 0.f;                 // guard band: inert wall, Y = 0
+        else if (r == L.gx || c == L.gy) v = 1.f;                            // padding row/col: b = 0, R = 0 -> Y = 1
+        else v = __uint_as_float(kAirBits);
+        w[i] = v;
+    }
+
+    // every alloc cell replays the ordered edit list and keeps the last edit covering it -- identical to
+    // applying the rectangles one after another (GeometryManager.cpp:130-143), in one launch
+    __global__ void applyRectsKernel(Layout L, float* __restrict__ w, const pvc_rect* __restrict__ rects, int n)
+    {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r = blockIdx.y * blockDim.y + threadIdx.y;
+        if (r > L.gx || c > L.gy) return;                                    // clip 0..gx / 0..gy inclusive (Grid.cpp:231,235)
+        const size_t i = cellIndex(L, r, c);
+        float v = w[i];
+        bool touched = false;
+        for (int k = 0; k < n; ++k)
+        {
+            const pvc_rect q = rects[k];
+            if (r >= q.r0 && r < q.r1 && c >= q.c0 && c < q.c1)
+            {
+                touched = true;
+                if (q.add) v = q.admittance;
+                else v = (r == L.gx || c == L.gy) ? 1.f : __uint_as_float(kAirBits);
+            }
+        }
+        if (touched) w[i] = v;
+    }
+
+    __global__ void fetchCoefKernel(Layout L, const float* __restrict__ w, short* __restrict__ b, float* __restrict__ y)
+    {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r = blockIdx.y;
+        if (c > L.gy) return;
+        const float v = w[cellIndex(L, r, c)];
+        const bool air = __float_as_uint(v) == kAirBits;
+        b[(size_t)r * L.cols + c] = air ? 1 : 0;
+        y[(size_t)r * L.cols + c] = air ? 1.f : v;       // air has R = 0 -> Y = 1 in the reference's terms
+    }
+
+    __global__ void gatherProbeKernel(const float* __restrict__ hist, size_t plane, size_t offset, int n, float* __restrict__ out)
+    {
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < n) out[t] = hist[(size_t)t * plane + offset];
+    }
+
+    __global__ void unpackPlaneKernel(Layout L, const float* __restrict__ plane, int guarded, float* __restrict__ out)
+    {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r = blockIdx.y;
+        if (c > L.gy) return;
+        out[(size_t)r * L.cols + c] = guarded ? plane[cellIndex(L, r, c)] : plane[(size_t)r * L.hist_pitch + c];
+    }
+
+    int launchClearGeometry(pvc_solver* s)
+    {
+        const Layout& L = s->L;
+        clearGeometryKernel<<<(unsigned)((L.plane + 255) / 256), 256, 0, s->stream>>>(L, s->w);
+        s->slowMaskDirty = 1;
+        PVC_CUDA(cudaGetLastError());
+        return PVC_OK;
+    }
+
+    int launchApplyRects(pvc_solver* s, const pvc_rect* rects_host, int n)
+    {
+        if (n <= 0) return PVC_OK;
+        const Layout& L = s->L;
+        pvc_rect* d = nullptr;
+        PVC_CUDA(cudaMallocAsync(&d, sizeof(pvc_rect) * n, s->stream));
+        PVC_CUDA(cudaMemcpyAsync(d, rects_host, sizeof(pvc_rect) * n, cudaMemcpyHostToDevice, s->stream));
+        dim3 block(32, 8), grid((L.cols + 31) / 32, (L.rows + 7) / 8);
+        applyRectsKernel<<<grid, block, 0, s->stream>>>(L, s->w, d, n);
+        PVC_CUDA(cudaGetLastError());
+        PVC_CUDA(cudaFreeAsync(d, s->stream));
+        PVC_CUDA(cudaStreamSynchronize(s->stream));      // rects_host may be a caller temporary
+        s->slowMaskDirty = 1;
+        return PVC_OK;
+    }
+
+    static int zeroState(pvc_solver* s, int nsrc)
+    {
+        for (int b = 0; b < 2; ++b)
+            for (int f = 0; f < 3; ++f)
+                PVC_CUDA(cudaMemsetAsync(s->state[b][f], 0, sizeof(float) * s->L.plane * nsrc, s->stream));
+        s->cur = 0;
+        return PVC_OK;
+    }
+
+    static int runSteps(pvc_solver* s, int nsrc, int T, int* launches)
+    {
+        if (s->cfg.step_kernel == 1) return launchBaselineSteps(s, nsrc, 0, T, s->hist, s->cfg.T, launches);
+        if (s->slowMaskDirty) { int rc = rebuildSlowMask(s); if (rc) return rc; }
+        return launchFusedSteps(s, nsrc, 0, T, s->hist, s->cfg.T, launches);
+    }
+}
+
+using namespace pvc;
+
+extern "C" {
+
+int pvc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* pvc_last_error(void) { return g_error; }
+
+size_t pvc_memory_requirement(const pvc_config* cfg)
+{
+    if (!validConfig(cfg)) return 0;
+    const Layout L = makeLayout(*cfg);
+    const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
+    return sizeof(float) * (6 * S * L.plane + L.plane + S * (size_t)cfg->T * L.hist_plane + (size_t)cfg->T +
+                            S * cells * 10 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
+}
+
+int pvc_create(const pvc_config* cfg, pvc_solver** out)
+{
+    if (!out) { setError("pvc_create: null out"); return PVC_ERR_INVALID; }
+    *out = nullptr;
+    if (!validConfig(cfg)) { setError("pvc_create: invalid config"); return PVC_ERR_INVALID; }
+    int ndev = pvc_device_count();
+    if (ndev <= 0) { setError("pvc_create: no CUDA device (this library has no CPU path)"); return PVC_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { setError("pvc_create: device %d of %d", cfg->device, ndev); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(cfg->device));
+
+    pvc_solver* s = new pvc_solver();
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->device = cfg->device;
+    s->L = makeLayout(*cfg);
+    const Layout& L = s->L;
+    const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
+    #define PVC_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                              \
+        setError("%s: %s", #call, cudaGetErrorString(e_)); pvc_destroy(s);                                     \
+        return (e_ == cudaErrorMemoryAllocation) ? PVC_ERR_MEMORY : PVC_ERR_CUDA; } } while (0)
+    PVC_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) PVC_TRY(cudaEventCreate(&s->ev[i]));
+    for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < 3; ++f)
+        {
+            PVC_TRY(cudaMalloc(&s->state[b][f], sizeof(float) * S * L.plane));
+            PVC_TRY(cudaMemsetAsync(s->state[b][f], 0, sizeof(float) * S * L.plane, s->stream));
+        }
+    PVC_TRY(cudaMalloc(&s->w, sizeof(float) * L.plane));
+    PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
+    PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * (size_t)cfg->T * L.hist_plane));
+    PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
+    PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
+    PVC_TRY(cudaMalloc(&s->results, sizeof(float) * S * cells * 8));
+    PVC_TRY(cudaMemsetAsync(s->results, 0, sizeof(float) * S * cells * 8, s->stream));
+    PVC_TRY(cudaMalloc(&s->delay, sizeof(float) * S * cells));
+    PVC_TRY(cudaMalloc(&s->walkDelay, sizeof(float) * S * cells));
+    PVC_TRY(cudaMalloc(&s->scratch, sizeof(float) * 3 * (size_t)cfg->T));
+    PVC_TRY(cudaMalloc(&s->src, sizeof(SourceParams) * S));
+    #undef PVC_TRY
+    s->efree = 1.f;
+    int rc = launchClearGeometry(s);
+    if (rc) { pvc_destroy(s); return rc; }
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) { setError("pvc_create: sync failed"); pvc_destroy(s); return PVC_ERR_CUDA; }
+    *out = s;
+    return PVC_OK;
+}
+
+void pvc_destroy(pvc_solver* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
+    cudaFree(s->w); cudaFree(s->slowMask); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
+    for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int pvc_set_pulse(pvc_solver* s, const float* pulse, int n)
+{
+    if (!s || !pulse || n < 0) { setError("pvc_set_pulse: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    if (n > s->cfg.T) n = s->cfg.T;
+    PVC_CUDA(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)s->cfg.T, s->stream));
+    PVC_CUDA(cudaMemcpyAsync(s->pulse, pulse, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+int pvc_clear_geometry(pvc_solver* s)
+{
+    if (!s) { setError("pvc_clear_geometry: null solver"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    return launchClearGeometry(s);
+}
+
+int pvc_apply_geometry(pvc_solver* s, const pvc_rect* rects, int n)
+{
+    if (!s || (n > 0 && !rects) || n < 0) { setError("pvc_apply_geometry: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    return launchApplyRects(s, rects, n);
+}
+
+int pvc_fetch_coefficients(pvc_solver* s, int16_t* b, float* admittance)
+{
+    if (!s || !b || !admittance) { setError("pvc_fetch_coefficients: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const Layout& L = s->L;
+    const size_t n = (size_t)L.rows * L.cols;
+    short* db = nullptr; float* dy = nullptr;
+    PVC_CUDA(cudaMalloc(&db, sizeof(short) * n));
+    PVC_CUDA(cudaMalloc(&dy, sizeof(float) * n));
+    fetchCoefKernel<<<dim3((L.cols + 127) / 128, L.rows), 128, 0, s->stream>>>(L, s->w, db, dy);
+    PVC_CUDA(cudaMemcpyAsync(b, db, sizeof(short) * n, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaMemcpyAsync(admittance, dy, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(db); cudaFree(dy);
+    return PVC_OK;
+}
+
+int pvc_set_efree(pvc_solver* s, float efree)
+{
+    if (!s) { setError("pvc_set_efree: null solver"); return PVC_ERR_INVALID; }
+    s->efree = efree;
+    return PVC_OK;
+}
+
+int pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, float r, float* efree)
+{
+    if (!s || n < 1 || n > s->cfg.T || lr < 0 || lc < 0 || lr > s->cfg.gx || lc > s->cfg.gy ||
+        er < 0 || ec < 0 || er > s->cfg.gx || ec > s->cfg.gy)
+    { setError("pvc_compute_efree: bad argument (n=%d, T=%d)", n, s ? s->cfg.T : -1); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const Layout& L = s->L;
+    // the free field is a second, empty coefficient plane (FreeGrid.cpp:11-18): swap it in for n steps
+    float* wScene = s->w;
+    float* wFree = nullptr;
+    PVC_CUDA(cudaMalloc(&wFree, sizeof(float) * L.plane));
+    s->w = wFree;
+    int rc = launchClearGeometry(s);
+    SourceParams sp{ lr, lc, lr, lc, 0.f, 0.f };
+    if (!rc && cudaMemcpyAsync(s->src, &sp, sizeof(sp), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) rc = PVC_ERR_CUDA;
+    if (!rc) rc = zeroState(s, 1);
+    int launches = 0;
+    if (!rc) rc = runSteps(s, 1, n, &launches);
+    std::vector<float> probe((size_t)n);
+    if (!rc)
+    {
+        gatherProbeKernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->hist, L.hist_plane, (size_t)er * L.hist_pitch + ec, n, s->scratch);
+        if (cudaMemcpyAsync(probe.data(), s->scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s->stream) != cudaSuccess)
+        { setError("pvc_compute_efree: %s", cudaGetErrorString(cudaGetLastError())); rc = PVC_ERR_CUDA; }
+    }
+    s->w = wScene;
+    s->slowMaskDirty = 1;
+    cudaFree(wFree);
+    if (rc) return rc;
+    // FreeGrid::CalculateEFree (FreeGrid.cpp:96-110): sequential fp32 sum of squares, then times r (:89-91)
+    volatile float e = 0.f;
+    for (int i = 0; i < n; ++i) { volatile float sq = probe[(size_t)i] * probe[(size_t)i]; e = e + sq; }
+    volatile float scaled = e * r;
+    s->efree = scaled;
+    if (efree) *efree = scaled;
+    return PVC_OK;
+}
+
+int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
+{
+    if (!s || !listeners || n < 1 || n > s->cfg.max_sources) { setError("pvc_run: bad argument (n=%d)", n); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    std::vector<SourceParams> sp((size_t)n);
+    for (int i = 0; i < n; ++i)
+    {
+        const pvc_listener& l = listeners[i];
+        if (l.cell_r < 0 || l.cell_c < 0 || l.cell_r > s->cfg.gx || l.cell_c > s->cfg.gy)
+        { setError("pvc_run: listener %d cell (%d,%d) outside the grid", i, l.cell_r, l.cell_c); return PVC_ERR_INVALID; }
+        sp[(size_t)i] = SourceParams{ l.cell_r, l.cell_c, l.efree_r, l.efree_c, l.x, l.z };
+    }
+    PVC_CUDA(cudaMemcpyAsync(s->src, sp.data(), sizeof(SourceParams) * n, cudaMemcpyHostToDevice, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));          // sp is a local
+    int launches = 0;
+    PVC_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    int rc = zeroState(s, n);
+    if (rc) return rc;
+    rc = runSteps(s, n, s->cfg.T, &launches);
+    if (rc) return rc;
+    PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    if (analyze) { rc = launchAnalyzer(s, n, &launches); if (rc) return rc; }
+    PVC_CUDA(cudaEventRecord(s->ev[2], s->stream));
+    s->lastSources = n;
+    s->lastLaunches = launches;
+    return PVC_OK;
+}
+
+int pvc_synchronize(pvc_solver* s)
+{
+    if (!s) { setError("pvc_synchronize: null solver"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+int pvc_clear_results(pvc_solver* s, int source)
+{
+    if (!s || source < 0 || source >= s->cfg.max_sources) { setError("pvc_clear_results: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
+    PVC_CUDA(cudaMemsetAsync(s->results + (size_t)source * cells * 8, 0, sizeof(float) * cells * 8, s->stream));
+    return PVC_OK;
+}
+
+int pvc_fetch_results(pvc_solver* s, int source, float* results, float* delay)
+{
+    if (!s || source < 0 || source >= s->cfg.max_sources) { setError("pvc_fetch_results: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
+    if (results) PVC_CUDA(cudaMemcpyAsync(results, s->results + (size_t)source * cells * 8, sizeof(float) * cells * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (delay) PVC_CUDA(cudaMemcpyAsync(delay, s->delay + (size_t)source * cells, sizeof(float) * cells, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+int pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8)
+{
+    if (!s || !out8 || source < 0 || source >= s->cfg.max_sources || r < 0 || c < 0 || r >= s->cfg.gx || c >= s->cfg.gy)
+    { setError("pvc_fetch_result_at: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
+    PVC_CUDA(cudaMemcpyAsync(out8, s->results + ((size_t)source * cells + (size_t)r * s->cfg.gx + c) * 8, sizeof(float) * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+int pvc_fetch_ir(pvc_solver* s, int source, int r, int c, float* out3T)
+{
+    if (!s || !out3T || source < 0 || source >= s->cfg.max_sources || r < 0 || c < 0 || r > s->cfg.gx || c > s->cfg.gy)
+    { setError("pvc_fetch_ir: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    int rc = launchIrRebuild(s, source, r, c, s->scratch);
+    if (rc) return rc;
+    PVC_CUDA(cudaMemcpyAsync(out3T, s->scratch, sizeof(float) * 3 * (size_t)s->cfg.T, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+static int fetchPlane(pvc_solver* s, const float* dev, int guarded, float* host)
+{
+    const Layout& L = s->L;
+    const size_t n = (size_t)L.rows * L.cols;
+    float* tmp = nullptr;
+    PVC_CUDA(cudaMalloc(&tmp, sizeof(float) * n));
+    unpackPlaneKernel<<<dim3((L.cols + 127) / 128, L.rows), 128, 0, s->stream>>>(L, dev, guarded, tmp);
+    PVC_CUDA(cudaMemcpyAsync(host, tmp, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(tmp);
+    return PVC_OK;
+}
+
+int pvc_fetch_pressure(pvc_solver* s, int source, int t, float* plane)
+{
+    if (!s || !plane || source < 0 || source >= s->cfg.max_sources || t < 0 || t >= s->cfg.T)
+    { setError("pvc_fetch_pressure: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    return fetchPlane(s, s->hist + ((size_t)source * s->cfg.T + t) * s->L.hist_plane, 0, plane);
+}
+
+int pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, float* vy)
+{
+    if (!s || source < 0 || source >= s->cfg.max_sources) { setError("pvc_fetch_state: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    float* host[3] = { p, vx, vy };
+    for (int f = 0; f < 3; ++f)
+        if (host[f]) { int rc = fetchPlane(s, s->state[s->cur][f] + (size_t)source * s->L.plane, 1, host[f]); if (rc) return rc; }
+    return PVC_OK;
+}
+
+int pvc_last_timing(pvc_solver* s, float* out3, int* launches)
+{
+    if (!s) { setError("pvc_last_timing: null solver"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaEventSynchronize(s->ev[2]));
+    float a = 0.f, b = 0.f;
+    PVC_CUDA(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+    PVC_CUDA(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+    if (out3) { out3[0] = a; out3[1] = b; out3[2] = a + b; }
+    if (launches) *launches = s->lastLaunches;
+    return PVC_OK;
+}
+
+const float* pvc_results_dev(pvc_solver* s, int source)
+{
+    if (!s || source < 0 || source >= s->cfg.max_sources) return nullptr;
+    return s->results + (size_t)source * s->cfg.gx * s->cfg.gy * 8;
+}
+
+void* pvc_stream(pvc_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+} // extern "C"

@@ -1,0 +1,100 @@
+// pvc_internal.h -- device data layout shared by the kernels of the thin CUDA layer.
+//
+// HBM layout (all fp32, one allocation per kind):
+//   state planes   p, vx, vy   [2 ping-pong][source][rows_alloc][pitch]
+//       Row r / column c of the reference's alloc grid (FDTD.cpp:99) lives at
+//       (r + kGuardRows) * pitch + (c + kGuardCols).  The guard band (kGuardRows rows above,
+//       kGuardCols columns to the left, tile overrun below/right) is zero and never written, so the
+//       temporally blocked step kernel loads whole tiles + halo without bounds checks.
+//   coefficient plane  w  [rows_alloc][pitch], shared by all sources:
+//       bit pattern kAirBits  -> air cell (reference b = 1)
+//       anything else         -> wall cell (b = 0) and the float is its admittance
+//                                Y = (1-R)/(1+R) (FDTD.cpp:153,160); guard cells are walls with Y = 0.
+//   pressure history   hist [source][T][hist_rows][hist_pitch]:  sample t of alloc cell (r, c) at
+//       t*hist_plane + r*hist_pitch + c -- the only per-step record kept (4 B per cell-step instead
+//       of the reference's 16-byte Cell, FDTD.cpp:226-231); vx/vy of any sample are rebuilt from it.
+//   results  [source][gx*gy][8], delay [source][gx*gy]   (Analyzer.h:13-21, Analyzer.cpp:40)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/planeverb_cuda.h"
+
+namespace pvc
+{
+    constexpr int kGuardRows = 4;          // = max temporal block depth K
+    constexpr int kGuardCols = 4;          // one float4
+    constexpr uint32_t kAirBits = 0xFFFFFFFFu;
+
+    // tile geometry of the fused step kernel (pvc_step_fused.cu)
+    constexpr int kTileK = 4;              // time steps per launch
+    constexpr int kTileCols = 128;         // one warp wide: 32 lanes x float4
+    constexpr int kValidCols = kTileCols - 2 * kGuardCols;   // 120 output columns per tile
+
+    struct Layout
+    {
+        int gx, gy;            // interior cells
+        int rows, cols;        // alloc grid: gx+1, gy+1
+        int pitch;             // floats per state row (multiple of 32)
+        int rows_alloc;        // state rows incl. guards
+        size_t plane;          // rows_alloc * pitch
+        int hist_pitch;        // floats per history row (multiple of 32)
+        size_t hist_plane;     // rows * hist_pitch
+        int tiles_x, tiles_y;  // fused-kernel tile grid
+        int tile_rows;         // rows per tile incl. halo (warps * rows per thread)
+        int valid_rows;        // tile_rows - 2*kTileK
+    };
+
+    __host__ __device__ inline size_t cellIndex(const Layout& L, int r, int c)
+    {
+        return (size_t)(r + kGuardRows) * L.pitch + (c + kGuardCols);
+    }
+
+    struct SourceParams       // one listener, device copy of pvc_listener plus derived indices
+    {
+        int cell_r, cell_c;
+        int efree_r, efree_c;
+        float x, z;
+    };
+}
+
+struct pvc_solver
+{
+    pvc_config cfg;
+    pvc::Layout L;
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev[4];
+
+    float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
+    float* w;                // coefficient plane
+    uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
+    int slowMaskDirty;
+    float* hist;             // max_sources * T * hist_plane
+    float* pulse;            // T floats
+    float* results;          // max_sources * gx*gy*8
+    float* delay;            // max_sources * gx*gy
+    float* walkDelay;        // max_sources * gx*gy   (delay of selectable cells, FLT_MAX otherwise)
+    float* scratch;          // small device scratch (IR fetch)
+    pvc::SourceParams* src;  // max_sources
+    float efree;
+    int cur;                 // ping-pong index holding the latest state
+    int lastSources;
+    float lastMs[3];
+    int lastLaunches;
+};
+
+namespace pvc
+{
+    // step kernels (pvc_step.cu / pvc_step_fused.cu)
+    int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches);
+    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches);
+    int rebuildSlowMask(pvc_solver* s);
+    int fusedTileRows(int variant);
+    // analyzer kernels (pvc_analyze.cu)
+    int launchAnalyzer(pvc_solver* s, int nsrc, int* launches);
+    int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev);
+    // geometry kernels (pvc_geometry.cu)
+    int launchClearGeometry(pvc_solver* s);
+    int launchApplyRects(pvc_solver* s, const pvc_rect* rects_host, int n);
+    void setError(const char* fmt, ...);
+}

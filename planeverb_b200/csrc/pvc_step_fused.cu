@@ -1,0 +1,338 @@
+// pvc_step_fused.cu -- the hot kernel: K = 4 full FDTD time steps per launch, state in registers.
+//
+// What it replaces: the per-time-step body of Grid::GenerateResponseCPU
+// (ProjectPlaneverb/src/FDTD/FDTD.cpp:122-235): pressure sweep, vx sweep, vy sweep, grid-edge
+// absorbing overrides, IR record, pulse injection -- three full-grid sweeps plus a 16-byte scatter per
+// cell per step on the CPU.  Here all of it is one launch per FOUR steps:
+//
+//   * A CTA owns a tile of (NW*R) rows x 128 columns of the alloc grid INCLUDING a 4-cell halo on
+//     every side; warp w owns R consecutive rows, lane l owns 4 consecutive columns (one float4), so a
+//     thread keeps p, vx, vy of R x 4 cells in registers for the whole launch (R*12 registers).
+//   * Loads/stores are 128-bit, 512 contiguous bytes per warp per row (guard band in the plane layout
+//     makes every tile load in-bounds, no predication).
+//   * Horizontal neighbours (vy of the cell to the right for the pressure update, p of the cell to the
+//     left for the vy update) come from the adjacent lane by warp shuffle; vertical neighbours are the
+//     thread's own registers except across warp boundaries, which exchange one row per sub-step through
+//     2 KB of shared memory.  Lanes 0/31 and the top/bottom 4 rows are halo: their values go stale by
+//     one cell per step, which is exactly the 4-cell halo budget, and are never stored.
+//   * Each of the 4 sub-steps streams the freshly updated pressure of the tile's owned cells to that
+//     sample's history plane (evict-first stores) -- the only per-step HBM traffic: 4 B per cell-step
+//     instead of the 28 B of a one-step-per-launch formulation (read+write p,vx,vy + coefficient).
+//   * Walls, the padding row/column and the grid-edge overrides take a general per-cell path; a
+//     per-(tile, warp) lane mask precomputed after every geometry edit tells a thread whether all its
+//     cells and their up/left neighbours are plain interior air, in which case it runs the branch-free
+//     11-flop update.  Both paths use explicit round-to-nearest mul/add/sub (never contracted to FMA),
+//     in the reference's operation order, so planes are bit-identical to the strict-fp32 CPU build.
+//
+// Roofline: with the state L2-resident between launches the kernel is bound by instruction issue and by
+// the history write stream to HBM; see DESIGN.md for the byte accounting.
+#include "pvc_internal.h"
+
+namespace pvc
+{
+    __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
+
+    __device__ __forceinline__ float ruleF(float v, float pThis, float pPrev, float wThis, float wPrev, float courant)
+    {
+        const bool aThis = isAirF(wThis), aPrev = isAirF(wPrev);
+        if (aThis && aPrev) return __fsub_rn(v, __fmul_rn(courant, __fsub_rn(pThis, pPrev)));
+        if (!aThis && aPrev) return __fmul_rn(wThis, pPrev);
+        if (aThis && !aPrev) return -__fmul_rn(wPrev, pThis);
+        return 0.f;
+    }
+
+    struct FusedArgs
+    {
+        const float* inP; const float* inVx; const float* inVy;
+        float* outP; float* outVx; float* outVy;
+        const float* w;
+        const uint32_t* slowMask;
+        float* hist;               // plane of sample t0 of source 0 (null: no record)
+        size_t histSourceStride;   // floats between sources in hist
+        const SourceParams* src;
+        const float* pulse;
+        int t0, nsteps;
+        float courant;
+    };
+
+    template <int NW, int R>
+    __global__ void __launch_bounds__(NW * 32, 1)
+    fusedStepKernel(const Layout L, const FusedArgs A)
+    {
+        __shared__ float4 sVxTop[NW][32];     // vx of each warp's first row (read by the warp above)
+        __shared__ float4 sPBot[NW][32];      // p of each warp's last row (read by the warp below)
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        const int tx = blockIdx.x, ty = blockIdx.y, s = blockIdx.z;
+        // domain coordinates of this thread's first cell (may be negative / beyond the grid: guard band)
+        const int rBase = ty * L.valid_rows - kTileK + wp * R;
+        const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+        const size_t planeOff = (size_t)s * L.plane;
+        const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
+
+        float p[R][4], vx[R][4], vy[R][4];
+        #pragma unroll
+        for (int j = 0; j < R; ++j)
+        {
+            const size_t o = planeOff + cell0 + (size_t)j * L.pitch;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(A.inP + o));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(A.inVx + o));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(A.inVy + o));
+            p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+            vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+            vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+        }
+
+        // warp-uniform on purpose: a warp with any general-path lane runs the general path for all lanes
+        // (it is a superset of the fast path), so the shuffles below never sit in divergent code
+        const bool slow = A.slowMask[((size_t)ty * L.tiles_x + tx) * 32 + wp] != 0u;
+        const float C = A.courant;
+
+        // owned (stored) part of the tile: not halo, inside the alloc grid
+        const bool ownCols = (lane >= 1) && (lane <= 30) && (cBase < L.cols);
+        bool ownRow[R];
+        #pragma unroll
+        for (int j = 0; j < R; ++j)
+        {
+            const int jt = wp * R + j;
+            ownRow[j] = ownCols && (jt >= kTileK) && (jt < NW * R - kTileK) && (rBase + j < L.rows);
+        }
+
+        // does this thread hold the pulse cell of its source?
+        const SourceParams sp = A.src[s];
+        const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
+        const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
+
+        // only dereferenced for owned rows/columns, where rBase + j >= 0 and cBase >= 0
+        float* histRow = nullptr;
+        if (A.hist) histRow = A.hist + (size_t)s * A.histSourceStride + ((ptrdiff_t)rBase * L.hist_pitch + cBase);
+
+        sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+        __syncthreads();
+
+        for (int step = 0; step < A.nsteps; ++step)
+        {
+            // ---------------- pressure sub-step (FDTD.cpp:125-141) ----------------
+            float4 vxBelow = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wp + 1 < NW) vxBelow = sVxTop[wp + 1][lane];
+            const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
+            if (!slow)
+            {
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                        p[j][k] = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                    }
+                }
+            }
+            else
+            {
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w + cell0 + (size_t)j * L.pitch));
+                    const float wa[4] = { w4.x, w4.y, w4.z, w4.w };
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                        p[j][k] = isAirF(wa[k]) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
+                    }
+                }
+            }
+            sPBot[wp][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+            __syncthreads();
+
+            // ---------------- velocity sub-steps + edge overrides (FDTD.cpp:144-223) ----------------
+            float4 pAbove = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (wp > 0) pAbove = sPBot[wp - 1][lane];
+            const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
+            if (!slow)
+            {
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                        vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
+                        vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                    }
+                }
+            }
+            else
+            {
+                // the row above / column left of the very first tile row / column lies outside the allocation
+                const bool haveUp = (rBase + kGuardRows) > 0, haveLeft = (cBase + kGuardCols) > 0;
+                float4 wPrevRow = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (haveUp) wPrevRow = __ldg(reinterpret_cast<const float4*>(A.w + cell0 - L.pitch));
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w + cell0 + (size_t)j * L.pitch));
+                    const float wLeft = haveLeft ? __ldg(A.w + cell0 + (size_t)j * L.pitch - 1) : 0.f;
+                    const float wa[5] = { wLeft, w4.x, w4.y, w4.z, w4.w };
+                    const float wu[4] = { wPrevRow.x, wPrevRow.y, wPrevRow.z, wPrevRow.w };
+                    const int r = rBase + j;
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const int cc = cBase + k;
+                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                        const float pt = p[j][k];
+                        float nx, ny;
+                        if (cc >= L.gy || cc < 0 || r < 0 || r > L.gx) nx = 0.f;
+                        else if (r == 0) nx = -pt;                              // FDTD.cpp:208
+                        else if (r == L.gx) nx = pu;                            // FDTD.cpp:209
+                        else nx = ruleF(vx[j][k], pt, pu, wa[k + 1], wu[k], C);
+                        if (r >= L.gx || r < 0 || cc < 0 || cc > L.gy) ny = 0.f;
+                        else if (cc == 0) ny = -pt;                             // FDTD.cpp:220
+                        else if (cc == L.gy) ny = pl;                           // FDTD.cpp:221
+                        else ny = ruleF(vy[j][k], pt, pl, wa[k + 1], wa[k], C);
+                        vx[j][k] = nx; vy[j][k] = ny;
+                    }
+                    wPrevRow = w4;
+                }
+            }
+
+            // ---------------- record sample t0+step (FDTD.cpp:226-231), then inject (FDTD.cpp:234) ----------------
+            if (histRow)
+            {
+                float* h = histRow + (size_t)step * L.hist_plane;
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if (ownRow[j])
+                        __stcs(reinterpret_cast<float4*>(h + (size_t)j * L.hist_pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+            }
+            if (hasSrc)
+            {
+                const float add = __ldg(A.pulse + A.t0 + step);
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (j == sj && k == sk) p[j][k] = __fadd_rn(p[j][k], add);
+            }
+            sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+            __syncthreads();
+        }
+
+        // ---------------- store the owned cells of the new state ----------------
+        #pragma unroll
+        for (int j = 0; j < R; ++j)
+        {
+            if (!ownRow[j]) continue;
+            const size_t o = planeOff + cell0 + (size_t)j * L.pitch;
+            *reinterpret_cast<float4*>(A.outP + o) = make_float4(p[j][0], p[j][1], p[j][2], p[j][3]);
+            *reinterpret_cast<float4*>(A.outVx + o) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
+            *reinterpret_cast<float4*>(A.outVy + o) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
+        }
+    }
+
+    // lane mask per (tile, warp): 1 = some cell of the thread, or an up/left neighbour of one, is not air.
+    // The step kernel only tests the word against zero (warp-uniform path choice).
+    template <int NW, int R>
+    __global__ void slowMaskKernel(const Layout L, const float* __restrict__ w, uint32_t* __restrict__ mask)
+    {
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        const int tx = blockIdx.x, ty = blockIdx.y;
+        const int rBase = ty * L.valid_rows - kTileK + wp * R;
+        const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+        bool slow = false;
+        for (int j = -1; j < R; ++j)
+            for (int k = -1; k < 4; ++k)
+            {
+                const int mr = rBase + j + kGuardRows, mc = cBase + k + kGuardCols;   // memory coordinates
+                if (mr < 0 || mc < 0) continue;          // above/left of the allocation: halo of a halo, value irrelevant
+                if (__float_as_uint(w[(size_t)mr * L.pitch + mc]) != kAirBits) slow = true;
+            }
+        const uint32_t m = __ballot_sync(0xffffffffu, slow);
+        if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = m;
+    }
+
+    struct Variant { int nw, r; };
+    static const Variant kVariants[] = { {12, 8}, {8, 8}, {16, 4}, {16, 8}, {8, 4} };
+    static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+    int fusedTileRows(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants) variant = 0;
+        return kVariants[variant].nw * kVariants[variant].r;
+    }
+
+    template <int NW, int R>
+    static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
+    {
+        const Layout& L = s->L;
+        dim3 grid(L.tiles_x, L.tiles_y, nsrc), block(NW * 32);
+        for (int t = t0; t < t1; t += kTileK)
+        {
+            FusedArgs A;
+            float** in = s->state[s->cur];
+            float** out = s->state[s->cur ^ 1];
+            A.inP = in[0]; A.inVx = in[1]; A.inVy = in[2];
+            A.outP = out[0]; A.outVx = out[1]; A.outVy = out[2];
+            A.w = s->w; A.slowMask = s->slowMask;
+            A.hist = hist ? hist + (size_t)t * L.hist_plane : nullptr;
+            A.histSourceStride = (size_t)T_hist * L.hist_plane;
+            A.src = s->src; A.pulse = s->pulse;
+            A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
+            A.courant = s->cfg.courant;
+            fusedStepKernel<NW, R><<<grid, block, 0, s->stream>>>(L, A);
+            s->cur ^= 1;
+            *launches += 1;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    template <int NW, int R>
+    static int maskVariant(pvc_solver* s)
+    {
+        const Layout& L = s->L;
+        slowMaskKernel<NW, R><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->slowMask);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("slow mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        s->slowMaskDirty = 0;
+        return PVC_OK;
+    }
+
+    #define PVC_DISPATCH(fn, ...)                                             \
+        switch (v) {                                                          \
+            case 1: return fn<8, 8>(__VA_ARGS__);                             \
+            case 2: return fn<16, 4>(__VA_ARGS__);                            \
+            case 3: return fn<16, 8>(__VA_ARGS__);                            \
+            case 4: return fn<8, 4>(__VA_ARGS__);                             \
+            default: return fn<12, 8>(__VA_ARGS__);                           \
+        }
+
+    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
+    {
+        int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
+        PVC_DISPATCH(launchVariant, s, nsrc, t0, t1, hist, T_hist, launches)
+    }
+
+    int rebuildSlowMask(pvc_solver* s)
+    {
+        int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
+        PVC_DISPATCH(maskVariant, s)
+    }
+}

@@ -1,0 +1,222 @@
+"""ctypes binding of planeverb_b200/lib/libplaneverb_b200.so -- the host-side mirror used by tests and
+bench.py.  It binds the C-ABI declared in include/planeverb_cuda.h (pvc_*) and include/planeverb_ext.h
+(pvx_*) and nothing else: no torch types cross the boundary, and there is NO CPU fallback -- if the
+library is missing or no CUDA device is usable, every constructor raises.
+
+`Scene` mirrors how a host program drives the reference's Grid / FreeGrid / Analyzer trio
+(ProjectPlaneverb/src/FDTD/Grid.cpp, FreeGrid.cpp, src/DSP/Analyzer.cpp): add_aabb / remove_aabb,
+generate+analyze for listener positions, per-emitter lookup.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libplaneverb_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PVC_OK, PVC_ERR_INVALID, PVC_ERR_MEMORY, PVC_ERR_CUDA, PVC_ERR_NO_DEVICE = range(5)
+_STATUS = {1: "invalid argument/config", 2: "device memory", 3: "CUDA error", 4: "no CUDA device"}
+
+# every symbol include/planeverb_cuda.h and include/planeverb_ext.h declare
+PVC_SYMBOLS = [
+    "pvc_device_count", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
+    "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
+    "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
+    "pvc_fetch_results", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
+    "pvc_last_timing", "pvc_results_dev", "pvc_stream",
+]
+PVX_SYMBOLS = [
+    "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
+    "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_lookup",
+    "pvx_impulse_response", "pvx_solver",
+]
+
+
+class PlaneverbCudaError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+
+
+_lib = None
+_f, _i, _vp = C.c_float, C.c_int, C.c_void_p
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlaneverbCudaError(
+                f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "planeverb_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.pvc_last_error.restype = C.c_char_p
+        L.pvc_memory_requirement.restype = C.c_size_t
+        L.pvc_results_dev.restype = _vp
+        L.pvc_stream.restype = _vp
+        L.pvx_solver.restype = _vp
+        L.pvx_create.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _vp]
+        L.pvx_destroy.argtypes = [_vp]
+        L.pvx_info.argtypes = [_vp, _vp, _vp]
+        L.pvx_pulse.argtypes = [_vp, _vp, _i]
+        L.pvx_add_aabb.argtypes = [_vp] + [_f] * 5
+        L.pvx_remove_aabb.argtypes = [_vp] + [_f] * 5
+        L.pvx_flush_geometry.argtypes = [_vp]
+        L.pvx_solve.argtypes = [_vp, _vp, _i, _i, _vp, _vp]
+        L.pvx_solve_async.argtypes = [_vp, _vp, _i, _i]
+        L.pvx_wait.argtypes = [_vp]
+        L.pvx_lookup.argtypes = [_vp, _i, _f, _f, _f, _vp]
+        L.pvx_impulse_response.argtypes = [_vp, _i, _f, _f, _f, _vp]
+        L.pvx_solver.argtypes = [_vp]
+        L.pvc_fetch_results.argtypes = [_vp, _i, _vp, _vp]
+        L.pvc_fetch_ir.argtypes = [_vp, _i, _i, _i, _vp]
+        L.pvc_fetch_pressure.argtypes = [_vp, _i, _i, _vp]
+        L.pvc_fetch_state.argtypes = [_vp, _i, _vp, _vp, _vp]
+        L.pvc_fetch_coefficients.argtypes = [_vp, _vp, _vp]
+        L.pvc_last_timing.argtypes = [_vp, _vp, _vp]
+        L.pvc_clear_results.argtypes = [_vp, _i]
+        L.pvc_synchronize.argtypes = [_vp]
+        _lib = L
+    return _lib
+
+
+def device_count():
+    return int(lib().pvc_device_count())
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().pvc_last_error().decode(errors="replace")
+        raise PlaneverbCudaError(f"{what}: {_STATUS.get(rc, rc)}" + (f" ({msg})" if msg else ""))
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+class Scene:
+    """Grid + FreeGrid + Analyzer on one B200 (batched listeners)."""
+
+    def __init__(self, size_x, size_y, resolution, T=0, efree=-1.0, max_sources=1, device=0,
+                 step_kernel=0, variant=0):
+        h = _vp()
+        _check(lib().pvx_create(size_x, size_y, int(resolution), int(T), float(efree), int(max_sources),
+                                int(device), int(step_kernel), int(variant), C.byref(h)), "pvx_create")
+        self._h = h
+        ii = np.zeros(10, np.int32)
+        ff = np.zeros(4, np.float32)
+        _check(lib().pvx_info(self._h, _p(ii), _p(ff)), "pvx_info")
+        (self.gx, self.gy, self.T, self.fs, self.Sd, self.D, self.W, self.tail, self.free_samples,
+         self.max_sources) = (int(v) for v in ii)
+        self.dx, self.dt, self.courant, self.efree = (np.float32(v) for v in ff)
+        self.resolution = int(resolution)
+        self._solver = lib().pvx_solver(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pvx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def pulse(self):
+        out = np.zeros(self.T, np.float32)
+        _check(lib().pvx_pulse(self._h, _p(out), self.T), "pvx_pulse")
+        return out
+
+    def add_aabb(self, px, py, w, h, absorption):
+        _check(lib().pvx_add_aabb(self._h, px, py, w, h, absorption), "pvx_add_aabb")
+
+    def remove_aabb(self, px, py, w, h, absorption=0.0):
+        _check(lib().pvx_remove_aabb(self._h, px, py, w, h, absorption), "pvx_remove_aabb")
+
+    def flush_geometry(self):
+        _check(lib().pvx_flush_geometry(self._h), "pvx_flush_geometry")
+
+    def coef(self):
+        self.flush_geometry()
+        n = (self.gx + 1) * (self.gy + 1)
+        b = np.zeros(n, np.int16)
+        y = np.zeros(n, np.float32)
+        _check(lib().pvc_fetch_coefficients(self._solver, _p(b), _p(y)), "pvc_fetch_coefficients")
+        shp = (self.gx + 1, self.gy + 1)
+        return b.reshape(shp), y.reshape(shp)
+
+    @staticmethod
+    def _listeners(listeners):
+        a = np.ascontiguousarray(np.asarray(listeners, np.float32).reshape(-1, 3))
+        return a, a.shape[0]
+
+    def solve(self, listeners, analyze=True, fetch=True):
+        """GenerateResponse + AnalyzeResponses for each listener (x, y, z). Returns (results, delay)
+        with shapes (n, gx*gy, 8) and (n, gx*gy) when fetch, else None."""
+        a, n = self._listeners(listeners)
+        cells = self.gx * self.gy
+        res = np.zeros((n, cells, 8), np.float32) if fetch else None
+        dly = np.zeros((n, cells), np.float32) if fetch else None
+        _check(lib().pvx_solve(self._h, _p(a), n, int(bool(analyze)), _p(res), _p(dly)), "pvx_solve")
+        return (res, dly) if fetch else None
+
+    def solve_async(self, listeners, analyze=True):
+        a, n = self._listeners(listeners)
+        _check(lib().pvx_solve_async(self._h, _p(a), n, int(bool(analyze))), "pvx_solve_async")
+
+    def wait(self):
+        _check(lib().pvx_wait(self._h), "pvx_wait")
+
+    def fetch_results(self, source=0):
+        cells = self.gx * self.gy
+        res = np.zeros((cells, 8), np.float32)
+        dly = np.zeros(cells, np.float32)
+        _check(lib().pvc_fetch_results(self._solver, int(source), _p(res), _p(dly)), "pvc_fetch_results")
+        return res, dly
+
+    def clear_results(self, source=0):
+        _check(lib().pvc_clear_results(self._solver, int(source)), "pvc_clear_results")
+
+    def lookup(self, pos, source=0):
+        out = np.zeros(8, np.float32)
+        rc = lib().pvx_lookup(self._h, int(source), float(pos[0]), float(pos[1]), float(pos[2]), _p(out))
+        if rc == PVC_ERR_INVALID:
+            return None
+        _check(rc, "pvx_lookup")
+        return out
+
+    def impulse_response(self, pos, source=0):
+        out = np.zeros((self.T, 3), np.float32)
+        _check(lib().pvx_impulse_response(self._h, int(source), float(pos[0]), float(pos[1]), float(pos[2]), _p(out)),
+               "pvx_impulse_response")
+        return out
+
+    def ir(self, r, c, source=0):
+        out = np.zeros((self.T, 3), np.float32)
+        _check(lib().pvc_fetch_ir(self._solver, int(source), int(r), int(c), _p(out)), "pvc_fetch_ir")
+        return out
+
+    def pressure(self, t, source=0):
+        out = np.zeros((self.gx + 1, self.gy + 1), np.float32)
+        _check(lib().pvc_fetch_pressure(self._solver, int(source), int(t), _p(out)), "pvc_fetch_pressure")
+        return out
+
+    def state(self, source=0):
+        shp = (self.gx + 1, self.gy + 1)
+        p, vx, vy = (np.zeros(shp, np.float32) for _ in range(3))
+        _check(lib().pvc_fetch_state(self._solver, int(source), _p(p), _p(vx), _p(vy)), "pvc_fetch_state")
+        return p, vx, vy
+
+    def timing(self):
+        """(step_ms, analyzer_ms, total_ms, kernel_launches) of the last solve, CUDA events on the solver stream."""
+        out = np.zeros(3, np.float32)
+        n = C.c_int()
+        _check(lib().pvc_last_timing(self._solver, _p(out), C.byref(n)), "pvc_last_timing")
+        return float(out[0]), float(out[1]), float(out[2]), int(n.value)

@@ -138,8 +138,15 @@ PVC_API int  pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, flo
 /* timing of the last pvc_run in milliseconds, measured with CUDA events on the solver's stream:
  * out[0] = step kernels, out[1] = analyzer kernels, out[2] = total; launches = kernels launched */
 PVC_API int  pvc_last_timing(pvc_solver* s, float* out3, int* launches);
+/* bracket any sequence of calls with two CUDA events on the solver's stream (which = 0 start, 1 stop);
+ * pvc_mark_elapsed waits for the stop event and returns the milliseconds between them */
+PVC_API int  pvc_mark(pvc_solver* s, int which);
+PVC_API int  pvc_mark_elapsed(pvc_solver* s, float* ms);
 /* device-resident raw pointers for zero-copy consumers (results_dev: gx*gy*8 floats of a source) */
 PVC_API const float* pvc_results_dev(pvc_solver* s, int source);
+/* page-locked host buffers for the result grids (plain malloc'd memory works too, just slower to copy) */
+PVC_API void* pvc_host_alloc(size_t bytes);
+PVC_API void  pvc_host_free(void* p);
 PVC_API void* pvc_stream(pvc_solver* s);
 
 #ifdef __cplusplus

@@ -59,6 +59,17 @@ PVC_API int  pvx_impulse_response(pvx_scene* sc, int source, float x, float y, f
 
 PVC_API pvc_solver* pvx_solver(pvx_scene* sc);
 
+/* ---- host-only helpers (no device needed): the index/scalar derivations the scene solver feeds the
+ * CUDA layer, exported so they can be checked against the reference on a machine without a GPU ---- */
+/* cfg is filled for (resolution, size, responseLength override); floats[2] = dt, FreeGrid probe radius;
+ * ints[5] = FreeGrid listener r,c, emitter r,c, sample count (FreeGrid.cpp:78-99) */
+PVC_API int  pvx_derive(int resolution, float sizeX, float sizeY, int responseLength, pvc_config* cfg, float* floats, int* ints);
+PVC_API int  pvx_derive_pulse(int resolution, int fs, float* out, int n);
+PVC_API int  pvx_derive_rect(int resolution, float posX, float posY, float width, float height, float absorption, int add, pvc_rect* out);
+PVC_API int  pvx_derive_listener(int resolution, float x, float z, pvc_listener* out);
+/* emitter cell of Analyzer::GetResponseResult; returns PVC_ERR_INVALID where the reference returns nullptr */
+PVC_API int  pvx_derive_emitter_cell(int resolution, float sizeX, float sizeY, float x, float z, int* rc);
+
 #ifdef __cplusplus
 }
 #endif

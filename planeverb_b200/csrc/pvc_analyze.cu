@@ -64,37 +64,49 @@ namespace pvc
         const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
 
         // ---- causal pass: onset, Edry over [0, onset+D), flux over [0, onset+Sd) ----
+        // Loads are issued kCausalBatch samples ahead of their use (3 per sample: the cell, the cell above and
+        // the cell to the left -- the last two are the neighbouring threads' lines, so they hit L1); reading a
+        // few samples past the end of the windows is harmless.
+        constexpr int kCausalBatch = 4;
         int onset = -1;
         float edry = 0.f, fx = 0.f, fy = 0.f, vx = 0.f, vy = 0.f;
         int dryEnd = T, fluxEnd = T;
-        for (int t = 0; t < dryEnd; ++t)
+        const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_pitch;
+        const ptrdiff_t leftOff = leftEdge ? 0 : -1;
+        for (int t0 = 0; t0 < dryEnd; t0 += kCausalBatch)
         {
-            const float p = H[(size_t)t * hp];
-            if (onset < 0 && fabsf(p) > kAudibleThreshold)
+            float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
+            #pragma unroll
+            for (int u = 0; u < kCausalBatch; ++u)
             {
-                onset = t;
-                dryEnd = min(t + A.drySamples, T);
-                fluxEnd = min(t + A.fluxSamples, T);
+                const int t = min(t0 + u, T - 1);
+                const float* q = H + (size_t)t * hp;
+                bp[u] = __ldg(q);
+                bu[u] = __ldg(q + upOff);
+                bl[u] = __ldg(q + leftOff);
+            }
+            #pragma unroll
+            for (int u = 0; u < kCausalBatch; ++u)
+            {
+                const int t = t0 + u;
                 if (t >= dryEnd) break;
-            }
-            if (t < fluxEnd)
-            {
-                if (topEdge) vx = -p;
-                else
+                const float p = bp[u];
+                if (onset < 0 && fabsf(p) > kAudibleThreshold)
                 {
-                    const float pu = H[(size_t)t * hp - L.hist_pitch];
-                    vx = upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, pu))) : -__fmul_rn(wUp, p);
+                    onset = t;
+                    dryEnd = min(t + A.drySamples, T);
+                    fluxEnd = min(t + A.fluxSamples, T);
+                    if (t >= dryEnd) break;
                 }
-                if (leftEdge) vy = -p;
-                else
+                if (t < fluxEnd)
                 {
-                    const float pl = H[(size_t)t * hp - 1];
-                    vy = leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, pl))) : -__fmul_rn(wLeft, p);
+                    vx = topEdge ? -p : (upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, bu[u]))) : -__fmul_rn(wUp, p));
+                    vy = leftEdge ? -p : (leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, bl[u]))) : -__fmul_rn(wLeft, p));
+                    fx = __fadd_rn(fx, __fmul_rn(p, vx));
+                    fy = __fadd_rn(fy, __fmul_rn(p, vy));
                 }
-                fx = __fadd_rn(fx, __fmul_rn(p, vx));
-                fy = __fadd_rn(fy, __fmul_rn(p, vy));
+                edry = __fadd_rn(edry, __fmul_rn(p, p));
             }
-            edry = __fadd_rn(edry, __fmul_rn(p, p));
         }
         if (onset < 0)
         {
@@ -129,9 +141,11 @@ namespace pvc
         float wet = 0.f;
         {
             const int end = min(directEnd + 1 + A.wetSamples, T);
-            for (int j = directEnd + 1; j < end; ++j)
+            const float* q = H + (size_t)(directEnd + 1) * hp;
+            #pragma unroll 4
+            for (int j = directEnd + 1; j < end; ++j, q += hp)
             {
-                const float p = H[(size_t)j * hp];
+                const float p = __ldg(q);
                 wet = __fadd_rn(wet, __fmul_rn(p, p));
             }
         }
@@ -146,19 +160,58 @@ namespace pvc
         const float xsum = __fmul_rn(rn, xmean);
         const float denominator = __fmul_rn(__fmul_rn(1.0f / 12.0f, rn), __fsub_rn(__fmul_rn(rn, rn), 1.0f));
         float edc = 0.f, xysum = 0.f, ysum = 0.f;
-        for (int i = T - 1; i >= endPoint && i >= 0; --i)
+        // Both backward loops walk one pointer down the history (no per-sample 64-bit index multiply) and
+        // keep kRtBatch independent streaming loads in flight per thread: with one 4-byte load outstanding
+        // per thread the pass is latency-bound at ~0.8 TB/s; batching lifts it towards the HBM roofline.
+        constexpr int kRtBatch = 8;
+        const ptrdiff_t hps = (ptrdiff_t)hp;
         {
-            const float p = H[(size_t)i * hp];
-            edc = __fadd_rn(edc, __fmul_rn(p, p));
+            int i = T - 1;
+            const int stop = max(endPoint, 0);
+            const float* q = H + (size_t)i * hp;
+            for (; i - (kRtBatch - 1) >= stop; i -= kRtBatch, q -= kRtBatch * hps)
+            {
+                float v[kRtBatch];
+                #pragma unroll
+                for (int u = 0; u < kRtBatch; ++u) v[u] = __ldcs(q - u * hps);
+                #pragma unroll
+                for (int u = 0; u < kRtBatch; ++u) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+            }
+            for (; i >= stop; --i, q -= hps)
+            {
+                const float p = __ldcs(q);
+                edc = __fadd_rn(edc, __fmul_rn(p, p));
+            }
         }
-        #pragma unroll 8
-        for (int i = endPoint - 1; i >= start; --i)
+        if (endPoint - 1 >= start)
         {
-            const float p = H[(size_t)i * hp];
-            edc = __fadd_rn(edc, __fmul_rn(p, p));
-            const float y = __fmul_rn(10.f, log10f(edc));
-            xysum = __fadd_rn(xysum, __fmul_rn(y, (float)(i - start)));
-            ysum = __fadd_rn(ysum, y);
+            int i = endPoint - 1;
+            float x = (float)(i - start);              // exact; decremented by 1.0f per sample (< 2^24)
+            const float* q = H + (size_t)i * hp;
+            for (; i - (kRtBatch - 1) >= start; i -= kRtBatch, q -= kRtBatch * hps)
+            {
+                float v[kRtBatch];
+                #pragma unroll
+                for (int u = 0; u < kRtBatch; ++u) v[u] = __ldcs(q - u * hps);
+                #pragma unroll
+                for (int u = 0; u < kRtBatch; ++u)
+                {
+                    edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+                    const float y = __fmul_rn(10.f, log10f(edc));
+                    xysum = __fadd_rn(xysum, __fmul_rn(y, x));
+                    ysum = __fadd_rn(ysum, y);
+                    x = __fsub_rn(x, 1.0f);
+                }
+            }
+            for (; i >= start; --i, q -= hps)
+            {
+                const float p = __ldcs(q);
+                edc = __fadd_rn(edc, __fmul_rn(p, p));
+                const float y = __fmul_rn(10.f, log10f(edc));
+                xysum = __fadd_rn(xysum, __fmul_rn(y, x));
+                ysum = __fadd_rn(ysum, y);
+                x = __fsub_rn(x, 1.0f);
+            }
         }
         const float ymean = __fdiv_rn(ysum, rn);
         float numerator = __fsub_rn(xysum, __fmul_rn(ymean, xsum));

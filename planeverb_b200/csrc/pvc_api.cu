@@ -199,6 +199,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
         return (e_ == cudaErrorMemoryAllocation) ? PVC_ERR_MEMORY : PVC_ERR_CUDA; } } while (0)
     PVC_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) PVC_TRY(cudaEventCreate(&s->ev[i]));
+    for (int i = 0; i < 2; ++i) PVC_TRY(cudaEventCreate(&s->mark[i]));
     for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f)
         {
@@ -234,6 +235,7 @@ void pvc_destroy(pvc_solver* s)
     cudaFree(s->w); cudaFree(s->slowMask); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 2; ++i) if (s->mark[i]) cudaEventDestroy(s->mark[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -449,11 +451,37 @@ int pvc_last_timing(pvc_solver* s, float* out3, int* launches)
     return PVC_OK;
 }
 
+int pvc_mark(pvc_solver* s, int which)
+{
+    if (!s || which < 0 || which > 1) { setError("pvc_mark: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaEventRecord(s->mark[which], s->stream));
+    return PVC_OK;
+}
+
+int pvc_mark_elapsed(pvc_solver* s, float* ms)
+{
+    if (!s || !ms) { setError("pvc_mark_elapsed: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaEventSynchronize(s->mark[1]));
+    PVC_CUDA(cudaEventElapsedTime(ms, s->mark[0], s->mark[1]));
+    return PVC_OK;
+}
+
 const float* pvc_results_dev(pvc_solver* s, int source)
 {
     if (!s || source < 0 || source >= s->cfg.max_sources) return nullptr;
     return s->results + (size_t)source * s->cfg.gx * s->cfg.gy * 8;
 }
+
+void* pvc_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { setError("pvc_host_alloc: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    return p;
+}
+
+void pvc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 void* pvc_stream(pvc_solver* s) { return s ? (void*)s->stream : nullptr; }
 

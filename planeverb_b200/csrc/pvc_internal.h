@@ -64,6 +64,7 @@ struct pvc_solver
     int device;
     cudaStream_t stream;
     cudaEvent_t ev[4];
+    cudaEvent_t mark[2];
 
     float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
     float* w;                // coefficient plane

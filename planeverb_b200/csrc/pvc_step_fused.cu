@@ -32,13 +32,17 @@ namespace pvc
 {
     __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
 
+    // general velocity rule (FDTD.cpp:149-168 in branch form), written as selects so the general path stays
+    // straight-line code
     __device__ __forceinline__ float ruleF(float v, float pThis, float pPrev, float wThis, float wPrev, float courant)
     {
         const bool aThis = isAirF(wThis), aPrev = isAirF(wPrev);
-        if (aThis && aPrev) return __fsub_rn(v, __fmul_rn(courant, __fsub_rn(pThis, pPrev)));
-        if (!aThis && aPrev) return __fmul_rn(wThis, pPrev);
-        if (aThis && !aPrev) return -__fmul_rn(wPrev, pThis);
-        return 0.f;
+        const float airAir = __fsub_rn(v, __fmul_rn(courant, __fsub_rn(pThis, pPrev)));
+        const float wallThis = __fmul_rn(wThis, pPrev);
+        const float wallPrev = -__fmul_rn(wPrev, pThis);
+        const float ifAirThis = aPrev ? airAir : wallPrev;
+        const float ifWallThis = aPrev ? wallThis : 0.f;
+        return aThis ? ifAirThis : ifWallThis;
     }
 
     struct FusedArgs
@@ -55,12 +59,13 @@ namespace pvc
         float courant;
     };
 
-    template <int NW, int R>
-    __global__ void __launch_bounds__(NW * 32, 1)
+    template <int NW, int R, int MINB>
+    __global__ void __launch_bounds__(NW * 32, MINB)
     fusedStepKernel(const Layout L, const FusedArgs A)
     {
-        __shared__ float4 sVxTop[NW][32];     // vx of each warp's first row (read by the warp above)
-        __shared__ float4 sPBot[NW][32];      // p of each warp's last row (read by the warp below)
+        // row NW of sVxTop and row 0 of sPBot stay zero: the tile's bottom / top neighbours (halo of the halo)
+        __shared__ float4 sVxTop[NW + 1][32];   // [w]   = vx of warp w's first row (read by warp w-1)
+        __shared__ float4 sPBot[NW + 1][32];    // [w+1] = p of warp w's last row  (read by warp w+1)
 
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
@@ -68,20 +73,24 @@ namespace pvc
         // domain coordinates of this thread's first cell (may be negative / beyond the grid: guard band)
         const int rBase = ty * L.valid_rows - kTileK + wp * R;
         const int cBase = tx * kValidCols - kGuardCols + lane * 4;
-        const size_t planeOff = (size_t)s * L.plane;
         const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
+        const size_t src0 = (size_t)s * L.plane + cell0;
 
         float p[R][4], vx[R][4], vy[R][4];
-        #pragma unroll
-        for (int j = 0; j < R; ++j)
         {
-            const size_t o = planeOff + cell0 + (size_t)j * L.pitch;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(A.inP + o));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(A.inVx + o));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(A.inVy + o));
-            p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
-            vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
-            vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            const float* gp = A.inP + src0;
+            const float* gx = A.inVx + src0;
+            const float* gy = A.inVy + src0;
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gp + (size_t)j * L.pitch));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(gx + (size_t)j * L.pitch));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(gy + (size_t)j * L.pitch));
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
         }
 
         // warp-uniform on purpose: a warp with any general-path lane runs the general path for all lanes
@@ -89,15 +98,12 @@ namespace pvc
         const bool slow = A.slowMask[((size_t)ty * L.tiles_x + tx) * 32 + wp] != 0u;
         const float C = A.courant;
 
-        // owned (stored) part of the tile: not halo, inside the alloc grid
-        const bool ownCols = (lane >= 1) && (lane <= 30) && (cBase < L.cols);
-        bool ownRow[R];
-        #pragma unroll
-        for (int j = 0; j < R; ++j)
-        {
-            const int jt = wp * R + j;
-            ownRow[j] = ownCols && (jt >= kTileK) && (jt < NW * R - kTileK) && (rBase + j < L.rows);
-        }
+        // owned (stored) rows of this thread: j in [jLo, jHi) -- not halo, inside the alloc grid; empty
+        // for the halo lanes 0 and 31 and for columns past the grid
+        int jLo = kTileK - wp * R, jHi = NW * R - kTileK - wp * R;
+        jLo = max(jLo, 0);
+        jHi = min(min(jHi, R), L.rows - rBase);
+        if (lane == 0 || lane == 31 || cBase >= L.cols) jHi = 0;
 
         // does this thread hold the pulse cell of its source?
         const SourceParams sp = A.src[s];
@@ -105,143 +111,165 @@ namespace pvc
         const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
 
         // only dereferenced for owned rows/columns, where rBase + j >= 0 and cBase >= 0
-        float* histRow = nullptr;
-        if (A.hist) histRow = A.hist + (size_t)s * A.histSourceStride + ((ptrdiff_t)rBase * L.hist_pitch + cBase);
+        float* hist = A.hist ? A.hist + (size_t)s * A.histSourceStride + ((ptrdiff_t)rBase * L.hist_pitch + cBase) : nullptr;
 
+        if (wp == 0)
+        {
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
         __syncthreads();
 
+        #pragma unroll 1
         for (int step = 0; step < A.nsteps; ++step)
         {
             // ---------------- pressure sub-step (FDTD.cpp:125-141) ----------------
-            float4 vxBelow = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (wp + 1 < NW) vxBelow = sVxTop[wp + 1][lane];
-            const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
-            if (!slow)
             {
-                #pragma unroll
-                for (int j = 0; j < R; ++j)
+                const float4 vxBelow = sVxTop[wp + 1][lane];
+                const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
+                if (!slow)
                 {
-                    const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
                     #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int j = 0; j < R; ++j)
                     {
-                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
-                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
-                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
-                        p[j][k] = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                        const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                            const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                            const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                            p[j][k] = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                        }
+                    }
+                }
+                else
+                {
+                    const float* wrow = A.w + cell0;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                    {
+                        const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)j * L.pitch));
+                        const float wa[4] = { w4.x, w4.y, w4.z, w4.w };
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                            const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                            const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                            p[j][k] = isAirF(wa[k]) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
+                        }
+                        asm volatile("" ::: "memory");      // keep the general path row-by-row: low register pressure
                     }
                 }
             }
-            else
-            {
-                #pragma unroll
-                for (int j = 0; j < R; ++j)
-                {
-                    const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w + cell0 + (size_t)j * L.pitch));
-                    const float wa[4] = { w4.x, w4.y, w4.z, w4.w };
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                    {
-                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
-                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
-                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
-                        p[j][k] = isAirF(wa[k]) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
-                    }
-                }
-            }
-            sPBot[wp][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+            sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
             __syncthreads();
 
             // ---------------- velocity sub-steps + edge overrides (FDTD.cpp:144-223) ----------------
-            float4 pAbove = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (wp > 0) pAbove = sPBot[wp - 1][lane];
-            const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
-            if (!slow)
             {
-                #pragma unroll
-                for (int j = 0; j < R; ++j)
+                const float4 pAbove = sPBot[wp][lane];
+                const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
+                if (!slow)
                 {
-                    const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
                     #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int j = 0; j < R; ++j)
                     {
-                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
-                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
-                        vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
-                        vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                        const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
+                            vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                        }
                     }
                 }
-            }
-            else
-            {
-                // the row above / column left of the very first tile row / column lies outside the allocation
-                const bool haveUp = (rBase + kGuardRows) > 0, haveLeft = (cBase + kGuardCols) > 0;
-                float4 wPrevRow = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (haveUp) wPrevRow = __ldg(reinterpret_cast<const float4*>(A.w + cell0 - L.pitch));
-                #pragma unroll
-                for (int j = 0; j < R; ++j)
+                else
                 {
-                    const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(A.w + cell0 + (size_t)j * L.pitch));
-                    const float wLeft = haveLeft ? __ldg(A.w + cell0 + (size_t)j * L.pitch - 1) : 0.f;
-                    const float wa[5] = { wLeft, w4.x, w4.y, w4.z, w4.w };
-                    const float wu[4] = { wPrevRow.x, wPrevRow.y, wPrevRow.z, wPrevRow.w };
-                    const int r = rBase + j;
+                    // the row above / column left of the very first tile row / column lies outside the allocation
+                    const bool haveUp = (rBase + kGuardRows) > 0, haveLeft = (cBase + kGuardCols) > 0;
+                    const float* wrow = A.w + cell0;
+                    float4 wPrevRow = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (haveUp) wPrevRow = __ldg(reinterpret_cast<const float4*>(wrow - L.pitch));
                     #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int j = 0; j < R; ++j)
                     {
-                        const int cc = cBase + k;
-                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
-                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
-                        const float pt = p[j][k];
-                        float nx, ny;
-                        if (cc >= L.gy || cc < 0 || r < 0 || r > L.gx) nx = 0.f;
-                        else if (r == 0) nx = -pt;                              // FDTD.cpp:208
-                        else if (r == L.gx) nx = pu;                            // FDTD.cpp:209
-                        else nx = ruleF(vx[j][k], pt, pu, wa[k + 1], wu[k], C);
-                        if (r >= L.gx || r < 0 || cc < 0 || cc > L.gy) ny = 0.f;
-                        else if (cc == 0) ny = -pt;                             // FDTD.cpp:220
-                        else if (cc == L.gy) ny = pl;                           // FDTD.cpp:221
-                        else ny = ruleF(vy[j][k], pt, pl, wa[k + 1], wa[k], C);
-                        vx[j][k] = nx; vy[j][k] = ny;
+                        const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)j * L.pitch));
+                        const float wLeft = haveLeft ? __ldg(wrow + (size_t)j * L.pitch - 1) : 0.f;
+                        const float wa[5] = { wLeft, w4.x, w4.y, w4.z, w4.w };
+                        const float wu[4] = { wPrevRow.x, wPrevRow.y, wPrevRow.z, wPrevRow.w };
+                        const int r = rBase + j;
+                        const bool rowDead = (r < 0) || (r > L.gx);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const int cc = cBase + k;
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            const float pt = p[j][k];
+                            float nx = ruleF(vx[j][k], pt, pu, wa[k + 1], wu[k], C);
+                            float ny = ruleF(vy[j][k], pt, pl, wa[k + 1], wa[k], C);
+                            if (r == 0) nx = -pt;                                   // FDTD.cpp:208
+                            if (r == L.gx) nx = pu;                                 // FDTD.cpp:209
+                            if (cc == 0) ny = -pt;                                  // FDTD.cpp:220
+                            if (cc == L.gy) ny = pl;                                // FDTD.cpp:221
+                            if (rowDead || cc < 0 || cc >= L.gy) nx = 0.f;          // padding column / guard band
+                            if (rowDead || r == L.gx || cc < 0 || cc > L.gy) ny = 0.f;   // padding row / guard band
+                            vx[j][k] = nx; vy[j][k] = ny;
+                        }
+                        wPrevRow = w4;
+                        asm volatile("" ::: "memory");
                     }
-                    wPrevRow = w4;
                 }
             }
 
             // ---------------- record sample t0+step (FDTD.cpp:226-231), then inject (FDTD.cpp:234) ----------------
-            if (histRow)
+            if (hist)
             {
-                float* h = histRow + (size_t)step * L.hist_plane;
                 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    if (ownRow[j])
-                        __stcs(reinterpret_cast<float4*>(h + (size_t)j * L.hist_pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                    if (j >= jLo && j < jHi)
+                        __stcs(reinterpret_cast<float4*>(hist + (size_t)j * L.hist_pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                hist += L.hist_plane;
             }
             if (hasSrc)
             {
+                // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
                 const float add = __ldg(A.pulse + A.t0 + step);
+                const float a0 = (sk == 0) ? add : 0.f, a1 = (sk == 1) ? add : 0.f;
+                const float a2 = (sk == 2) ? add : 0.f, a3 = (sk == 3) ? add : 0.f;
                 #pragma unroll
                 for (int j = 0; j < R; ++j)
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (j == sj && k == sk) p[j][k] = __fadd_rn(p[j][k], add);
+                    if (j == sj)
+                    {
+                        p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
+                        p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
+                    }
             }
             sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
             __syncthreads();
         }
 
         // ---------------- store the owned cells of the new state ----------------
-        #pragma unroll
-        for (int j = 0; j < R; ++j)
         {
-            if (!ownRow[j]) continue;
-            const size_t o = planeOff + cell0 + (size_t)j * L.pitch;
-            *reinterpret_cast<float4*>(A.outP + o) = make_float4(p[j][0], p[j][1], p[j][2], p[j][3]);
-            *reinterpret_cast<float4*>(A.outVx + o) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
-            *reinterpret_cast<float4*>(A.outVy + o) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
+            float* gp = A.outP + src0;
+            float* gx = A.outVx + src0;
+            float* gy = A.outVy + src0;
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                if (j >= jLo && j < jHi)
+                {
+                    *reinterpret_cast<float4*>(gp + (size_t)j * L.pitch) = make_float4(p[j][0], p[j][1], p[j][2], p[j][3]);
+                    *reinterpret_cast<float4*>(gx + (size_t)j * L.pitch) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
+                    *reinterpret_cast<float4*>(gy + (size_t)j * L.pitch) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
+                }
+            }
         }
     }
 
@@ -267,8 +295,8 @@ namespace pvc
         if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = m;
     }
 
-    struct Variant { int nw, r; };
-    static const Variant kVariants[] = { {12, 8}, {8, 8}, {16, 4}, {16, 8}, {8, 4} };
+    struct Variant { int nw, r, minBlocks; };
+    static const Variant kVariants[] = { {12, 8, 1}, {8, 8, 2}, {16, 4, 2}, {16, 8, 1}, {8, 4, 4}, {8, 8, 1}, {16, 4, 1} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -277,7 +305,7 @@ namespace pvc
         return kVariants[variant].nw * kVariants[variant].r;
     }
 
-    template <int NW, int R>
+    template <int NW, int R, int MINB>
     static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
     {
         const Layout& L = s->L;
@@ -295,7 +323,7 @@ namespace pvc
             A.src = s->src; A.pulse = s->pulse;
             A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
             A.courant = s->cfg.courant;
-            fusedStepKernel<NW, R><<<grid, block, 0, s->stream>>>(L, A);
+            fusedStepKernel<NW, R, MINB><<<grid, block, 0, s->stream>>>(L, A);
             s->cur ^= 1;
             *launches += 1;
         }
@@ -304,7 +332,7 @@ namespace pvc
         return PVC_OK;
     }
 
-    template <int NW, int R>
+    template <int NW, int R, int MINB>
     static int maskVariant(pvc_solver* s)
     {
         const Layout& L = s->L;
@@ -317,11 +345,13 @@ namespace pvc
 
     #define PVC_DISPATCH(fn, ...)                                             \
         switch (v) {                                                          \
-            case 1: return fn<8, 8>(__VA_ARGS__);                             \
-            case 2: return fn<16, 4>(__VA_ARGS__);                            \
-            case 3: return fn<16, 8>(__VA_ARGS__);                            \
-            case 4: return fn<8, 4>(__VA_ARGS__);                             \
-            default: return fn<12, 8>(__VA_ARGS__);                           \
+            case 1: return fn<8, 8, 2>(__VA_ARGS__);                          \
+            case 2: return fn<16, 4, 2>(__VA_ARGS__);                         \
+            case 3: return fn<16, 8, 1>(__VA_ARGS__);                         \
+            case 4: return fn<8, 4, 4>(__VA_ARGS__);                          \
+            case 5: return fn<8, 8, 1>(__VA_ARGS__);                          \
+            case 6: return fn<16, 4, 1>(__VA_ARGS__);                         \
+            default: return fn<12, 8, 1>(__VA_ARGS__);                        \
         }
 
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)

@@ -167,4 +167,46 @@ int pvx_impulse_response(pvx_scene* sc, int source, float x, float y, float z, f
 
 pvc_solver* pvx_solver(pvx_scene* sc) { return sc ? sc->solver : nullptr; }
 
+int pvx_derive(int resolution, float sizeX, float sizeY, int responseLength, pvc_config* cfg, float* floats, int* ints)
+{
+    if (resolution <= 0 || !cfg) return PVC_ERR_INVALID;
+    const pvhost::GridParams g = pvhost::derive(resolution, sizeX, sizeY, responseLength);
+    *cfg = pvhost::configFor(g, 1, 0);
+    if (floats) { floats[0] = g.dt; floats[1] = g.freeRadius; }
+    if (ints) { ints[0] = g.freeListenerR; ints[1] = g.freeListenerC; ints[2] = g.freeEmitterR; ints[3] = g.freeEmitterC; ints[4] = g.freeSamples; }
+    return PVC_OK;
+}
+
+int pvx_derive_pulse(int resolution, int fs, float* out, int n)
+{
+    if (resolution <= 0 || fs <= 0 || !out || n < 0) return PVC_ERR_INVALID;
+    std::vector<float> v;
+    pvhost::gaussianPulse(resolution, (unsigned)fs, v, n);
+    std::memcpy(out, v.data(), sizeof(float) * (size_t)n);
+    return PVC_OK;
+}
+
+int pvx_derive_rect(int resolution, float posX, float posY, float width, float height, float absorption, int add, pvc_rect* out)
+{
+    if (resolution <= 0 || !out) return PVC_ERR_INVALID;
+    const pvhost::GridParams g = pvhost::derive(resolution, 1.f, 1.f);
+    *out = pvhost::rectFor(g, posX, posY, width, height, absorption, add != 0);
+    return PVC_OK;
+}
+
+int pvx_derive_listener(int resolution, float x, float z, pvc_listener* out)
+{
+    if (resolution <= 0 || !out) return PVC_ERR_INVALID;
+    const pvhost::GridParams g = pvhost::derive(resolution, 1.f, 1.f);
+    *out = pvhost::listenerFor(g, x, z);
+    return PVC_OK;
+}
+
+int pvx_derive_emitter_cell(int resolution, float sizeX, float sizeY, float x, float z, int* rc)
+{
+    if (resolution <= 0 || !rc) return PVC_ERR_INVALID;
+    const pvhost::GridParams g = pvhost::derive(resolution, sizeX, sizeY);
+    return pvhost::emitterCell(g, x, z, rc[0], rc[1]) ? PVC_OK : PVC_ERR_INVALID;
+}
+
 } // extern "C"

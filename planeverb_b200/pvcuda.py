@@ -26,13 +26,32 @@ PVC_SYMBOLS = [
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
-    "pvc_last_timing", "pvc_results_dev", "pvc_stream",
+    "pvc_last_timing", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
+    "pvc_mark", "pvc_mark_elapsed",
 ]
 PVX_SYMBOLS = [
     "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
     "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_lookup",
     "pvx_impulse_response", "pvx_solver",
+    "pvx_derive", "pvx_derive_pulse", "pvx_derive_rect", "pvx_derive_listener", "pvx_derive_emitter_cell",
 ]
+
+
+class PvcConfig(C.Structure):
+    _fields_ = [("gx", C.c_int), ("gy", C.c_int), ("T", C.c_int), ("fs", C.c_int), ("resolution", C.c_int),
+                ("dx", C.c_float), ("courant", C.c_float), ("flux_samples", C.c_int), ("dry_samples", C.c_int),
+                ("wet_samples", C.c_int), ("tail_samples", C.c_int), ("max_sources", C.c_int), ("device", C.c_int),
+                ("step_kernel", C.c_int), ("reserved", C.c_int)]
+
+
+class PvcRect(C.Structure):
+    _fields_ = [("r0", C.c_int), ("r1", C.c_int), ("c0", C.c_int), ("c1", C.c_int), ("add", C.c_int),
+                ("admittance", C.c_float)]
+
+
+class PvcListener(C.Structure):
+    _fields_ = [("cell_r", C.c_int), ("cell_c", C.c_int), ("efree_r", C.c_int), ("efree_c", C.c_int),
+                ("x", C.c_float), ("z", C.c_float)]
 
 
 class PlaneverbCudaError(RuntimeError):
@@ -64,6 +83,9 @@ def lib():
         L.pvc_results_dev.restype = _vp
         L.pvc_stream.restype = _vp
         L.pvx_solver.restype = _vp
+        L.pvc_host_alloc.restype = _vp
+        L.pvc_host_alloc.argtypes = [C.c_size_t]
+        L.pvc_host_free.argtypes = [_vp]
         L.pvx_create.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _vp]
         L.pvx_destroy.argtypes = [_vp]
         L.pvx_info.argtypes = [_vp, _vp, _vp]
@@ -85,8 +107,45 @@ def lib():
         L.pvc_last_timing.argtypes = [_vp, _vp, _vp]
         L.pvc_clear_results.argtypes = [_vp, _i]
         L.pvc_synchronize.argtypes = [_vp]
+        L.pvc_mark.argtypes = [_vp, _i]
+        L.pvc_mark_elapsed.argtypes = [_vp, _vp]
+        L.pvc_clear_geometry.argtypes = [_vp]
         _lib = L
     return _lib
+
+
+def derive(resolution, size_x, size_y, T=0):
+    """Host-side derivation (no GPU needed): returns (PvcConfig, dt, free_radius, free_ints[5])."""
+    cfg = PvcConfig()
+    ff = np.zeros(2, np.float32)
+    ii = np.zeros(5, np.int32)
+    _check(lib().pvx_derive(int(resolution), C.c_float(size_x), C.c_float(size_y), int(T), C.byref(cfg), _p(ff), _p(ii)), "pvx_derive")
+    return cfg, np.float32(ff[0]), np.float32(ff[1]), [int(v) for v in ii]
+
+
+def derive_pulse(resolution, fs, n):
+    out = np.zeros(n, np.float32)
+    _check(lib().pvx_derive_pulse(int(resolution), int(fs), _p(out), int(n)), "pvx_derive_pulse")
+    return out
+
+
+def derive_rect(resolution, px, py, w, h, absorption, add=True):
+    r = PvcRect()
+    _check(lib().pvx_derive_rect(int(resolution), C.c_float(px), C.c_float(py), C.c_float(w), C.c_float(h),
+                                 C.c_float(absorption), int(add), C.byref(r)), "pvx_derive_rect")
+    return r
+
+
+def derive_listener(resolution, x, z):
+    l = PvcListener()
+    _check(lib().pvx_derive_listener(int(resolution), C.c_float(x), C.c_float(z), C.byref(l)), "pvx_derive_listener")
+    return l
+
+
+def derive_emitter_cell(resolution, size_x, size_y, x, z):
+    rc = np.zeros(2, np.int32)
+    code = lib().pvx_derive_emitter_cell(int(resolution), C.c_float(size_x), C.c_float(size_y), C.c_float(x), C.c_float(z), _p(rc))
+    return None if code else (int(rc[0]), int(rc[1]))
 
 
 def device_count():
@@ -101,6 +160,30 @@ def _check(rc, what):
 
 def _p(a):
     return a.ctypes.data_as(_vp) if a is not None else None
+
+
+def pinned_array(shape, dtype=np.float32):
+    """numpy array over page-locked host memory (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = lib().pvc_host_alloc(n * dtype.itemsize)
+    if not ptr:
+        _check(PVC_ERR_MEMORY, "pvc_host_alloc")
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[id(buf)] = (buf, ptr)
+    import weakref
+    weakref.finalize(arr, _free_pinned, id(buf))
+    return arr
+
+
+_PINNED = {}
+
+
+def _free_pinned(key):
+    ent = _PINNED.pop(key, None)
+    if ent is not None and _lib is not None:
+        _lib.pvc_host_free(ent[1])
 
 
 class Scene:
@@ -157,13 +240,19 @@ class Scene:
         a = np.ascontiguousarray(np.asarray(listeners, np.float32).reshape(-1, 3))
         return a, a.shape[0]
 
-    def solve(self, listeners, analyze=True, fetch=True):
+    def solve(self, listeners, analyze=True, fetch=True, out=None):
         """GenerateResponse + AnalyzeResponses for each listener (x, y, z). Returns (results, delay)
-        with shapes (n, gx*gy, 8) and (n, gx*gy) when fetch, else None."""
+        with shapes (n, gx*gy, 8) and (n, gx*gy) when fetch, else None. out = (results, delay) host
+        buffers to fill (e.g. pinned_array) instead of fresh ones."""
         a, n = self._listeners(listeners)
         cells = self.gx * self.gy
-        res = np.zeros((n, cells, 8), np.float32) if fetch else None
-        dly = np.zeros((n, cells), np.float32) if fetch else None
+        if out is not None:
+            res, dly = out
+            assert res.shape == (n, cells, 8) and dly.shape == (n, cells)
+            fetch = True
+        else:
+            res = np.zeros((n, cells, 8), np.float32) if fetch else None
+            dly = np.zeros((n, cells), np.float32) if fetch else None
         _check(lib().pvx_solve(self._h, _p(a), n, int(bool(analyze)), _p(res), _p(dly)), "pvx_solve")
         return (res, dly) if fetch else None
 
@@ -213,6 +302,17 @@ class Scene:
         p, vx, vy = (np.zeros(shp, np.float32) for _ in range(3))
         _check(lib().pvc_fetch_state(self._solver, int(source), _p(p), _p(vx), _p(vy)), "pvc_fetch_state")
         return p, vx, vy
+
+    def clear_geometry(self):
+        _check(lib().pvc_clear_geometry(self._solver), "pvc_clear_geometry")
+
+    def mark(self, which):
+        _check(lib().pvc_mark(self._solver, int(which)), "pvc_mark")
+
+    def mark_elapsed_ms(self):
+        ms = C.c_float()
+        _check(lib().pvc_mark_elapsed(self._solver, C.byref(ms)), "pvc_mark_elapsed")
+        return float(ms.value)
 
     def timing(self):
         """(step_ms, analyzer_ms, total_ms, kernel_launches) of the last solve, CUDA events on the solver stream."""

@@ -78,3 +78,23 @@ def compare_results(got, got_delay, ref, ref_delay, exclude=None, rtol=RTOL, dir
         report[name] = float(e.max()) if e.size else 0.0
         assert report[name] <= tol, f"{name}: max error {report[name]:.3e} > {tol:.1e} ({int((e > tol).sum())} cells)"
     return report
+
+
+GOLDEN_CASES = ["smallroom_70", "bigroom_70", "shoebox_70", "hugeroom_70", "floorplan_70",
+                "singlewall_95_res375", "middlewall_127_res500", "smallroom_128_T500",
+                "directiontester_101_T300"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return meta, z
+
+
+def golden_boxes(z):
+    return [tuple(float(v) for v in row) for row in z["boxes"]]
+
+
+def reference_clamped(meta, delay, D):
+    """cells whose dry window runs past the IR (the reference reads out of bounds there)"""
+    return (delay < 3e38) & (delay + D >= meta["T"])

@@ -14,7 +14,7 @@
 //   * wet energy: ascending t over its window (Analyzer.cpp:235-247);
 //   * RT60: backward Schroeder integral, descending t, with the running log10 and the two regression
 //     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
-// Adjacent threads read adjacent floats of each history plane (coalesced 128-byte lines).
+// A block is the 128 cells of one history strip: its 4 warps walk one contiguous 512-byte-per-sample stream.
 #include <float.h>
 #include "pvc_internal.h"
 
@@ -26,6 +26,77 @@ namespace pvc
     constexpr float kGainThreshold = 0.891251f;        // PvTypes.h:99
     constexpr float kDelayClose = 5.f;                 // PvTypes.h:100
     constexpr float kSpeedOfSoundA = 343.21f;          // PvTypes.h:85
+
+    // ---- log10f exactly as the reference's libm computes it -------------------------------------------------
+    // RT60 is a regression over y_i = 10*log10f(E_i) accumulated in fp32 (Analyzer.cpp:309-319); with few
+    // regression points a 1-ulp difference in y_i moves RT60 by more than 1e-4, so the device reproduces the
+    // libm the oracle links (glibc 2.39, x86-64) bit for bit instead of calling CUDA's log10f (<= 2 ulp):
+    //   log10f(x) = (k*log10_2lo + ivln10*logf(m)) + k*log10_2hi   with x = m*2^k, m in [~0.7, 1.4)   (fdlibm e_log10f)
+    //   logf(m)   = the table-driven double-precision kernel of glibc's e_logf.c (16-entry {1/c, log c} table,
+    //               degree-3 polynomial in r = m/c - 1), rounded once to float.
+    // tests/test_oracle.py::test_device_log10f_recipe_matches_libm checks this recipe against libm on the CPU.
+    struct LogfEntry { double invc, logc; };
+    __device__ const LogfEntry kLogfTable[16] = {
+        { 0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2 }, { 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2 },
+        { 0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2 }, { 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3 },
+        { 0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3 }, { 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3 },
+        { 0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4 }, { 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4 },
+        { 0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5 }, { 0x1.0000000000000p+0, 0x0.0p+0 },
+        { 0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5 }, { 0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4 },
+        { 0x1.b2036576afce6p-1, 0x1.526e57720db08p-3 }, { 0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3 },
+        { 0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2 }, { 0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2 } };
+
+    // logf for a normal positive float (the only inputs log10fExact hands it)
+    __device__ __forceinline__ float logfExact(float x, const LogfEntry* __restrict__ tab)
+    {
+        const uint32_t ix = __float_as_uint(x);
+        if (ix == 0x3f800000u) return 0.f;
+        const uint32_t tmp = ix - 0x3f330000u;
+        const int i = (tmp >> 19) & 15;
+        const int k = (int)tmp >> 23;
+        const uint32_t iz = ix - (tmp & 0xff800000u);
+        const LogfEntry e = tab[i];
+        const double z = (double)__uint_as_float(iz);
+        const double r = __dsub_rn(__dmul_rn(z, e.invc), 1.0);
+        const double y0 = __dadd_rn(e.logc, __dmul_rn((double)k, 0x1.62e42fefa39efp-1));
+        const double r2 = __dmul_rn(r, r);
+        double y = __dadd_rn(__dmul_rn(0x1.5575b0be00b6ap-2, r), -0x1.ffffef20a4123p-2);
+        y = __dadd_rn(__dmul_rn(-0x1.00ea348b88334p-2, r2), y);
+        y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+        return (float)y;
+    }
+
+    __device__ __forceinline__ float log10fExact(float x, const LogfEntry* __restrict__ tab)
+    {
+        int hx = __float_as_int(x);
+        int k = 0;
+        if (hx < 0x00800000)
+        {
+            if ((hx & 0x7fffffff) == 0) return __int_as_float(0xff800000);       // log10(0) = -inf
+            if (hx < 0) return __int_as_float(0x7fc00000);                       // negative: NaN
+            k -= 25; x = __fmul_rn(x, 3.3554432000e+07f);                        // subnormal: scale by 2^25
+            hx = __float_as_int(x);
+        }
+        if (hx >= 0x7f800000) return __fadd_rn(x, x);
+        k += (hx >> 23) - 127;
+        const int i = (int)((unsigned)k >> 31);
+        hx = (hx & 0x007fffff) | ((0x7f - i) << 23);
+        const float y = (float)(k + i);
+        const float m = __int_as_float(hx);
+        const float z = __fadd_rn(__fmul_rn(y, 7.9034151668e-07f), __fmul_rn(4.3429449201e-01f, logfExact(m, tab)));
+        return __fadd_rn(z, __fmul_rn(y, 3.0102920532e-01f));
+    }
+
+    // 10*log10f(E) of the Schroeder curve (Analyzer.cpp:313).  -DPVC_FAST_LOG10 swaps in the hardware base-2
+    // logarithm (MUFU.LG2; a few ulp off, RT60 then agrees only to ~1e-5 on well-conditioned cells).
+    __device__ __forceinline__ float decibels(float e, const LogfEntry* __restrict__ tab)
+    {
+    #ifdef PVC_FAST_LOG10
+        return __fmul_rn(__log2f(e), 3.0102999566398120f);
+    #else
+        return __fmul_rn(10.f, log10fExact(e, tab));
+    #endif
+    }
 
     struct AnalyzeParams
     {
@@ -40,16 +111,21 @@ namespace pvc
                          const SourceParams* __restrict__ src, float* __restrict__ results,
                          float* __restrict__ delay, float* __restrict__ walkDelay)
     {
-        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        __shared__ LogfEntry sTab[16];
+        if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
+        __syncthreads();
+
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;      // block = one 128-column history strip of one row
         const int r = blockIdx.y;
         const int s = blockIdx.z;
         if (c >= L.gy) return;
         const size_t cells = (size_t)L.gx * L.gy;
         const size_t serial = (size_t)r * L.gx + c;              // INDEX_TO_POS, PvDefinitions.h:24
         float* out = results + ((size_t)s * cells + serial) * 8;
-        const float* H = hist + (size_t)s * A.T * L.hist_plane + (size_t)r * L.hist_pitch + c;
-        const size_t hp = L.hist_plane;
         const int T = A.T;
+        // sample t of this cell is H[t * 128]: the 4 warps of the block walk one contiguous 512-byte-per-sample stream
+        const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c);
+        constexpr ptrdiff_t hs = kHistChunk;
 
         const size_t wi = cellIndex(L, r, c);
         const float wSelf = w[wi];
@@ -59,54 +135,18 @@ namespace pvc
             walkDelay[(size_t)s * cells + serial] = FLT_MAX;
             return;
         }
-        const float wUp = w[wi - L.pitch], wLeft = w[wi - 1];
-        const bool topEdge = (r == 0), leftEdge = (c == 0);
-        const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
 
-        // ---- causal pass: onset, Edry over [0, onset+D), flux over [0, onset+Sd) ----
-        // Loads are issued kCausalBatch samples ahead of their use (3 per sample: the cell, the cell above and
-        // the cell to the left -- the last two are the neighbouring threads' lines, so they hit L1); reading a
-        // few samples past the end of the windows is harmless.
-        constexpr int kCausalBatch = 4;
+        // ---- onset: first sample with |p| > threshold (Analyzer.cpp:146-154); kBatch loads in flight ----
+        constexpr int kBatch = 8;
         int onset = -1;
-        float edry = 0.f, fx = 0.f, fy = 0.f, vx = 0.f, vy = 0.f;
-        int dryEnd = T, fluxEnd = T;
-        const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_pitch;
-        const ptrdiff_t leftOff = leftEdge ? 0 : -1;
-        for (int t0 = 0; t0 < dryEnd; t0 += kCausalBatch)
+        for (int t0 = 0; t0 < T && onset < 0; t0 += kBatch)
         {
-            float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
+            float v[kBatch];
             #pragma unroll
-            for (int u = 0; u < kCausalBatch; ++u)
-            {
-                const int t = min(t0 + u, T - 1);
-                const float* q = H + (size_t)t * hp;
-                bp[u] = __ldg(q);
-                bu[u] = __ldg(q + upOff);
-                bl[u] = __ldg(q + leftOff);
-            }
+            for (int u = 0; u < kBatch; ++u) v[u] = __ldg(H + (ptrdiff_t)min(t0 + u, T - 1) * hs);
             #pragma unroll
-            for (int u = 0; u < kCausalBatch; ++u)
-            {
-                const int t = t0 + u;
-                if (t >= dryEnd) break;
-                const float p = bp[u];
-                if (onset < 0 && fabsf(p) > kAudibleThreshold)
-                {
-                    onset = t;
-                    dryEnd = min(t + A.drySamples, T);
-                    fluxEnd = min(t + A.fluxSamples, T);
-                    if (t >= dryEnd) break;
-                }
-                if (t < fluxEnd)
-                {
-                    vx = topEdge ? -p : (upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, bu[u]))) : -__fmul_rn(wUp, p));
-                    vy = leftEdge ? -p : (leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, bl[u]))) : -__fmul_rn(wLeft, p));
-                    fx = __fadd_rn(fx, __fmul_rn(p, vx));
-                    fy = __fadd_rn(fy, __fmul_rn(p, vy));
-                }
-                edry = __fadd_rn(edry, __fmul_rn(p, p));
-            }
+            for (int u = kBatch - 1; u >= 0; --u)
+                if (t0 + u < T && fabsf(v[u]) > kAudibleThreshold) onset = t0 + u;
         }
         if (onset < 0)
         {
@@ -115,6 +155,50 @@ namespace pvc
             return;
         }
         const int directEnd = onset + A.drySamples;
+        const int dryEnd = min(directEnd, T), fluxEnd = min(onset + A.fluxSamples, T);
+
+        // ---- Edry over [0, onset+D), flux over [0, onset+Sd), both from sample 0 (Analyzer.cpp:182-195).
+        //      vx, vy of the cell are rebuilt from the recorded pressures of the cell and of its up / left
+        //      neighbours (the neighbouring threads' lines: L1 hits) with the solver's own rules. ----
+        float edry = 0.f, fx = 0.f, fy = 0.f;
+        {
+            const float wUp = w[wi - L.pitch], wLeft = w[wi - 1];
+            const bool topEdge = (r == 0), leftEdge = (c == 0);
+            const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
+            const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
+            const ptrdiff_t leftOff = leftEdge ? 0 : (((c & 127) != 0) ? -1 : -(ptrdiff_t)T * kHistChunk + 127);
+            float vx = 0.f, vy = 0.f;
+            constexpr int kCausalBatch = 4;
+            for (int t0 = 0; t0 < fluxEnd; t0 += kCausalBatch)
+            {
+                float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
+                #pragma unroll
+                for (int u = 0; u < kCausalBatch; ++u)
+                {
+                    const float* q = H + (ptrdiff_t)min(t0 + u, T - 1) * hs;
+                    bp[u] = __ldg(q);
+                    bu[u] = __ldg(q + upOff);
+                    bl[u] = __ldg(q + leftOff);
+                }
+                #pragma unroll
+                for (int u = 0; u < kCausalBatch; ++u)
+                {
+                    if (t0 + u >= fluxEnd) break;
+                    const float p = bp[u];
+                    vx = topEdge ? -p : (upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, bu[u]))) : -__fmul_rn(wUp, p));
+                    vy = leftEdge ? -p : (leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, bl[u]))) : -__fmul_rn(wLeft, p));
+                    edry = __fadd_rn(edry, __fmul_rn(p, p));
+                    fx = __fadd_rn(fx, __fmul_rn(p, vx));
+                    fy = __fadd_rn(fy, __fmul_rn(p, vy));
+                }
+            }
+            const float* q = H + (ptrdiff_t)fluxEnd * hs;
+            for (int t = fluxEnd; t < dryEnd; ++t, q += hs)
+            {
+                const float p = __ldg(q);
+                edry = __fadd_rn(edry, __fmul_rn(p, p));
+            }
+        }
 
         // ---- obstruction gain and source directivity (Analyzer.cpp:199-220, FreeGrid.cpp:41-59) ----
         const SourceParams sp = src[s];
@@ -131,8 +215,8 @@ namespace pvc
         norm = __fdiv_rn(-1.0f, (norm > 0.0f ? norm : 1.0f));
         const float sdx = __fmul_rn(norm, fx), sdy = __fmul_rn(norm, fy);
 
-        // ---- low-pass cutoff (Analyzer.cpp:227-230); powf evaluated in double then rounded, which is
-        //      what a correctly rounded libm powf returns in all but vanishingly rare ties ----
+        // ---- low-pass cutoff (Analyzer.cpp:227-230); powf evaluated in double then rounded: equals libm's
+        //      powf except on rare cells where that one is 1 ulp off the correctly rounded value ----
         const float rinv = __fdiv_rn(1.0f, fmaxf(0.001f, occ));
         const float pw = (float)pow((double)__fdiv_rn(rinv, 12.f), (double)0.8f);
         const float lowpass = __fadd_rn(-147.f, __fdiv_rn(18390.f, __fadd_rn(1.f, pw)));
@@ -141,9 +225,9 @@ namespace pvc
         float wet = 0.f;
         {
             const int end = min(directEnd + 1 + A.wetSamples, T);
-            const float* q = H + (size_t)(directEnd + 1) * hp;
+            const float* q = H + (ptrdiff_t)(directEnd + 1) * hs;
             #pragma unroll 4
-            for (int j = directEnd + 1; j < end; ++j, q += hp)
+            for (int j = directEnd + 1; j < end; ++j, q += hs)
             {
                 const float p = __ldg(q);
                 wet = __fadd_rn(wet, __fmul_rn(p, p));
@@ -160,24 +244,21 @@ namespace pvc
         const float xsum = __fmul_rn(rn, xmean);
         const float denominator = __fmul_rn(__fmul_rn(1.0f / 12.0f, rn), __fsub_rn(__fmul_rn(rn, rn), 1.0f));
         float edc = 0.f, xysum = 0.f, ysum = 0.f;
-        // Both backward loops walk one pointer down the history (no per-sample 64-bit index multiply) and
-        // keep kRtBatch independent streaming loads in flight per thread: with one 4-byte load outstanding
-        // per thread the pass is latency-bound at ~0.8 TB/s; batching lifts it towards the HBM roofline.
-        constexpr int kRtBatch = 8;
-        const ptrdiff_t hps = (ptrdiff_t)hp;
+        // both backward loops walk one pointer down the strip and keep kBatch streaming loads in flight per
+        // thread (one outstanding 4-byte load per thread leaves the pass latency-bound far below HBM speed)
         {
             int i = T - 1;
             const int stop = max(endPoint, 0);
-            const float* q = H + (size_t)i * hp;
-            for (; i - (kRtBatch - 1) >= stop; i -= kRtBatch, q -= kRtBatch * hps)
+            const float* q = H + (ptrdiff_t)i * hs;
+            for (; i - (kBatch - 1) >= stop; i -= kBatch, q -= kBatch * hs)
             {
-                float v[kRtBatch];
+                float v[kBatch];
                 #pragma unroll
-                for (int u = 0; u < kRtBatch; ++u) v[u] = __ldcs(q - u * hps);
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - u * hs);
                 #pragma unroll
-                for (int u = 0; u < kRtBatch; ++u) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+                for (int u = 0; u < kBatch; ++u) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
             }
-            for (; i >= stop; --i, q -= hps)
+            for (; i >= stop; --i, q -= hs)
             {
                 const float p = __ldcs(q);
                 edc = __fadd_rn(edc, __fmul_rn(p, p));
@@ -187,27 +268,27 @@ namespace pvc
         {
             int i = endPoint - 1;
             float x = (float)(i - start);              // exact; decremented by 1.0f per sample (< 2^24)
-            const float* q = H + (size_t)i * hp;
-            for (; i - (kRtBatch - 1) >= start; i -= kRtBatch, q -= kRtBatch * hps)
+            const float* q = H + (ptrdiff_t)i * hs;
+            for (; i - (kBatch - 1) >= start; i -= kBatch, q -= kBatch * hs)
             {
-                float v[kRtBatch];
+                float v[kBatch];
                 #pragma unroll
-                for (int u = 0; u < kRtBatch; ++u) v[u] = __ldcs(q - u * hps);
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - u * hs);
                 #pragma unroll
-                for (int u = 0; u < kRtBatch; ++u)
+                for (int u = 0; u < kBatch; ++u)
                 {
                     edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
-                    const float y = __fmul_rn(10.f, log10f(edc));
+                    const float y = decibels(edc, sTab);
                     xysum = __fadd_rn(xysum, __fmul_rn(y, x));
                     ysum = __fadd_rn(ysum, y);
                     x = __fsub_rn(x, 1.0f);
                 }
             }
-            for (; i >= start; --i, q -= hps)
+            for (; i >= start; --i, q -= hs)
             {
                 const float p = __ldcs(q);
                 edc = __fadd_rn(edc, __fmul_rn(p, p));
-                const float y = __fmul_rn(10.f, log10f(edc));
+                const float y = decibels(edc, sTab);
                 xysum = __fadd_rn(xysum, __fmul_rn(y, x));
                 ysum = __fadd_rn(ysum, y);
                 x = __fsub_rn(x, 1.0f);
@@ -292,16 +373,18 @@ namespace pvc
                                     const float* __restrict__ w, int r, int c, float* __restrict__ out)
     {
         if (blockIdx.x != 0 || threadIdx.x != 0) return;
-        const float* H = hist + (size_t)r * L.hist_pitch + c;
+        const float* H = hist + histCell(L, r, c);
+        const float* Hu = (r > 0) ? hist + histCell(L, r - 1, c) : H;
+        const float* Hl = (c > 0) ? hist + histCell(L, r, c - 1) : H;
         const size_t wi = cellIndex(L, r, c);
         const float wSelf = w[wi], wUp = w[wi - L.pitch], wLeft = w[wi - 1];
         const bool aSelf = isAirA(wSelf), aUp = isAirA(wUp), aLeft = isAirA(wLeft);
         float vx = 0.f, vy = 0.f;
         for (int t = 0; t < T; ++t)
         {
-            const float p = H[(size_t)t * L.hist_plane];
-            const float pu = (r > 0) ? H[(size_t)t * L.hist_plane - L.hist_pitch] : 0.f;
-            const float pl = (c > 0) ? H[(size_t)t * L.hist_plane - 1] : 0.f;
+            const float p = H[(size_t)t * kHistChunk];
+            const float pu = (r > 0) ? Hu[(size_t)t * kHistChunk] : 0.f;
+            const float pl = (c > 0) ? Hl[(size_t)t * kHistChunk] : 0.f;
             if (c >= L.gy) vx = 0.f;
             else if (r == 0) vx = -p;
             else if (r == L.gx) vx = pu;
@@ -348,7 +431,7 @@ namespace pvc
     int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev)
     {
         const Layout& L = s->L;
-        const float* h = s->hist + (size_t)source * s->cfg.T * L.hist_plane;
+        const float* h = s->hist + (size_t)source * L.hist_source;
         rebuildIrKernel<<<1, 32, 0, s->stream>>>(L, s->cfg.T, s->cfg.courant, h, s->w, r, c, out_dev);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("ir rebuild launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }

@@ -40,8 +40,10 @@ namespace pvc
         L.rows_alloc = L.tiles_y * L.valid_rows + 2 * kGuardRows;
         if (L.rows_alloc < L.rows + kGuardRows + 1) L.rows_alloc = L.rows + kGuardRows + 1;
         L.plane = (size_t)L.rows_alloc * L.pitch;
-        L.hist_pitch = roundUp(L.cols, 32);
-        L.hist_plane = (size_t)L.rows * L.hist_pitch;
+        L.T = c.T;
+        L.hist_chunks = (L.cols + kHistChunk - 1) / kHistChunk;
+        L.hist_row = (size_t)L.hist_chunks * c.T * kHistChunk;
+        L.hist_source = (size_t)L.rows * L.hist_row;
         return L;
     }
 
@@ -99,18 +101,19 @@ namespace pvc
         y[(size_t)r * L.cols + c] = air ? 1.f : v;       // air has R = 0 -> Y = 1 in the reference's terms
     }
 
-    __global__ void gatherProbeKernel(const float* __restrict__ hist, size_t plane, size_t offset, int n, float* __restrict__ out)
+    __global__ void gatherProbeKernel(const float* __restrict__ hist, size_t offset, int n, float* __restrict__ out)
     {
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
-        if (t < n) out[t] = hist[(size_t)t * plane + offset];
+        if (t < n) out[t] = hist[offset + (size_t)t * kHistChunk];
     }
 
-    __global__ void unpackPlaneKernel(Layout L, const float* __restrict__ plane, int guarded, float* __restrict__ out)
+    // t < 0: a guarded state plane; t >= 0: sample t of a source's pressure history
+    __global__ void unpackPlaneKernel(Layout L, const float* __restrict__ plane, int t, float* __restrict__ out)
     {
         const int c = blockIdx.x * blockDim.x + threadIdx.x;
         const int r = blockIdx.y;
         if (c > L.gy) return;
-        out[(size_t)r * L.cols + c] = guarded ? plane[cellIndex(L, r, c)] : plane[(size_t)r * L.hist_pitch + c];
+        out[(size_t)r * L.cols + c] = (t < 0) ? plane[cellIndex(L, r, c)] : plane[histCell(L, r, c) + (size_t)t * kHistChunk];
     }
 
     int launchClearGeometry(pvc_solver* s)
@@ -149,9 +152,9 @@ namespace pvc
 
     static int runSteps(pvc_solver* s, int nsrc, int T, int* launches)
     {
-        if (s->cfg.step_kernel == 1) return launchBaselineSteps(s, nsrc, 0, T, s->hist, s->cfg.T, launches);
+        if (s->cfg.step_kernel == 1) return launchBaselineSteps(s, nsrc, 0, T, s->hist, launches);
         if (s->slowMaskDirty) { int rc = rebuildSlowMask(s); if (rc) return rc; }
-        return launchFusedSteps(s, nsrc, 0, T, s->hist, s->cfg.T, launches);
+        return launchFusedSteps(s, nsrc, 0, T, s->hist, launches);
     }
 }
 
@@ -173,7 +176,7 @@ size_t pvc_memory_requirement(const pvc_config* cfg)
     if (!validConfig(cfg)) return 0;
     const Layout L = makeLayout(*cfg);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + L.plane + S * (size_t)cfg->T * L.hist_plane + (size_t)cfg->T +
+    return sizeof(float) * (6 * S * L.plane + L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 10 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
@@ -208,7 +211,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
         }
     PVC_TRY(cudaMalloc(&s->w, sizeof(float) * L.plane));
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
-    PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * (size_t)cfg->T * L.hist_plane));
+    PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
     PVC_TRY(cudaMalloc(&s->results, sizeof(float) * S * cells * 8));
@@ -310,7 +313,7 @@ int pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, floa
     std::vector<float> probe((size_t)n);
     if (!rc)
     {
-        gatherProbeKernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->hist, L.hist_plane, (size_t)er * L.hist_pitch + ec, n, s->scratch);
+        gatherProbeKernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->hist, histCell(L, er, ec), n, s->scratch);
         if (cudaMemcpyAsync(probe.data(), s->scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
             cudaStreamSynchronize(s->stream) != cudaSuccess)
         { setError("pvc_compute_efree: %s", cudaGetErrorString(cudaGetLastError())); rc = PVC_ERR_CUDA; }
@@ -407,13 +410,13 @@ int pvc_fetch_ir(pvc_solver* s, int source, int r, int c, float* out3T)
     return PVC_OK;
 }
 
-static int fetchPlane(pvc_solver* s, const float* dev, int guarded, float* host)
+static int fetchPlane(pvc_solver* s, const float* dev, int t, float* host)
 {
     const Layout& L = s->L;
     const size_t n = (size_t)L.rows * L.cols;
     float* tmp = nullptr;
     PVC_CUDA(cudaMalloc(&tmp, sizeof(float) * n));
-    unpackPlaneKernel<<<dim3((L.cols + 127) / 128, L.rows), 128, 0, s->stream>>>(L, dev, guarded, tmp);
+    unpackPlaneKernel<<<dim3((L.cols + 127) / 128, L.rows), 128, 0, s->stream>>>(L, dev, t, tmp);
     PVC_CUDA(cudaMemcpyAsync(host, tmp, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
     cudaFree(tmp);
@@ -425,7 +428,7 @@ int pvc_fetch_pressure(pvc_solver* s, int source, int t, float* plane)
     if (!s || !plane || source < 0 || source >= s->cfg.max_sources || t < 0 || t >= s->cfg.T)
     { setError("pvc_fetch_pressure: bad argument"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
-    return fetchPlane(s, s->hist + ((size_t)source * s->cfg.T + t) * s->L.hist_plane, 0, plane);
+    return fetchPlane(s, s->hist + (size_t)source * s->L.hist_source, t, plane);
 }
 
 int pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, float* vy)
@@ -434,7 +437,7 @@ int pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, float* vy)
     PVC_CUDA(cudaSetDevice(s->device));
     float* host[3] = { p, vx, vy };
     for (int f = 0; f < 3; ++f)
-        if (host[f]) { int rc = fetchPlane(s, s->state[s->cur][f] + (size_t)source * s->L.plane, 1, host[f]); if (rc) return rc; }
+        if (host[f]) { int rc = fetchPlane(s, s->state[s->cur][f] + (size_t)source * s->L.plane, -1, host[f]); if (rc) return rc; }
     return PVC_OK;
 }
 

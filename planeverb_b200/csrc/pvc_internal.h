@@ -10,9 +10,12 @@
 //       bit pattern kAirBits  -> air cell (reference b = 1)
 //       anything else         -> wall cell (b = 0) and the float is its admittance
 //                                Y = (1-R)/(1+R) (FDTD.cpp:153,160); guard cells are walls with Y = 0.
-//   pressure history   hist [source][T][hist_rows][hist_pitch]:  sample t of alloc cell (r, c) at
-//       t*hist_plane + r*hist_pitch + c -- the only per-step record kept (4 B per cell-step instead
-//       of the reference's 16-byte Cell, FDTD.cpp:226-231); vx/vy of any sample are rebuilt from it.
+//   pressure history   hist [source][row][chunk][t][128]: sample t of alloc cell (r, c) lives at
+//       ((r*hist_chunks + c/128)*T + t)*128 + c%128 -- time-major inside each 128-column strip, so the
+//       step kernel appends 512 contiguous bytes per warp-row per step and the analyzer, which walks
+//       every cell through time, reads each strip as ONE sequential stream.  It is the only per-step
+//       record kept (4 B per cell-step instead of the reference's 16-byte Cell, FDTD.cpp:226-231);
+//       vx/vy of any sample are rebuilt from it.
 //   results  [source][gx*gy][8], delay [source][gx*gy]   (Analyzer.h:13-21, Analyzer.cpp:40)
 #pragma once
 #include <cuda_runtime.h>
@@ -37,8 +40,10 @@ namespace pvc
         int pitch;             // floats per state row (multiple of 32)
         int rows_alloc;        // state rows incl. guards
         size_t plane;          // rows_alloc * pitch
-        int hist_pitch;        // floats per history row (multiple of 32)
-        size_t hist_plane;     // rows * hist_pitch
+        int T;                 // samples per impulse response
+        int hist_chunks;       // 128-column strips per row: ceil(cols / 128)
+        size_t hist_row;       // floats between consecutive rows of the history: hist_chunks * T * 128
+        size_t hist_source;    // floats between sources: rows * hist_row
         int tiles_x, tiles_y;  // fused-kernel tile grid
         int tile_rows;         // rows per tile incl. halo (warps * rows per thread)
         int valid_rows;        // tile_rows - 2*kTileK
@@ -47,6 +52,14 @@ namespace pvc
     __host__ __device__ inline size_t cellIndex(const Layout& L, int r, int c)
     {
         return (size_t)(r + kGuardRows) * L.pitch + (c + kGuardCols);
+    }
+
+    constexpr int kHistChunk = 128;
+
+    // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*128
+    __host__ __device__ inline size_t histCell(const Layout& L, int r, int c)
+    {
+        return (size_t)r * L.hist_row + (size_t)(c >> 7) * L.T * kHistChunk + (c & 127);
     }
 
     struct SourceParams       // one listener, device copy of pvc_listener plus derived indices
@@ -87,8 +100,8 @@ struct pvc_solver
 namespace pvc
 {
     // step kernels (pvc_step.cu / pvc_step_fused.cu)
-    int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches);
-    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches);
+    int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
+    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int rebuildSlowMask(pvc_solver* s);
     int fusedTileRows(int variant);
     // analyzer kernels (pvc_analyze.cu)

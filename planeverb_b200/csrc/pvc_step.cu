@@ -27,7 +27,7 @@ namespace pvc
     // sample's injection folded in front (p[li] += pulse[t-1], FDTD.cpp:234)
     __global__ void __launch_bounds__(256)
     baselinePressureKernel(Layout L, float* __restrict__ p, const float* __restrict__ vx, const float* __restrict__ vy,
-                           const float* __restrict__ w, float* __restrict__ hist, size_t histSourceStride,
+                           const float* __restrict__ w, float* __restrict__ hist,
                            const SourceParams* __restrict__ src, const float* __restrict__ pulse, int t, float courant)
     {
         const int q = blockIdx.x * blockDim.x + threadIdx.x;       // column quad
@@ -70,7 +70,7 @@ namespace pvc
         p4 = make_float4(pv[0], pv[1], pv[2], pv[3]);
         *reinterpret_cast<float4*>(p + base + i) = p4;
         if (hist)
-            __stcs(reinterpret_cast<float4*>(hist + (size_t)s * histSourceStride + (size_t)r * L.hist_pitch + c), p4);
+            __stcs(reinterpret_cast<float4*>(hist + (size_t)s * L.hist_source + histCell(L, r, c) + (size_t)t * kHistChunk), p4);
     }
 
     // both velocity sub-steps + the grid-edge absorbing overrides (FDTD.cpp:144-223)
@@ -123,18 +123,16 @@ namespace pvc
     }
 
     // steps t0..t1-1 on state[s->cur]; hist (may be null) receives one plane per step
-    int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
+    int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
         const int quads = (L.cols + 3) / 4;
         dim3 block(32, 8, 1);
         dim3 grid((quads + 31) / 32, (L.rows + 7) / 8, nsrc);
         float** st = s->state[s->cur];
-        const size_t srcStride = (size_t)T_hist * L.hist_plane;
         for (int t = t0; t < t1; ++t)
         {
-            float* h = hist ? hist + (size_t)t * L.hist_plane : nullptr;
-            baselinePressureKernel<<<grid, block, 0, s->stream>>>(L, st[0], st[1], st[2], s->w, h, srcStride,
+            baselinePressureKernel<<<grid, block, 0, s->stream>>>(L, st[0], st[1], st[2], s->w, hist,
                                                                  s->src, s->pulse, t, s->cfg.courant);
             baselineVelocityKernel<<<grid, block, 0, s->stream>>>(L, st[0], st[1], st[2], s->w, s->cfg.courant);
             *launches += 2;

@@ -15,8 +15,8 @@
 //     thread's own registers except across warp boundaries, which exchange one row per sub-step through
 //     2 KB of shared memory.  Lanes 0/31 and the top/bottom 4 rows are halo: their values go stale by
 //     one cell per step, which is exactly the 4-cell halo budget, and are never stored.
-//   * Each of the 4 sub-steps streams the freshly updated pressure of the tile's owned cells to that
-//     sample's history plane (evict-first stores) -- the only per-step HBM traffic: 4 B per cell-step
+//   * Each of the 4 sub-steps appends the freshly updated pressure of the tile's owned cells to the
+//     time-major pressure history (evict-first stores; the 4 samples of a warp-row are 2 KB contiguous) -- the only per-step HBM traffic: 4 B per cell-step
 //     instead of the 28 B of a one-step-per-launch formulation (read+write p,vx,vy + coefficient).
 //   * Walls, the padding row/column and the grid-edge overrides take a general per-cell path; a
 //     per-(tile, warp) lane mask precomputed after every geometry edit tells a thread whether all its
@@ -51,8 +51,7 @@ namespace pvc
         float* outP; float* outVx; float* outVy;
         const float* w;
         const uint32_t* slowMask;
-        float* hist;               // plane of sample t0 of source 0 (null: no record)
-        size_t histSourceStride;   // floats between sources in hist
+        float* hist;               // pressure history of source 0 (null: no record)
         const SourceParams* src;
         const float* pulse;
         int t0, nsteps;
@@ -93,10 +92,26 @@ namespace pvc
             }
         }
 
-        // warp-uniform on purpose: a warp with any general-path lane runs the general path for all lanes
-        // (it is a superset of the fast path), so the shuffles below never sit in divergent code
-        const bool slow = A.slowMask[((size_t)ty * L.tiles_x + tx) * 32 + wp] != 0u;
+        // warp-uniform path choice (so the shuffles below never sit in divergent code):
+        //   0 fast    every cell of the warp, and each one's up/left neighbour, is interior air
+        //   1 edge    no wall, but the warp touches the grid edge / padding / guard band: fast arithmetic plus
+        //             position-only overwrites (the absorbing-edge overrides and the zeros outside the interior)
+        //   2 general some cell or neighbour is a wall: per-cell coefficient loads and the full rule
+        const uint32_t mode = A.slowMask[((size_t)ty * L.tiles_x + tx) * 32 + wp];
+        const bool slow = mode == 2u;
+        const bool edge = mode == 1u;
         const float C = A.courant;
+
+        // column classes of this thread's 4 cells, one bit per k (only consulted on the edge path)
+        uint32_t colOut = 0u, colPad = 0u, colLeft = 0u;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int cc = cBase + k;
+            if (cc < 0 || cc > L.gy) colOut |= 1u << k;
+            if (cc == L.gy) colPad |= 1u << k;
+            if (cc == 0) colLeft |= 1u << k;
+        }
 
         // owned (stored) rows of this thread: j in [jLo, jHi) -- not halo, inside the alloc grid; empty
         // for the halo lanes 0 and 31 and for columns past the grid
@@ -110,8 +125,12 @@ namespace pvc
         const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
         const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
 
-        // only dereferenced for owned rows/columns, where rBase + j >= 0 and cBase >= 0
-        float* hist = A.hist ? A.hist + (size_t)s * A.histSourceStride + ((ptrdiff_t)rBase * L.hist_pitch + cBase) : nullptr;
+        // sample t0 of this thread's 4 cells in row rBase; only dereferenced for owned rows/columns, where
+        // rBase + j >= 0 and cBase >= 0.  Rows are hist_row floats apart, consecutive samples 128 floats.
+        float* hist = nullptr;
+        if (A.hist)
+            hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
+                 + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
 
         if (wp == 0)
         {
@@ -128,7 +147,7 @@ namespace pvc
             {
                 const float4 vxBelow = sVxTop[wp + 1][lane];
                 const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
-                if (!slow)
+                if (!slow && !edge)
                 {
                     #pragma unroll
                     for (int j = 0; j < R; ++j)
@@ -141,6 +160,26 @@ namespace pvc
                             const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
                             const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
                             p[j][k] = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                        }
+                    }
+                }
+                else if (edge)
+                {
+                    const uint32_t colDead = colOut | colPad;          // b = 0 there: pressure stays 0
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                    {
+                        const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                        const int r = rBase + j;
+                        const bool rowDead = (r < 0) || (r >= L.gx);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                            const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                            const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                            const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                            p[j][k] = (rowDead || ((colDead >> k) & 1u)) ? 0.f : pn;
                         }
                     }
                 }
@@ -172,7 +211,7 @@ namespace pvc
             {
                 const float4 pAbove = sPBot[wp][lane];
                 const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
-                if (!slow)
+                if (!slow && !edge)
                 {
                     #pragma unroll
                     for (int j = 0; j < R; ++j)
@@ -185,6 +224,34 @@ namespace pvc
                             const float pl = (k > 0) ? p[j][k - 1] : pLeft;
                             vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
                             vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                        }
+                    }
+                }
+                else if (edge)
+                {
+                    const uint32_t colDeadX = colOut | colPad;         // vx: padding column is never driven
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                    {
+                        const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                        const int r = rBase + j;
+                        const bool rowOut = (r < 0) || (r > L.gx);
+                        const bool rowTop = (r == 0), rowPad = (r == L.gx);
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            const float pt = p[j][k];
+                            float nx = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
+                            float ny = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
+                            nx = rowTop ? -pt : nx;                                  // FDTD.cpp:208
+                            nx = rowPad ? pu : nx;                                   // FDTD.cpp:209
+                            nx = (rowOut || ((colDeadX >> k) & 1u)) ? 0.f : nx;
+                            ny = ((colLeft >> k) & 1u) ? -pt : ny;                   // FDTD.cpp:220
+                            ny = ((colPad >> k) & 1u) ? pl : ny;                     // FDTD.cpp:221
+                            ny = (rowOut || rowPad || ((colOut >> k) & 1u)) ? 0.f : ny;
+                            vx[j][k] = nx; vy[j][k] = ny;
                         }
                     }
                 }
@@ -234,8 +301,8 @@ namespace pvc
                 #pragma unroll
                 for (int j = 0; j < R; ++j)
                     if (j >= jLo && j < jHi)
-                        __stcs(reinterpret_cast<float4*>(hist + (size_t)j * L.hist_pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
-                hist += L.hist_plane;
+                        __stcs(reinterpret_cast<float4*>(hist + (size_t)j * L.hist_row), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                hist += kHistChunk;
             }
             if (hasSrc)
             {
@@ -273,9 +340,10 @@ namespace pvc
         }
     }
 
-    // lane mask per (tile, warp): 1 = some cell of the thread, or an up/left neighbour of one, is not air.
-    // The step kernel only tests the word against zero (warp-uniform path choice).
-    template <int NW, int R>
+    // path mode per (tile, warp), see fusedStepKernel: 0 fast, 1 edge, 2 general.  Only INTERIOR cells can be
+    // walls that matter: the padding row/column is b = 0 whatever an AABB wrote there (Grid.cpp:94-97,276-280)
+    // and its admittance is never used (every velocity next to it is an edge override).
+    template <int NW, int R, int MINB>
     __global__ void slowMaskKernel(const Layout L, const float* __restrict__ w, uint32_t* __restrict__ mask)
     {
         const int lane = threadIdx.x & 31;
@@ -283,16 +351,22 @@ namespace pvc
         const int tx = blockIdx.x, ty = blockIdx.y;
         const int rBase = ty * L.valid_rows - kTileK + wp * R;
         const int cBase = tx * kValidCols - kGuardCols + lane * 4;
-        bool slow = false;
+        bool wall = false, edge = false;
         for (int j = -1; j < R; ++j)
             for (int k = -1; k < 4; ++k)
             {
-                const int mr = rBase + j + kGuardRows, mc = cBase + k + kGuardCols;   // memory coordinates
-                if (mr < 0 || mc < 0) continue;          // above/left of the allocation: halo of a halo, value irrelevant
-                if (__float_as_uint(w[(size_t)mr * L.pitch + mc]) != kAirBits) slow = true;
+                const int r = rBase + j, c = cBase + k;
+                const bool interior = (r >= 0) && (r < L.gx) && (c >= 0) && (c < L.gy);
+                if (interior)
+                {
+                    if (__float_as_uint(w[cellIndex(L, r, c)]) != kAirBits) wall = true;
+                    if ((j >= 0 && r == 0) || (k >= 0 && c == 0)) edge = true;
+                }
+                else if (j >= 0 && k >= 0) edge = true;       // an own cell outside the interior
             }
-        const uint32_t m = __ballot_sync(0xffffffffu, slow);
-        if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = m;
+        const uint32_t anyWall = __ballot_sync(0xffffffffu, wall);
+        const uint32_t anyEdge = __ballot_sync(0xffffffffu, edge);
+        if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = anyWall ? 2u : (anyEdge ? 1u : 0u);
     }
 
     struct Variant { int nw, r, minBlocks; };
@@ -306,7 +380,7 @@ namespace pvc
     }
 
     template <int NW, int R, int MINB>
-    static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
+    static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
         dim3 grid(L.tiles_x, L.tiles_y, nsrc), block(NW * 32);
@@ -318,8 +392,7 @@ namespace pvc
             A.inP = in[0]; A.inVx = in[1]; A.inVy = in[2];
             A.outP = out[0]; A.outVx = out[1]; A.outVy = out[2];
             A.w = s->w; A.slowMask = s->slowMask;
-            A.hist = hist ? hist + (size_t)t * L.hist_plane : nullptr;
-            A.histSourceStride = (size_t)T_hist * L.hist_plane;
+            A.hist = hist;
             A.src = s->src; A.pulse = s->pulse;
             A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
             A.courant = s->cfg.courant;
@@ -336,7 +409,7 @@ namespace pvc
     static int maskVariant(pvc_solver* s)
     {
         const Layout& L = s->L;
-        slowMaskKernel<NW, R><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->slowMask);
+        slowMaskKernel<NW, R, MINB><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->slowMask);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("slow mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         s->slowMaskDirty = 0;
@@ -354,10 +427,10 @@ namespace pvc
             default: return fn<12, 8, 1>(__VA_ARGS__);                        \
         }
 
-    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int T_hist, int* launches)
+    int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
-        PVC_DISPATCH(launchVariant, s, nsrc, t0, t1, hist, T_hist, launches)
+        PVC_DISPATCH(launchVariant, s, nsrc, t0, t1, hist, launches)
     }
 
     int rebuildSlowMask(pvc_solver* s)

@@ -1,0 +1,283 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI
+(include/planeverb_cuda.h, planeverb_ext.h via planeverb_b200/pvcuda.py).  The checker is the oracle:
+golden vectors captured from the unmodified reference (tests/golden/) and the plain-C restatement
+(oracle/pv_oracle.c), itself pinned bit-for-bit to the reference by tests/test_oracle.py.
+
+Bar: pressure/velocity fields, impulse responses, onset delays, obstruction, wet gain, low-pass cutoff,
+source directivity, listener direction AND RT60 BIT-EXACT (the device reproduces glibc's log10f bit for bit,
+tests/test_oracle.py::test_device_log10f_recipe_matches_libm); the low-pass cutoff within 1 ulp (powf is
+evaluated in double and rounded).  BASELINE.json would allow 1e-4 relative.
+"""
+import numpy as np
+import pytest
+
+from oracle import pvoracle
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+RT60_RTOL = 0.0           # bit-exact (north_star would allow 1e-4)
+LOWPASS_RTOL = 2.5e-7     # powf: the device rounds a double pow, libm's powf may differ by 1 ulp on rare cells
+EXACT = [0, 1, 4, 5, 6, 7]
+
+
+@pytest.fixture(scope="module")
+def pv():
+    from planeverb_b200 import pvcuda
+    if pvcuda.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU path, GPU tests cannot run")
+    return pvcuda
+
+
+def assert_results(got, got_delay, ref, ref_delay, exclude=None, rt60_rtol=RT60_RTOL):
+    assert np.array_equal(got_delay, ref_delay), "onset delays differ"
+    valid = ref_delay < 3e38
+    if exclude is not None:
+        valid &= ~exclude
+    every = np.ones_like(valid) if exclude is None else ~exclude
+    for k in EXACT:
+        m = every if k in (4, 5) else valid
+        ok = common.bit_equal(got[m, k], ref[m, k])
+        assert ok.all(), f"{common.FIELDS[k]}: {int((~ok).sum())} cells differ (max rel {common.rel_err(got[m, k], ref[m, k]).max():.3e})"
+    lp = common.rel_err(got[valid, 3], ref[valid, 3])
+    assert lp.size == 0 or lp.max() <= LOWPASS_RTOL, f"lowpass max rel err {lp.max():.3e}"
+    # RT60 can legitimately be +-inf / NaN on degenerate regressions (Analyzer.cpp:321-326): compare bits
+    same = common.bit_equal(got[valid, 2], ref[valid, 2]) | (np.isnan(got[valid, 2]) & np.isnan(ref[valid, 2]))
+    e = common.rel_err(got[valid, 2][~same], ref[valid, 2][~same])
+    assert e.size == 0 or e.max() <= rt60_rtol, f"rt60: {e.size} cells differ, max rel err {e.max():.3e} > {rt60_rtol:.1e}"
+    return float(e.max()) if e.size else 0.0
+
+
+def run_pair(pv, scenes, scene, n=None, res=275, T=0, listeners=None, **kw):
+    if n is None:
+        size, scale = 25.0, 1.0
+    else:
+        size, scale = common.scaled_config(n, res)
+    listeners = listeners or [tuple(v * scale for v in common.DEFAULT_LISTENER)]
+    ora = pvoracle.OracleSim(size, size, res, T=T)
+    gpu = pv.Scene(size, size, res, T=T, max_sources=len(listeners), **kw)
+    assert (gpu.gx, gpu.gy, gpu.T, gpu.fs) == (ora.gx, ora.gy, ora.T, ora.fs)
+    assert gpu.efree == ora.efree
+    for b in (common.boxes_of(scenes, scene, scale) if scene else []):
+        ora.add_aabb(*b)
+        gpu.add_aabb(*b)
+    return gpu, ora, listeners
+
+
+@pytest.mark.parametrize("name", common.GOLDEN_CASES)
+def test_golden_vectors(pv, name):
+    """Outputs of the unmodified reference (tools/make_golden.py) reproduced on the device."""
+    meta, z = common.load_golden(name)
+    gpu = pv.Scene(meta["size"], meta["size"], meta["resolution"], T=meta["T_override"])
+    assert (gpu.gx, gpu.gy, gpu.T, gpu.fs) == (meta["gx"], meta["gy"], meta["T"], meta["fs"])
+    dx, dt, efree, courant = z["scalars"]
+    assert (gpu.dx, gpu.dt, gpu.efree, gpu.courant) == (dx, dt, efree, courant)
+    assert np.array_equal(gpu.pulse(), z["pulse"])
+    for b in common.golden_boxes(z):
+        gpu.add_aabb(*b)
+    gb, gy = gpu.coef()
+    assert np.array_equal(gb, z["b"])
+    R = z["R"]
+    assert common.bit_equal(gy[gb == 0], ((1 - R) / (1 + R))[gb == 0]).all()
+    res, dly = gpu.solve([meta["listener"]])
+    for k, t in enumerate(meta["snaps_t"]):
+        assert common.bit_equal(gpu.pressure(t), z["snap_p"][k]).all(), f"pressure plane t={t}"
+    pr, pc = meta["probe"]
+    ir = gpu.ir(pr, pc)
+    for f, fname in enumerate(("p", "vx", "vy")):
+        assert common.bit_equal(ir[:, f], z["ir"][:, f]).all(), f"impulse response {fname}"
+    clamped = common.reference_clamped(meta, z["delay"], gpu.D)
+    assert_results(res[0], dly[0], z["results"], z["delay"], exclude=clamped)
+    gpu.close()
+
+
+@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6)])
+def test_every_step_kernel_variant_matches_oracle(pv, scenes, step_kernel, variant):
+    gpu, ora, Ls = run_pair(pv, scenes, "FloorPlanScene", n=250, T=301, step_kernel=step_kernel, variant=variant)
+    res, dly = gpu.solve(Ls)
+    ora.generate(Ls[0], keep_velocity=True)
+    ora.analyze(Ls[0])
+    for t in (0, 1, 2, 3, 4, 5, 150, 299, 300):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(gpu.gx + 1, gpu.gy + 1)).all(), f"t={t}"
+    p, vx, vy = gpu.state()
+    shp = p.shape
+    assert common.bit_equal(p, ora.hist[-1].reshape(shp)).all()
+    assert common.bit_equal(vx, ora.hvx[-1].reshape(shp)).all()
+    assert common.bit_equal(vy, ora.hvy[-1].reshape(shp)).all()
+    assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    gpu.close()
+
+
+def test_config1_smallroom_128_500(pv, scenes):
+    """BASELINE.json configs[0]: SmallRoom.pv, 128x128, 1 source, 500 steps."""
+    gpu, ora, Ls = run_pair(pv, scenes, "SmallRoom", n=128, T=500)
+    res, dly = gpu.solve(Ls)
+    ora.generate(Ls[0]); ora.analyze(Ls[0])
+    assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    for (x, z) in common.EMITTERS:
+        pos = (x * 128 * float(ora.dx) / 25.0, 0.0, z * 128 * float(ora.dx) / 25.0)
+        out = gpu.lookup(pos)
+        cell = (int(np.float32(pos[0]) / ora.dx), int(np.float32(pos[2]) / ora.dx))      # Analyzer.cpp:110-111
+        assert out is not None
+        assert common.bit_equal(out[EXACT], ora.results[cell[0] * gpu.gx + cell[1], EXACT]).all()
+        assert common.rel_err(out[2:4], ora.results[cell[0] * gpu.gx + cell[1], 2:4]).max() <= LOWPASS_RTOL
+    gpu.close()
+
+
+def test_config2_shoebox_512_2000(pv, scenes):
+    """BASELINE.json configs[1]: Shoebox.pv, 512x512, 1 source, 2000 steps (oracle: the C restatement)."""
+    gpu, ora, Ls = run_pair(pv, scenes, "Shoebox", n=512, T=2000)
+    res, dly = gpu.solve(Ls)
+    ora.generate(Ls[0]); ora.analyze(Ls[0])
+    for t in (0, 7, 500, 1999):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(gpu.gx + 1, gpu.gy + 1)).all(), f"t={t}"
+    worst = assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    print(f"config2 rt60 max rel err {worst:.2e}")
+    gpu.close()
+
+
+def test_batched_sources_equal_separate_solves(pv, scenes):
+    """Sources are independent: a batch of 3 listeners == 3 single solves, bit for bit (the multi-GPU
+    sharding relies on exactly this)."""
+    size, scale = common.scaled_config(300)
+    Ls = common.listeners_for(3, scale)
+    boxes = common.boxes_of(scenes, "HugeRoom", scale)
+    batch = pv.Scene(size, size, 275, T=400, max_sources=3)
+    for b in boxes:
+        batch.add_aabb(*b)
+    rb, db = batch.solve(Ls)
+    single = pv.Scene(size, size, 275, T=400, max_sources=1)
+    for b in boxes:
+        single.add_aabb(*b)
+    for i, L in enumerate(Ls):
+        single.clear_results(0)
+        rs, ds = single.solve([L])
+        assert np.array_equal(ds[0], db[i])
+        assert np.array_equal(rs[0].view(np.uint32), rb[i].view(np.uint32))
+        assert common.bit_equal(single.pressure(399), batch.pressure(399, i)).all()
+    batch.close(); single.close()
+
+
+@pytest.mark.parametrize("n,T,listener_cell", [
+    (5, 40, (2, 2)),            # tiny grid, T shorter than the analysis windows (clamped cells excluded)
+    (119, 133, (0, 0)),         # listener in the corner cell, T not a multiple of the 4-step block
+    (120, 97, (119, 119)),      # grid exactly one tile wide, listener in the last interior cell
+    (121, 150, (60, 120)),      # one column past a tile boundary, listener on the last interior column
+    (239, 202, (238, 0)),
+    (97, 64, (50, 50)),
+])
+def test_edge_case_grids_and_listeners(pv, n, T, listener_cell):
+    size, _ = common.scaled_config(n)
+    ora = pvoracle.OracleSim(size, size, 275, T=T, efree=0.0447895788)
+    gpu = pv.Scene(size, size, 275, T=T, efree=0.0447895788)
+    dx = float(ora.dx)
+    L = ((listener_cell[0] + 0.5) * dx, 0.0, (listener_cell[1] + 0.5) * dx)
+    assert ora.listener_cell(L) == listener_cell
+    # a wall clipped by the grid edge and one covering the padding row/column (Grid.cpp:231,235 clip inclusive)
+    for b in [(-0.5 * dx, 0.3 * n * dx, 3 * dx, 4 * dx, 0.9), (n * dx, 0.7 * n * dx, 4 * dx, 6 * dx, 0.5),
+              (0.6 * n * dx, n * dx, 5 * dx, 2.5 * dx, 0.97)]:
+        ora.add_aabb(*b); gpu.add_aabb(*b)
+    res, dly = gpu.solve([L])
+    ora.generate(L, keep_velocity=True); ora.analyze(L)
+    for t in sorted(set([0, 1, 2, 3, 4, T // 2, T - 1])):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(n + 1, n + 1)).all(), f"t={t}"
+    p, vx, vy = gpu.state()
+    assert common.bit_equal(vx, ora.hvx[-1].reshape(n + 1, n + 1)).all()
+    assert common.bit_equal(vy, ora.hvy[-1].reshape(n + 1, n + 1)).all()
+    assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    gpu.close()
+
+
+def test_listener_inside_a_wall_produces_no_onsets(pv):
+    gpu = pv.Scene(25.0, 25.0, 275)
+    ora = pvoracle.OracleSim(25.0, 25.0, 275)
+    box = (5.0, 4.0, 3.0, 3.0, 0.9)
+    gpu.add_aabb(*box); ora.add_aabb(*box)
+    L = common.DEFAULT_LISTENER
+    res, dly = gpu.solve([L])
+    ora.generate(L); ora.analyze(L)
+    assert (dly[0] > 3e38).all() and np.array_equal(dly[0], ora.delay)
+    assert (res[0][:, [0, 1, 2, 3, 6, 7]] == 0).all()
+    assert common.bit_equal(res[0][:, 4:6], ora.results[:, 4:6]).all()      # direction is still written for every cell
+    gpu.close()
+
+
+def test_stale_results_and_geometry_edits_follow_the_reference(pv, scenes):
+    """Frame 1: listener A. Then UpdateGeometry (= remove old + add new, GeometryManager.cpp:112-121) and
+    frame 2 with listener B WITHOUT clearing: cells with no onset keep frame 1's values (Analyzer.cpp:161-165)."""
+    gpu = pv.Scene(25.0, 25.0, 275, T=60)                    # 60 steps: each frame reaches only ~35 cells
+    ora = pvoracle.OracleSim(25.0, 25.0, 275, T=60)
+    boxes = common.boxes_of(scenes, "SingleWall")
+    for b in boxes:
+        gpu.add_aabb(*b); ora.add_aabb(*b)
+    A, B = (5.0, 0.0, 5.0), (20.0, 0.0, 18.0)
+    res1, dly1 = gpu.solve([A])
+    ora.generate(A); ora.analyze(A)
+    assert_results(res1[0], dly1[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    old, new = boxes[0], (boxes[0][0] + 2.0, boxes[0][1] + 1.0, boxes[0][2], boxes[0][3], 0.8)
+    gpu.remove_aabb(*old); gpu.add_aabb(*new)
+    ora.remove_aabb(*old); ora.add_aabb(*new)
+    gb, _ = gpu.coef()
+    assert np.array_equal(gb, ora.coef()[0])
+    res2, dly2 = gpu.solve([B])
+    ora.generate(B); ora.analyze(B)
+    stale = ora.delay > 3e38
+    assert stale.any() and (ora.results[stale, 0] != 0).any(), "test needs stale non-zero cells"
+    assert np.array_equal(dly2[0], ora.delay)
+    for k in EXACT:
+        assert common.bit_equal(res2[0][:, k], ora.results[:, k]).all(), common.FIELDS[k]
+    ok2 = common.bit_equal(res2[0][:, 2], ora.results[:, 2]) | (np.isnan(res2[0][:, 2]) & np.isnan(ora.results[:, 2]))
+    assert ok2.all()
+    assert common.rel_err(res2[0][:, 3], ora.results[:, 3]).max() <= LOWPASS_RTOL
+    # removing everything returns to the empty-grid solution
+    for b in boxes[1:] + [new]:
+        gpu.remove_aabb(*b)
+    gpu.clear_results(0)
+    res3, dly3 = gpu.solve([B])
+    empty = pv.Scene(25.0, 25.0, 275, T=60, efree=float(gpu.efree))
+    res4, dly4 = empty.solve([B])
+    assert np.array_equal(dly3, dly4) and np.array_equal(res3.view(np.uint32), res4.view(np.uint32))
+    gpu.close(); empty.close()
+
+
+def test_full_size_fused_equals_baseline_kernel(pv, scenes):
+    """BASELINE.json configs[2] grid and step count (1024x1024, 4000 steps), one source: the temporally blocked
+    register-tiled kernel and the two-launch baseline kernel are independent device formulations and must
+    agree bit for bit on fields and on every analyzer output; plus determinism of a second run."""
+    size, scale = common.scaled_config(1024)
+    L = [common.listeners_for(1, scale)[0]]
+    boxes = common.boxes_of(scenes, "BigRoom", scale)
+    out = []
+    for sk in (0, 1):
+        sc = pv.Scene(size, size, 275, T=4000, max_sources=1, step_kernel=sk, efree=0.0447895788)
+        for b in boxes:
+            sc.add_aabb(*b)
+        res, dly = sc.solve(L)
+        planes = [sc.pressure(t) for t in (3, 1000, 3999)]
+        state = sc.state()
+        if sk == 0:
+            res_again, dly_again = sc.solve(L)
+            assert np.array_equal(res.view(np.uint32), res_again.view(np.uint32)) and np.array_equal(dly, dly_again)
+        out.append((res, dly, planes, state))
+        sc.close()
+    (r0, d0, p0, s0), (r1, d1, p1, s1) = out
+    assert np.array_equal(d0, d1)
+    assert (d0 < 3e38).sum() > 0.1 * d0.size          # BigRoom is a closed room: the wave never leaves it
+    assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32))
+    for a, b in zip(p0 + list(s0), p1 + list(s1)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # physical sanity at full size: outputs finite where an onset exists, unit vectors are unit
+    valid = d0[0] < 3e38
+    assert np.isfinite(r0[0][valid][:, [0, 1, 3]]).all()
+    norm = np.hypot(r0[0][valid, 6], r0[0][valid, 7])
+    assert np.allclose(norm[norm > 0], 1.0, atol=1e-5)
+
+
+def test_rt60_tolerance_at_long_response(pv, scenes):
+    """RT60 is the only output that is not bit-exact; check it at a long response (T=4000) against the oracle."""
+    gpu, ora, Ls = run_pair(pv, scenes, "Shoebox", n=200, T=4000)
+    res, dly = gpu.solve(Ls)
+    ora.generate(Ls[0]); ora.analyze(Ls[0])
+    worst = assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    print(f"T=4000 rt60 max rel err {worst:.2e}")
+    gpu.close()

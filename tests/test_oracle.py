@@ -151,3 +151,59 @@ def test_no_onset_cells_keep_stale_results():
     sim.generate(L); sim.analyze(L)
     far = (sim.gx - 1) * sim.gx + (sim.gy - 1)
     assert sim.delay[far] > 3e38 and (sim.results[far, [0, 1, 2, 3, 6, 7]] == 123.0).all()
+
+
+def test_device_log10f_recipe_matches_libm():
+    """planeverb_b200/csrc/pvc_analyze.cu reproduces glibc's log10f (fdlibm wrapper around the table-driven
+    double-precision logf kernel) so that RT60 is bit-exact.  Re-evaluate that recipe here in numpy, with the
+    table constants parsed out of the .cu source, and compare with the libm this oracle links."""
+    import ctypes as C
+    import os
+    import re
+    src = open(os.path.join(common.ROOT, "planeverb_b200", "csrc", "pvc_analyze.cu")).read()
+    body = src[src.index("kLogfTable[16]"):]
+    body = body[:body.index("};")]
+    vals = [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+", body)]
+    assert len(vals) == 32
+    tab = np.array(vals).reshape(16, 2)
+    ln2 = float.fromhex("0x1.62e42fefa39efp-1")
+    A = [float.fromhex(v) for v in ("-0x1.00ea348b88334p-2", "0x1.5575b0be00b6ap-2", "-0x1.ffffef20a4123p-2")]
+    for v in ("0x1.62e42fefa39efp-1", "-0x1.00ea348b88334p-2", "0x1.5575b0be00b6ap-2", "-0x1.ffffef20a4123p-2"):
+        assert v in src
+
+    def logf(x):
+        ix = x.view(np.uint32).astype(np.int64)
+        tmp = (ix - 0x3f330000) & 0xffffffff
+        i = (tmp >> 19) & 15
+        k = tmp.astype(np.uint32).view(np.int32) >> 23
+        iz = (ix - (tmp & 0xff800000)) & 0xffffffff
+        z = iz.astype(np.uint32).view(np.float32).astype(np.float64)
+        r = z * tab[i, 0] - 1.0
+        y0 = tab[i, 1] + k.astype(np.float64) * ln2
+        r2 = r * r
+        y = A[1] * r + A[2]
+        y = A[0] * r2 + y
+        y = y * r2 + (y0 + r)
+        out = y.astype(np.float32)
+        out[x == np.float32(1.0)] = 0.0
+        return out
+
+    def log10f(x):
+        f32 = np.float32
+        hx = x.view(np.int32).astype(np.int64)
+        k = (hx >> 23) - 127
+        i = (k < 0).astype(np.int64)
+        m = ((hx & 0x007fffff) | ((0x7f - i) << 23)).astype(np.uint32).view(np.float32)
+        y = (k + i).astype(np.float32)
+        z = (y * f32(7.9034151668e-07)).astype(f32) + (f32(4.3429449201e-01) * logf(m)).astype(f32)
+        return (z.astype(f32) + (y * f32(3.0102920532e-01)).astype(f32)).astype(f32)
+
+    libm = C.CDLL("libm.so.6")
+    libm.log10f.restype = C.c_float
+    libm.log10f.argtypes = [C.c_float]
+    rng = np.random.default_rng(3)
+    x = np.concatenate([(10.0 ** rng.uniform(-37, 4, 60000)).astype(np.float32),
+                        np.float32([1.0, 0.5, 2.0, 10.0, 1e-30, 0.99999994, 1.0000001])])
+    want = np.array([libm.log10f(float(v)) for v in x], np.float32)
+    got = log10f(x)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -144,6 +144,9 @@ PVC_API int  pvc_mark(pvc_solver* s, int which);
 PVC_API int  pvc_mark_elapsed(pvc_solver* s, float* ms);
 /* device-resident raw pointers for zero-copy consumers (results_dev: gx*gy*8 floats of a source) */
 PVC_API const float* pvc_results_dev(pvc_solver* s, int source);
+/* debug/profiling aid: runs a few 4-step launches and returns, per CTA of the last one, 8 %globaltimer stamps
+ * (start, tile loaded, after each of the 4 steps, stores issued); returns the number of CTAs or a negative... >= 0 ok */
+PVC_API int  pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out, int maxBlocks);
 /* page-locked host buffers for the result grids (plain malloc'd memory works too, just slower to copy) */
 PVC_API void* pvc_host_alloc(size_t bytes);
 PVC_API void  pvc_host_free(void* p);

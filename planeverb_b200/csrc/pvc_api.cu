@@ -176,7 +176,7 @@ size_t pvc_memory_requirement(const pvc_config* cfg)
     if (!validConfig(cfg)) return 0;
     const Layout L = makeLayout(*cfg);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + L.plane + S * L.hist_source + (size_t)cfg->T +
+    return sizeof(float) * (6 * S * L.plane + 4 * L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 10 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
@@ -195,6 +195,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     s->cfg = *cfg;
     s->device = cfg->device;
     s->L = makeLayout(*cfg);
+    { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device); s->numSMs = sms > 0 ? sms : 148; }
     const Layout& L = s->L;
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
     #define PVC_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                              \
@@ -210,7 +211,9 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
             PVC_TRY(cudaMemsetAsync(s->state[b][f], 0, sizeof(float) * S * L.plane, s->stream));
         }
     PVC_TRY(cudaMalloc(&s->w, sizeof(float) * L.plane));
+    for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->coef[f], sizeof(float) * L.plane));
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
+    PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
@@ -235,7 +238,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); cudaFree(s->slowMask); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 2; ++i) if (s->mark[i]) cudaEventDestroy(s->mark[i]);
@@ -475,6 +478,28 @@ const float* pvc_results_dev(pvc_solver* s, int source)
 {
     if (!s || source < 0 || source >= s->cfg.max_sources) return nullptr;
     return s->results + (size_t)source * s->cfg.gx * s->cfg.gy * 8;
+}
+
+int pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out, int maxBlocks)
+{
+    if (!s || !out || nsrc < 1 || nsrc > s->cfg.max_sources || s->cfg.step_kernel != 0) { setError("pvc_debug_timeline: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const int blocks = s->L.tiles_x * s->L.tiles_y * nsrc;
+    if (blocks > maxBlocks) { setError("pvc_debug_timeline: need room for %d blocks", blocks); return PVC_ERR_INVALID; }
+    unsigned long long* d = nullptr;
+    PVC_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * 8 * blocks));
+    PVC_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 8 * blocks, s->stream));
+    if (s->slowMaskDirty) { int rc = rebuildSlowMask(s); if (rc) return rc; }
+    int launches = 0;
+    // a few untimed launches to reach steady state, then one stamped launch (state keeps evolving, harmless)
+    int rc = launchFusedSteps(s, nsrc, 8, 20, s->hist, &launches);
+    s->timeline = d;
+    if (!rc) rc = launchFusedSteps(s, nsrc, 20, 24, s->hist, &launches);
+    s->timeline = nullptr;
+    if (!rc && (cudaMemcpyAsync(out, d, sizeof(unsigned long long) * 8 * blocks, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess)) { setError("pvc_debug_timeline: copy failed"); rc = PVC_ERR_CUDA; }
+    cudaFree(d);
+    return rc ? rc : blocks;
 }
 
 void* pvc_host_alloc(size_t bytes)

@@ -75,14 +75,17 @@ struct pvc_solver
     pvc_config cfg;
     pvc::Layout L;
     int device;
+    int numSMs;
     cudaStream_t stream;
     cudaEvent_t ev[4];
     cudaEvent_t mark[2];
 
     float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
-    float* w;                // coefficient plane
+    float* w;                // wall plane (air flag / admittance), the geometry's source of truth
+    float* coef[3];          // general-path coefficient planes bp, gx, gy derived from w (pvc_step_fused.cu)
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
     int slowMaskDirty;
+    int* tileOrder;          // tiles_x*tiles_y tile ids, most expensive first
     float* hist;             // max_sources * T * hist_plane
     float* pulse;            // T floats
     float* results;          // max_sources * gx*gy*8
@@ -95,6 +98,7 @@ struct pvc_solver
     int lastSources;
     float lastMs[3];
     int lastLaunches;
+    unsigned long long* timeline;   // debug only
 };
 
 namespace pvc

@@ -26,71 +26,55 @@
 //
 // Roofline: with the state L2-resident between launches the kernel is bound by instruction issue and by
 // the history write stream to HBM; see DESIGN.md for the byte accounting.
+#include <algorithm>
+#include <utility>
+#include <vector>
 #include "pvc_internal.h"
 
 namespace pvc
 {
     __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
 
-    // general velocity rule (FDTD.cpp:149-168 in branch form), written as selects so the general path stays
-    // straight-line code
-    __device__ __forceinline__ float ruleF(float v, float pThis, float pPrev, float wThis, float wPrev, float courant)
-    {
-        const bool aThis = isAirF(wThis), aPrev = isAirF(wPrev);
-        const float airAir = __fsub_rn(v, __fmul_rn(courant, __fsub_rn(pThis, pPrev)));
-        const float wallThis = __fmul_rn(wThis, pPrev);
-        const float wallPrev = -__fmul_rn(wPrev, pThis);
-        const float ifAirThis = aPrev ? airAir : wallPrev;
-        const float ifWallThis = aPrev ? wallThis : 0.f;
-        return aThis ? ifAirThis : ifWallThis;
-    }
-
     struct FusedArgs
     {
         const float* inP; const float* inVx; const float* inVy;
         float* outP; float* outVx; float* outVy;
-        const float* w;
+        const float* coefBp; const float* coefGx; const float* coefGy;   // general-path coefficient planes
         const uint32_t* slowMask;
+        const int* tileOrder;      // tiles of one source sorted by estimated cost, most expensive first
+        int tilesPerSource, nsrc;
         float* hist;               // pressure history of source 0 (null: no record)
         const SourceParams* src;
         const float* pulse;
         int t0, nsteps;
         float courant;
+        unsigned long long* timeline;   // debug: 8 globaltimer stamps per CTA (pvc_debug_timeline), else null
     };
 
-    template <int NW, int R, int MINB>
-    __global__ void __launch_bounds__(NW * 32, MINB)
-    fusedStepKernel(const Layout L, const FusedArgs A)
+    // Everything after the tile's state is in registers: K sub-steps, history append, injection, state store.
+    // sVxTop / sPBot: (NW+1) x 32 float4 each; row NW of sVxTop and row 0 of sPBot stay zero (the tile's bottom /
+    // top neighbours, halo of the halo).
+    __device__ __forceinline__ void stamp(const FusedArgs& A, int slot)
     {
-        // row NW of sVxTop and row 0 of sPBot stay zero: the tile's bottom / top neighbours (halo of the halo)
-        __shared__ float4 sVxTop[NW + 1][32];   // [w]   = vx of warp w's first row (read by warp w-1)
-        __shared__ float4 sPBot[NW + 1][32];    // [w+1] = p of warp w's last row  (read by warp w+1)
+        if (A.timeline && threadIdx.x == 0)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.timeline[(size_t)blockIdx.x * 8 + slot] = t;
+        }
+    }
 
+    template <int NW, int R>
+    __device__ __forceinline__ void computeTile(const Layout& L, const FusedArgs& A, const int tx, const int ty, const int s,
+                                                float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
+                                                float4 (*sVxTop)[32], float4 (*sPBot)[32])
+    {
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
-        const int tx = blockIdx.x, ty = blockIdx.y, s = blockIdx.z;
-        // domain coordinates of this thread's first cell (may be negative / beyond the grid: guard band)
         const int rBase = ty * L.valid_rows - kTileK + wp * R;
         const int cBase = tx * kValidCols - kGuardCols + lane * 4;
         const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
         const size_t src0 = (size_t)s * L.plane + cell0;
-
-        float p[R][4], vx[R][4], vy[R][4];
-        {
-            const float* gp = A.inP + src0;
-            const float* gx = A.inVx + src0;
-            const float* gy = A.inVy + src0;
-            #pragma unroll
-            for (int j = 0; j < R; ++j)
-            {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(gp + (size_t)j * L.pitch));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(gx + (size_t)j * L.pitch));
-                const float4 c = __ldg(reinterpret_cast<const float4*>(gy + (size_t)j * L.pitch));
-                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
-                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
-                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
-            }
-        }
 
         // warp-uniform path choice (so the shuffles below never sit in divergent code):
         //   0 fast    every cell of the warp, and each one's up/left neighbour, is interior air
@@ -132,13 +116,9 @@ namespace pvc
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
                  + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
 
-        if (wp == 0)
-        {
-            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
         __syncthreads();
+        stamp(A, 1);
 
         #pragma unroll 1
         for (int step = 0; step < A.nsteps; ++step)
@@ -185,22 +165,22 @@ namespace pvc
                 }
                 else
                 {
-                    const float* wrow = A.w + cell0;
+                    const float* bpRow = A.coefBp + cell0;
                     #pragma unroll
                     for (int j = 0; j < R; ++j)
                     {
                         const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)j * L.pitch));
-                        const float wa[4] = { w4.x, w4.y, w4.z, w4.w };
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
+                        const float ba[4] = { b4.x, b4.y, b4.z, b4.w };
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
                             const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
                             const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
                             const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
-                            p[j][k] = isAirF(wa[k]) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
+                            p[j][k] = (ba[k] != 0.f) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
                         }
-                        asm volatile("" ::: "memory");      // keep the general path row-by-row: low register pressure
+                        if (j & 1) asm volatile("" ::: "memory");   // bound how far coefficient loads are hoisted (register pressure)
                     }
                 }
             }
@@ -257,40 +237,36 @@ namespace pvc
                 }
                 else
                 {
-                    // the row above / column left of the very first tile row / column lies outside the allocation
-                    const bool haveUp = (rBase + kGuardRows) > 0, haveLeft = (cBase + kGuardCols) > 0;
-                    const float* wrow = A.w + cell0;
-                    float4 wPrevRow = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (haveUp) wPrevRow = __ldg(reinterpret_cast<const float4*>(wrow - L.pitch));
+                    // per-cell coefficient planes (buildCoefficientsKernel): every special case -- walls, the
+                    // absorbing grid edge, padding, guard band -- is data, the code is straight-line
+                    const float* bpRow = A.coefBp + cell0;
+                    const float* gxRow = A.coefGx + cell0;
+                    const float* gyRow = A.coefGy + cell0;
                     #pragma unroll
                     for (int j = 0; j < R; ++j)
                     {
                         const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
-                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)j * L.pitch));
-                        const float wLeft = haveLeft ? __ldg(wrow + (size_t)j * L.pitch - 1) : 0.f;
-                        const float wa[5] = { wLeft, w4.x, w4.y, w4.z, w4.w };
-                        const float wu[4] = { wPrevRow.x, wPrevRow.y, wPrevRow.z, wPrevRow.w };
-                        const int r = rBase + j;
-                        const bool rowDead = (r < 0) || (r > L.gx);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
+                        const float4 x4 = __ldg(reinterpret_cast<const float4*>(gxRow + (size_t)j * L.pitch));
+                        const float4 y4 = __ldg(reinterpret_cast<const float4*>(gyRow + (size_t)j * L.pitch));
+                        const float ba[4] = { b4.x, b4.y, b4.z, b4.w };
+                        const float ga[4] = { x4.x, x4.y, x4.z, x4.w };
+                        const float ha[4] = { y4.x, y4.y, y4.z, y4.w };
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
-                            const int cc = cBase + k;
                             const float pu = (j > 0) ? p[j - 1][k] : pa[k];
                             const float pl = (k > 0) ? p[j][k - 1] : pLeft;
                             const float pt = p[j][k];
-                            float nx = ruleF(vx[j][k], pt, pu, wa[k + 1], wu[k], C);
-                            float ny = ruleF(vy[j][k], pt, pl, wa[k + 1], wa[k], C);
-                            if (r == 0) nx = -pt;                                   // FDTD.cpp:208
-                            if (r == L.gx) nx = pu;                                 // FDTD.cpp:209
-                            if (cc == 0) ny = -pt;                                  // FDTD.cpp:220
-                            if (cc == L.gy) ny = pl;                                // FDTD.cpp:221
-                            if (rowDead || cc < 0 || cc >= L.gy) nx = 0.f;          // padding column / guard band
-                            if (rowDead || r == L.gx || cc < 0 || cc > L.gy) ny = 0.f;   // padding row / guard band
-                            vx[j][k] = nx; vy[j][k] = ny;
+                            const bool air = ba[k] != 0.f;
+                            const float airX = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
+                            const float airY = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
+                            const float wallX = __fmul_rn(ga[k], air ? pt : pu);
+                            const float wallY = __fmul_rn(ha[k], air ? pt : pl);
+                            vx[j][k] = (air && isAirF(ga[k])) ? airX : wallX;
+                            vy[j][k] = (air && isAirF(ha[k])) ? airY : wallY;
                         }
-                        wPrevRow = w4;
-                        asm volatile("" ::: "memory");
+                        if (j & 1) asm volatile("" ::: "memory");
                     }
                 }
             }
@@ -320,6 +296,7 @@ namespace pvc
             }
             sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
             __syncthreads();
+            stamp(A, 2 + step);
         }
 
         // ---------------- store the owned cells of the new state ----------------
@@ -338,6 +315,205 @@ namespace pvc
                 }
             }
         }
+        __syncthreads();
+        stamp(A, 6);
+    }
+
+    // One tile per CTA, state loaded straight from global memory into registers.
+    template <int NW, int R, int MINB>
+    __global__ void __launch_bounds__(NW * 32, MINB)
+    fusedStepKernel(const Layout L, const FusedArgs A)
+    {
+        __shared__ float4 sVxTop[NW + 1][32];   // [w]   = vx of warp w's first row (read by warp w-1)
+        __shared__ float4 sPBot[NW + 1][32];    // [w+1] = p of warp w's last row  (read by warp w+1)
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        // 1-D grid in longest-first order: CTAs are dispatched in blockIdx order, so the expensive tiles (walls:
+        // general path) start in the first wave instead of forming the kernel's tail
+        const int s = blockIdx.x % A.nsrc;
+        const int tileId = A.tileOrder[blockIdx.x / A.nsrc];
+        const int ty = tileId / L.tiles_x, tx = tileId - ty * L.tiles_x;
+        const int rBase = ty * L.valid_rows - kTileK + wp * R;
+        const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+        const size_t src0 = (size_t)s * L.plane + (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
+        stamp(A, 0);
+
+        float p[R][4], vx[R][4], vy[R][4];
+        {
+            const float* gp = A.inP + src0;
+            const float* gx = A.inVx + src0;
+            const float* gy = A.inVy + src0;
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(gp + (size_t)j * L.pitch));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(gx + (size_t)j * L.pitch));
+                const float4 c = __ldg(reinterpret_cast<const float4*>(gy + (size_t)j * L.pitch));
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
+        }
+
+        if (wp == 0)
+        {
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        computeTile<NW, R>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot);
+    }
+
+    // ---- persistent variant: TMA bulk-copy prefetch of the next tile through shared memory ----------------
+    // One CTA per SM walks tiles b, b+G, b+2G, ...  While it steps tile i in registers, the TMA engine
+    // (cp.async.bulk global->shared, mbarrier complete_tx) lands the 3*TR 512-byte rows of tile i+1 in a
+    // shared-memory stage; switching tiles is then 3R conflict-free LDS.128 per thread instead of a cold
+    // round trip to L2/HBM, and the stores of tile i drain while tile i+1 computes.  Without this every CTA of
+    // a launch loads, computes and stores in lockstep and the memory system idles during the compute phase.
+    __device__ __forceinline__ uint32_t smemAddr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+    __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+    }
+    __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred ready;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 ready, [%0], %1;\n"
+            "@ready bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+    }
+    __device__ __forceinline__ void bulkLoadRow(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+    {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+    }
+
+    template <int NW, int R>
+    __global__ void __launch_bounds__(NW * 32, 1)
+    fusedStepPersistentKernel(const Layout L, const FusedArgs A, const int numTiles)
+    {
+        constexpr int TR = NW * R;                          // tile rows incl. halo
+        constexpr uint32_t kRowBytes = kTileCols * sizeof(float);
+        extern __shared__ __align__(128) unsigned char smemRaw[];
+        float* stage = reinterpret_cast<float*>(smemRaw);                                   // [3][TR][128]
+        float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + 3 * TR * kRowBytes);
+        float4 (*sPBot)[32] = sVxTop + (NW + 1);
+        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        // issue the 3*TR row copies of a tile; thread i copies row i%TR of field i/TR
+        auto prefetch = [&](int tile) {
+            const int s = tile % A.nsrc, rem = A.tileOrder[tile / A.nsrc];
+            const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+            if (threadIdx.x == 0) mbarExpectTx(full, 3u * TR * kRowBytes);
+            for (int i = threadIdx.x; i < 3 * TR; i += NW * 32)
+            {
+                const int f = i / TR, row = i - f * TR;
+                const float* plane = (f == 0) ? A.inP : (f == 1 ? A.inVx : A.inVy);
+                const float* src = plane + (size_t)s * L.plane + (size_t)(ty * L.valid_rows + row) * L.pitch + (size_t)tx * kValidCols;
+                bulkLoadRow(stage + (size_t)i * kTileCols, src, kRowBytes, full);
+            }
+        };
+
+        if (threadIdx.x == 0) mbarInit(full, 1);
+        if (wp == 0)
+        {
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+
+        int tile = blockIdx.x;
+        if (tile < numTiles) prefetch(tile);
+        uint32_t parity = 0;
+        while (tile < numTiles)
+        {
+            const int s = tile % A.nsrc, rem = A.tileOrder[tile / A.nsrc];
+            const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
+
+            mbarWait(full, parity);
+            parity ^= 1u;
+            float p[R][4], vx[R][4], vy[R][4];
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const int row = wp * R + j;
+                const float4 a = *reinterpret_cast<const float4*>(stage + ((size_t)(0 * TR + row)) * kTileCols + lane * 4);
+                const float4 b = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + row)) * kTileCols + lane * 4);
+                const float4 c = *reinterpret_cast<const float4*>(stage + ((size_t)(2 * TR + row)) * kTileCols + lane * 4);
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
+            __syncthreads();                                   // every thread has drained the stage: refill it
+            const int next = tile + gridDim.x;
+            if (next < numTiles) prefetch(next);
+
+            computeTile<NW, R>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot);
+            tile = next;
+        }
+    }
+
+    // Per-cell coefficients of the general path, rebuilt after every geometry edit from the wall plane w.
+    // With bp = 1 for an interior air cell (reference b = 1) and 0 otherwise, the reference's three update
+    // rules (FDTD.cpp:125-223 incl. the grid-edge overrides) collapse to data:
+    //   p  <- bp ? p - C*div : 0
+    //   vx <- bp ? (gx == AIR ? vx - C*(p - p_up) : gx * p) : gx * p_up        (same for vy with p_left, gy)
+    // where gx is  AIR       interior air cell with an interior air cell above it
+    //              -Y_up     air cell under a wall            (reference: -(Y_n * p))
+    //              -1        air cell in row 0                (vx = -p, FDTD.cpp:208)
+    //              +Y_self   wall cell under an air cell      (reference: Y * p_prev)
+    //              +1        padding row gx                   (vx = p_up, FDTD.cpp:209)
+    //              0         everything else (wall under wall, padding column, guard band)
+    // Multiplying by +-1 or 0 and negating a product are exact, so the planes reproduce the branch form bit for bit.
+    __global__ void buildCoefficientsKernel(const Layout L, const float* __restrict__ w,
+                                            float* __restrict__ bp, float* __restrict__ gx, float* __restrict__ gy)
+    {
+        const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= L.plane) return;
+        const int r = (int)(i / L.pitch) - kGuardRows, c = (int)(i % L.pitch) - kGuardCols;
+        const float AIR = __uint_as_float(kAirBits);
+        const bool inRows = (r >= 0) && (r < L.gx), inCols = (c >= 0) && (c < L.gy);
+        const float wSelf = w[i];
+        const bool air = inRows && inCols && isAirF(wSelf);
+        float cx = 0.f, cy = 0.f;
+        if (inCols && r >= 0 && r <= L.gx)
+        {
+            if (r == 0) cx = air ? -1.f : 0.f;
+            else if (r == L.gx) cx = 1.f;
+            else
+            {
+                const float wUp = w[i - L.pitch];
+                const bool airUp = isAirF(wUp);
+                cx = air ? (airUp ? AIR : -wUp) : (airUp ? wSelf : 0.f);
+            }
+        }
+        if (inRows && c >= 0 && c <= L.gy)
+        {
+            if (c == 0) cy = air ? -1.f : 0.f;
+            else if (c == L.gy) cy = 1.f;
+            else
+            {
+                const float wLeft = w[i - 1];
+                const bool airLeft = isAirF(wLeft);
+                cy = air ? (airLeft ? AIR : -wLeft) : (airLeft ? wSelf : 0.f);
+            }
+        }
+        bp[i] = air ? 1.f : 0.f;
+        gx[i] = cx;
+        gy[i] = cy;
     }
 
     // path mode per (tile, warp), see fusedStepKernel: 0 fast, 1 edge, 2 general.  Only INTERIOR cells can be
@@ -369,8 +545,11 @@ namespace pvc
         if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = anyWall ? 2u : (anyEdge ? 1u : 0u);
     }
 
-    struct Variant { int nw, r, minBlocks; };
-    static const Variant kVariants[] = { {12, 8, 1}, {8, 8, 2}, {16, 4, 2}, {16, 8, 1}, {8, 4, 4}, {8, 8, 1}, {16, 4, 1} };
+    // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, persistent TMA-prefetch
+    struct Variant { int nw, r, minBlocks, persistent; };
+    static const Variant kVariants[] = { {20, 4, 1, 0}, {8, 8, 2, 0}, {16, 4, 2, 0}, {16, 8, 1, 0}, {8, 4, 4, 0}, {8, 8, 1, 0},
+                                         {16, 4, 1, 0}, {12, 8, 1, 0}, {8, 8, 1, 1}, {14, 8, 1, 1},
+                                         {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -379,29 +558,65 @@ namespace pvc
         return kVariants[variant].nw * kVariants[variant].r;
     }
 
+    static FusedArgs makeArgs(pvc_solver* s, float* hist, int t, int t1)
+    {
+        FusedArgs A;
+        float** in = s->state[s->cur];
+        float** out = s->state[s->cur ^ 1];
+        A.inP = in[0]; A.inVx = in[1]; A.inVy = in[2];
+        A.outP = out[0]; A.outVx = out[1]; A.outVy = out[2];
+        A.coefBp = s->coef[0]; A.coefGx = s->coef[1]; A.coefGy = s->coef[2]; A.slowMask = s->slowMask; A.tileOrder = s->tileOrder; A.tilesPerSource = s->L.tiles_x * s->L.tiles_y;
+        A.hist = hist;
+        A.src = s->src; A.pulse = s->pulse;
+        A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
+        A.courant = s->cfg.courant;
+        A.timeline = s->timeline;
+        return A;
+    }
+
     template <int NW, int R, int MINB>
     static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
-        dim3 grid(L.tiles_x, L.tiles_y, nsrc), block(NW * 32);
+        dim3 grid(L.tiles_x * L.tiles_y * nsrc), block(NW * 32);
         for (int t = t0; t < t1; t += kTileK)
         {
-            FusedArgs A;
-            float** in = s->state[s->cur];
-            float** out = s->state[s->cur ^ 1];
-            A.inP = in[0]; A.inVx = in[1]; A.inVy = in[2];
-            A.outP = out[0]; A.outVx = out[1]; A.outVy = out[2];
-            A.w = s->w; A.slowMask = s->slowMask;
-            A.hist = hist;
-            A.src = s->src; A.pulse = s->pulse;
-            A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
-            A.courant = s->cfg.courant;
+            FusedArgs A = makeArgs(s, hist, t, t1);
+            A.nsrc = nsrc;
             fusedStepKernel<NW, R, MINB><<<grid, block, 0, s->stream>>>(L, A);
             s->cur ^= 1;
             *launches += 1;
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    template <int NW, int R>
+    static int launchPersistent(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
+    {
+        const Layout& L = s->L;
+        constexpr int TR = NW * R;
+        const size_t smem = (size_t)3 * TR * kTileCols * sizeof(float) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 16;
+        static bool configured[64] = {};
+        if (!configured[s->device & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(fusedStepPersistentKernel<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { setError("persistent kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            configured[s->device & 63] = true;
+        }
+        const int numTiles = L.tiles_x * L.tiles_y * nsrc;
+        const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;
+        for (int t = t0; t < t1; t += kTileK)
+        {
+            FusedArgs A = makeArgs(s, hist, t, t1);
+            A.nsrc = nsrc;
+            fusedStepPersistentKernel<NW, R><<<grid, NW * 32, smem, s->stream>>>(L, A, numTiles);
+            s->cur ^= 1;
+            *launches += 1;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("persistent fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         return PVC_OK;
     }
 
@@ -412,30 +627,68 @@ namespace pvc
         slowMaskKernel<NW, R, MINB><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->slowMask);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("slow mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        // tile order, most expensive first (general-path warps cost ~3x, edge-path ~1.3x a fast warp)
+        const int tiles = L.tiles_x * L.tiles_y;
+        std::vector<uint32_t> modes((size_t)tiles * 32);
+        if (cudaMemcpyAsync(modes.data(), s->slowMask, sizeof(uint32_t) * modes.size(), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s->stream) != cudaSuccess)
+        { setError("slow mask readback: %s", cudaGetErrorString(cudaGetLastError())); return PVC_ERR_CUDA; }
+        std::vector<std::pair<int, int>> cost((size_t)tiles);
+        for (int t = 0; t < tiles; ++t)
+        {
+            int c = 0;
+            for (int wIdx = 0; wIdx < NW; ++wIdx) { const uint32_t m = modes[(size_t)t * 32 + wIdx]; c += (m == 2u) ? 30 : (m == 1u ? 13 : 10); }
+            cost[(size_t)t] = std::make_pair(-c, t);
+        }
+        std::sort(cost.begin(), cost.end());
+        std::vector<int> order((size_t)tiles);
+        for (int t = 0; t < tiles; ++t) order[(size_t)t] = cost[(size_t)t].second;
+        if (cudaMemcpyAsync(s->tileOrder, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s->stream) != cudaSuccess)
+        { setError("tile order upload: %s", cudaGetErrorString(cudaGetLastError())); return PVC_ERR_CUDA; }
         s->slowMaskDirty = 0;
         return PVC_OK;
     }
 
-    #define PVC_DISPATCH(fn, ...)                                             \
-        switch (v) {                                                          \
-            case 1: return fn<8, 8, 2>(__VA_ARGS__);                          \
-            case 2: return fn<16, 4, 2>(__VA_ARGS__);                         \
-            case 3: return fn<16, 8, 1>(__VA_ARGS__);                         \
-            case 4: return fn<8, 4, 4>(__VA_ARGS__);                          \
-            case 5: return fn<8, 8, 1>(__VA_ARGS__);                          \
-            case 6: return fn<16, 4, 1>(__VA_ARGS__);                         \
-            default: return fn<12, 8, 1>(__VA_ARGS__);                        \
-        }
-
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
-        PVC_DISPATCH(launchVariant, s, nsrc, t0, t1, hist, launches)
+        switch (v)
+        {
+            case 1: return launchVariant<8, 8, 2>(s, nsrc, t0, t1, hist, launches);
+            case 2: return launchVariant<16, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 3: return launchVariant<16, 8, 1>(s, nsrc, t0, t1, hist, launches);
+            case 4: return launchVariant<8, 4, 4>(s, nsrc, t0, t1, hist, launches);
+            case 5: return launchVariant<8, 8, 1>(s, nsrc, t0, t1, hist, launches);
+            case 6: return launchVariant<16, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 7: return launchVariant<12, 8, 1>(s, nsrc, t0, t1, hist, launches);
+            case 8: return launchPersistent<8, 8>(s, nsrc, t0, t1, hist, launches);
+            case 9: return launchPersistent<14, 8>(s, nsrc, t0, t1, hist, launches);
+            case 10: return launchVariant<24, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 11: return launchVariant<16, 6, 1>(s, nsrc, t0, t1, hist, launches);
+            case 12: return launchVariant<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 13: return launchPersistent<24, 4>(s, nsrc, t0, t1, hist, launches);
+            case 14: return launchPersistent<16, 6>(s, nsrc, t0, t1, hist, launches);
+            case 15: return launchPersistent<12, 8>(s, nsrc, t0, t1, hist, launches);
+            default: return launchVariant<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
+        }
     }
 
     int rebuildSlowMask(pvc_solver* s)
     {
+        buildCoefficientsKernel<<<(unsigned)((s->L.plane + 255) / 256), 256, 0, s->stream>>>(s->L, s->w, s->coef[0], s->coef[1], s->coef[2]);
         int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
-        PVC_DISPATCH(maskVariant, s)
+        switch (kVariants[v].nw * 100 + kVariants[v].r)
+        {
+            case 808: return maskVariant<8, 8, 1>(s);
+            case 1604: return maskVariant<16, 4, 1>(s);
+            case 1608: return maskVariant<16, 8, 1>(s);
+            case 804: return maskVariant<8, 4, 1>(s);
+            case 1408: return maskVariant<14, 8, 1>(s);
+            case 2404: return maskVariant<24, 4, 1>(s);
+            case 1606: return maskVariant<16, 6, 1>(s);
+            case 2004: return maskVariant<20, 4, 1>(s);
+            default: return maskVariant<12, 8, 1>(s);
+        }
     }
 }

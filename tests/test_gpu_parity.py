@@ -91,7 +91,7 @@ def test_golden_vectors(pv, name):
     gpu.close()
 
 
-@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6)])
+@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 7), (0, 8), (0, 9), (0, 10), (0, 11), (0, 12), (0, 13), (0, 14), (0, 15)])
 def test_every_step_kernel_variant_matches_oracle(pv, scenes, step_kernel, variant):
     gpu, ora, Ls = run_pair(pv, scenes, "FloorPlanScene", n=250, T=301, step_kernel=step_kernel, variant=variant)
     res, dly = gpu.solve(Ls)
@@ -265,7 +265,7 @@ def test_full_size_fused_equals_baseline_kernel(pv, scenes):
     assert (d0 < 3e38).sum() > 0.1 * d0.size          # BigRoom is a closed room: the wave never leaves it
     assert np.array_equal(r0.view(np.uint32), r1.view(np.uint32))
     for a, b in zip(p0 + list(s0), p1 + list(s1)):
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert common.bit_equal(a, b).all()                 # identical up to the sign of exact zeros
     # physical sanity at full size: outputs finite where an onset exists, unit vectors are unit
     valid = d0[0] < 3e38
     assert np.isfinite(r0[0][valid][:, [0, 1, 3]]).all()

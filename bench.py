@@ -96,6 +96,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bench_listeners(k, scale):
+    """k distinct, deterministic listener positions inside BigRoom's room (so every rank of a weak-scaling run
+    gets statistically the same work): the Sandbox default (5, 0, 4) first, the rest on a fixed lattice walk."""
+    out = []
+    for i in range(k):
+        x = 5.0 if i == 0 else 2.0 + (i * 1.37) % 6.0
+        z = 4.0 if i == 0 else 2.0 + (i * 0.91) % 6.0
+        out.append((x * scale, 0.0, z * scale))
+    return out
+
+
 def scene_inputs(cfg):
     from tests import common
     scenes = common.load_scenes()
@@ -108,7 +119,7 @@ def run_reference_sample(steps, warmup, cfg=CPU_SAMPLE):
     the build container, else the plain-C port) on the host cores of this box, single thread: the
     reference has no active parallel region (Analyzer.cpp:73,90 commented out, FDTD.cpp has none)."""
     size, scale, boxes, common = scene_inputs(cfg)
-    listener = common.listeners_for(1, scale)[0]
+    listener = bench_listeners(1, scale)[0]
     from oracle import pvref
     kind = "reference"
     if pvref.available():
@@ -183,18 +194,20 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
-    from planeverb_b200 import pvcuda
+    from planeverb_b200 import pvcuda, sharding
     dist = None
+    tdev = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tdev = torch.device("cuda", local_rank)
+        dist.init_process_group("nccl", device_id=tdev)
     device = local_rank if world > 1 else 0
 
     size, scale, boxes, common = scene_inputs(cfg)
     S = cfg["sources"]
-    listeners = common.listeners_for(S * world, scale)[rank * S:(rank + 1) * S]
+    listeners = sharding.shard(bench_listeners(S * world, scale), world, rank)      # S sources on every rank
     emitters = [(x * scale, 0.0, z * scale) for (x, z) in common.EMITTERS]
     scene = pvcuda.Scene(size, size, cfg["resolution"], T=cfg["T"], max_sources=S, device=device,
                          step_kernel=args.step_kernel, variant=args.variant)
@@ -216,19 +229,13 @@ def main():
             torch.cuda.synchronize()
 
     def gather_outputs():
-        """the one exchange of the path: per-emitter acoustic parameters of every source, all ranks"""
+        """the one exchange of the path: per-emitter acoustic parameters of every source, all ranks (NCCL all-gather)"""
         out = np.zeros((S, len(emitters), 8), np.float32)
         for s in range(S):
             for e, pos in enumerate(emitters):
                 r = scene.lookup(pos, s)
                 out[s, e] = r if r is not None else -1.0
-        if dist is None:
-            return out[None]
-        import torch
-        mine = torch.from_numpy(out).cuda()
-        allv = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        return torch.stack(allv).cpu().numpy()
+        return np.concatenate(sharding.gather_outputs(out, dist, tdev))
 
     upload_geometry()
     # ---------------- device-resident timing (value) ----------------
@@ -267,12 +274,7 @@ def main():
     h2d = len(boxes) * 24 + S * 24
     d2h = res.nbytes + dly.nbytes + S * len(emitters) * 32
 
-    times = np.array([dev_ms / 1e3, e2e_s, step_ms / 1e3, ana_ms / 1e3], np.float64)
-    if dist is not None:
-        import torch
-        t = torch.from_numpy(times).cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        times = t.cpu().numpy()
+    times = sharding.max_over_ranks([dev_ms / 1e3, e2e_s, step_ms / 1e3, ana_ms / 1e3], dist, tdev)
     dev_s, e2e_s, step_s, ana_s = (float(v) for v in times)
     total_units = units_per_step * world * args.steps
 

@@ -1,0 +1,56 @@
+"""Multi-GPU sharding of the hot path: the independent units are listener positions
+("sources").  One process per GPU; every rank solves its own contiguous shard of the source list with no
+data-path collective, and the ranks exchange only the per-emitter acoustic parameters (8 floats per
+source x emitter) once at the end of a frame -- a single all-gather.
+
+torch.distributed is plumbing here (NCCL over NVLink on the GPUs, gloo in the CPU tests); the solve itself
+never sees a torch type.
+"""
+import numpy as np
+
+
+def shard_bounds(n_items, world, rank):
+    """Contiguous, balanced shard [lo, hi) of n_items for `rank` of `world` (first ranks take the remainder)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(items, world, rank):
+    lo, hi = shard_bounds(len(items), world, rank)
+    return list(items[lo:hi])
+
+
+def gather_outputs(local, dist=None, device=None):
+    """All-gather per-source outputs.  local: float32 array [n_local_sources, n_emitters, 8].
+    Returns the list of every rank's array, in rank order (shards may differ in length)."""
+    local = np.ascontiguousarray(local, np.float32)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [local]
+    import torch
+    world = dist.get_world_size()
+    dev = device if device is not None else torch.device("cpu")
+    count = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count)
+    most = max(int(c.item()) for c in counts)
+    padded = np.zeros((most,) + local.shape[1:], np.float32)
+    padded[:local.shape[0]] = local
+    mine = torch.from_numpy(padded).to(dev)
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    return [t.cpu().numpy()[:int(c.item())] for t, c in zip(everyone, counts)]
+
+
+def max_over_ranks(values, dist=None, device=None):
+    """Element-wise max of a small float64 vector over all ranks (timing: the job takes as long as its slowest rank)."""
+    values = np.asarray(values, np.float64)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return values
+    import torch
+    dev = device if device is not None else torch.device("cpu")
+    t = torch.from_numpy(values.copy()).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy()

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <float.h>
 #include "pvc_internal.h"
@@ -150,11 +151,48 @@ namespace pvc
         return PVC_OK;
     }
 
+    // The T/4 fused launches of a full solve are captured once per batch size into a CUDA graph and replayed:
+    // every kernel argument (ping-pong pointers, t0, work-counter slot) is a pure function of the launch index, and
+    // the buffers live as long as the solver.  The first solve of a batch size runs eagerly (it also performs the
+    // one-time function-attribute setup), the second captures, later ones replay.
     static int runSteps(pvc_solver* s, int nsrc, int T, int* launches)
     {
         if (s->cfg.step_kernel == 1) return launchBaselineSteps(s, nsrc, 0, T, s->hist, launches);
         if (s->slowMaskDirty) { int rc = rebuildSlowMask(s); if (rc) return rc; }
-        return launchFusedSteps(s, nsrc, 0, T, s->hist, launches);
+        const bool graphable = s->useGraphs && T == s->cfg.T && nsrc >= 1 && nsrc <= kMaxGraphBatch && s->cur == 0;
+        if (!graphable) return launchFusedSteps(s, nsrc, 0, T, s->hist, launches);
+        GraphSlot& g = s->graphs[nsrc];
+        if (g.exec)
+        {
+            cudaError_t e = cudaGraphLaunch(g.exec, s->stream);
+            if (e != cudaSuccess) { setError("cudaGraphLaunch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            s->cur = g.finalCur;
+            *launches += g.launches;
+            return PVC_OK;
+        }
+        if (g.seen++ == 0) return launchFusedSteps(s, nsrc, 0, T, s->hist, launches);
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        { cudaGetLastError(); s->useGraphs = 0; return launchFusedSteps(s, nsrc, 0, T, s->hist, launches); }
+        int captured = 0;
+        int rc = launchFusedSteps(s, nsrc, 0, T, s->hist, &captured);
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc || e != cudaSuccess || !graph)
+        {   // capture failed: fall back to eager launches for good
+            cudaGetLastError(); s->useGraphs = 0; s->cur = 0;
+            if (graph) cudaGraphDestroy(graph);
+            return launchFusedSteps(s, nsrc, 0, T, s->hist, launches);
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; s->useGraphs = 0; s->cur = 0; return launchFusedSteps(s, nsrc, 0, T, s->hist, launches); }
+        g.finalCur = s->cur; g.launches = captured;
+        s->cur = 0;
+        e = cudaGraphLaunch(g.exec, s->stream);
+        if (e != cudaSuccess) { setError("cudaGraphLaunch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        s->cur = g.finalCur;
+        *launches += g.launches;
+        return PVC_OK;
     }
 }
 
@@ -214,6 +252,8 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->coef[f], sizeof(float) * L.plane));
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
+    s->tileCounterCount = cfg->T / kTileK + 2;
+    PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
@@ -225,6 +265,8 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->src, sizeof(SourceParams) * S));
     #undef PVC_TRY
     s->efree = 1.f;
+    s->useGraphs = getenv("PVC_NO_GRAPHS") ? 0 : 1;
+    buildTensorMaps(s);
     int rc = launchClearGeometry(s);
     if (rc) { pvc_destroy(s); return rc; }
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) { setError("pvc_create: sync failed"); pvc_destroy(s); return PVC_ERR_CUDA; }
@@ -238,8 +280,9 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->tileCounters); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
+    for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 2; ++i) if (s->mark[i]) cudaEventDestroy(s->mark[i]);
     if (s->stream) cudaStreamDestroy(s->stream);

@@ -70,6 +70,12 @@ namespace pvc
     };
 }
 
+namespace pvc
+{
+    constexpr int kMaxGraphBatch = 16;
+    struct GraphSlot { cudaGraphExec_t exec; int finalCur, launches, seen; };
+}
+
 struct pvc_solver
 {
     pvc_config cfg;
@@ -86,6 +92,10 @@ struct pvc_solver
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
     int slowMaskDirty;
     int* tileOrder;          // tiles_x*tiles_y tile ids, most expensive first
+    int* tileCounters;       // one work counter per launch of the persistent TMA variant
+    int tileCounterCount;
+    alignas(64) unsigned char tensorMaps[6 * 128];   // CUtensorMap[2 ping-pong][3 fields] (128 B each)
+    int tmaReady, tmaTileRows;
     float* hist;             // max_sources * T * hist_plane
     float* pulse;            // T floats
     float* results;          // max_sources * gx*gy*8
@@ -99,6 +109,8 @@ struct pvc_solver
     float lastMs[3];
     int lastLaunches;
     unsigned long long* timeline;   // debug only
+    int useGraphs;
+    pvc::GraphSlot graphs[pvc::kMaxGraphBatch + 1];   // captured step-launch sequences, by batch size
 };
 
 namespace pvc
@@ -107,6 +119,7 @@ namespace pvc
     int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int rebuildSlowMask(pvc_solver* s);
+    int buildTensorMaps(pvc_solver* s);
     int fusedTileRows(int variant);
     // analyzer kernels (pvc_analyze.cu)
     int launchAnalyzer(pvc_solver* s, int nsrc, int* launches);

@@ -26,6 +26,8 @@
 //
 // Roofline: with the state L2-resident between launches the kernel is bound by instruction issue and by
 // the history write stream to HBM; see DESIGN.md for the byte accounting.
+#include <cuda.h>
+#include <cstdlib>
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -54,20 +56,20 @@ namespace pvc
     // Everything after the tile's state is in registers: K sub-steps, history append, injection, state store.
     // sVxTop / sPBot: (NW+1) x 32 float4 each; row NW of sVxTop and row 0 of sPBot stay zero (the tile's bottom /
     // top neighbours, halo of the halo).
-    __device__ __forceinline__ void stamp(const FusedArgs& A, int slot)
+    __device__ __forceinline__ void stamp(const FusedArgs& A, int slot, int idx = -1)
     {
         if (A.timeline && threadIdx.x == 0)
         {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            A.timeline[(size_t)blockIdx.x * 8 + slot] = t;
+            A.timeline[(size_t)(idx < 0 ? blockIdx.x : idx) * 8 + slot] = t;
         }
     }
 
-    template <int NW, int R>
+    template <int NW, int R, bool CS>
     __device__ __forceinline__ void computeTile(const Layout& L, const FusedArgs& A, const int tx, const int ty, const int s,
                                                 float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
-                                                float4 (*sVxTop)[32], float4 (*sPBot)[32])
+                                                float4 (*sVxTop)[32], float4 (*sPBot)[32], float4* sCoefArg, const int stampIdx = -1)
     {
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
@@ -85,6 +87,28 @@ namespace pvc
         const bool slow = mode == 2u;
         const bool edge = mode == 1u;
         const float C = A.courant;
+
+        // General-path warps stage their coefficient rows (bp, gx, gy) in shared memory once per launch with
+        // cp.async (no registers, all 3R copies in flight together); every thread later reads back only the
+        // float4s it copied itself, so cp.async.wait_group is the only synchronisation needed.
+        // sCoef layout: [plane][tile row][lane] float4.
+        constexpr int TR = NW * R;
+        float4* const sCoef = CS ? sCoefArg : nullptr;      // compile-time null without CS: the staging code folds away
+        if (CS && slow)
+        {
+            #pragma unroll
+            for (int f = 0; f < 3; ++f)
+            {
+                const float* plane = (f == 0 ? A.coefBp : (f == 1 ? A.coefGx : A.coefGy)) + cell0;
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sCoef + ((size_t)f * TR + wp * R + j) * 32 + lane);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(plane + (size_t)j * L.pitch) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         // column classes of this thread's 4 cells, one bit per k (only consulted on the edge path)
         uint32_t colOut = 0u, colPad = 0u, colLeft = 0u;
@@ -116,9 +140,10 @@ namespace pvc
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
                  + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
 
+        if (CS && slow) asm volatile("cp.async.wait_group 0;" ::: "memory");
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
         __syncthreads();
-        stamp(A, 1);
+        stamp(A, 1, stampIdx);
 
         #pragma unroll 1
         for (int step = 0; step < A.nsteps; ++step)
@@ -170,7 +195,8 @@ namespace pvc
                     for (int j = 0; j < R; ++j)
                     {
                         const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
+                        const float4 b4 = CS ? sCoef[((size_t)0 * TR + wp * R + j) * 32 + lane]
+                                                : __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
                         const float ba[4] = { b4.x, b4.y, b4.z, b4.w };
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -180,7 +206,7 @@ namespace pvc
                             const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
                             p[j][k] = (ba[k] != 0.f) ? __fsub_rn(p[j][k], __fmul_rn(C, div)) : 0.f;
                         }
-                        if (j & 1) asm volatile("" ::: "memory");   // bound how far coefficient loads are hoisted (register pressure)
+                        if (!CS && (j & 1)) asm volatile("" ::: "memory");   // global fallback: bound load hoisting (register pressure)
                     }
                 }
             }
@@ -246,9 +272,19 @@ namespace pvc
                     for (int j = 0; j < R; ++j)
                     {
                         const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
-                        const float4 x4 = __ldg(reinterpret_cast<const float4*>(gxRow + (size_t)j * L.pitch));
-                        const float4 y4 = __ldg(reinterpret_cast<const float4*>(gyRow + (size_t)j * L.pitch));
+                        float4 b4, x4, y4;
+                        if (CS)
+                        {
+                            b4 = sCoef[((size_t)0 * TR + wp * R + j) * 32 + lane];
+                            x4 = sCoef[((size_t)1 * TR + wp * R + j) * 32 + lane];
+                            y4 = sCoef[((size_t)2 * TR + wp * R + j) * 32 + lane];
+                        }
+                        else
+                        {
+                            b4 = __ldg(reinterpret_cast<const float4*>(bpRow + (size_t)j * L.pitch));
+                            x4 = __ldg(reinterpret_cast<const float4*>(gxRow + (size_t)j * L.pitch));
+                            y4 = __ldg(reinterpret_cast<const float4*>(gyRow + (size_t)j * L.pitch));
+                        }
                         const float ba[4] = { b4.x, b4.y, b4.z, b4.w };
                         const float ga[4] = { x4.x, x4.y, x4.z, x4.w };
                         const float ha[4] = { y4.x, y4.y, y4.z, y4.w };
@@ -266,7 +302,7 @@ namespace pvc
                             vx[j][k] = (air && isAirF(ga[k])) ? airX : wallX;
                             vy[j][k] = (air && isAirF(ha[k])) ? airY : wallY;
                         }
-                        if (j & 1) asm volatile("" ::: "memory");
+                        if (!CS && (j & 1)) asm volatile("" ::: "memory");
                     }
                 }
             }
@@ -296,7 +332,7 @@ namespace pvc
             }
             sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
             __syncthreads();
-            stamp(A, 2 + step);
+            stamp(A, 2 + step, stampIdx);
         }
 
         // ---------------- store the owned cells of the new state ----------------
@@ -316,11 +352,11 @@ namespace pvc
             }
         }
         __syncthreads();
-        stamp(A, 6);
+        stamp(A, 6, stampIdx);
     }
 
     // One tile per CTA, state loaded straight from global memory into registers.
-    template <int NW, int R, int MINB>
+    template <int NW, int R, int MINB, bool CS>
     __global__ void __launch_bounds__(NW * 32, MINB)
     fusedStepKernel(const Layout L, const FusedArgs A)
     {
@@ -361,7 +397,8 @@ namespace pvc
             sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        computeTile<NW, R>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot);
+        extern __shared__ __align__(16) float4 sCoefDyn[];        // [3][NW*R][32] float4
+        computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoefDyn);
     }
 
     // ---- persistent variant: TMA bulk-copy prefetch of the next tile through shared memory ----------------
@@ -443,6 +480,7 @@ namespace pvc
             const int s = tile % A.nsrc, rem = A.tileOrder[tile / A.nsrc];
             const int ty = rem / L.tiles_x, tx = rem - ty * L.tiles_x;
 
+            stamp(A, 0, tile);
             mbarWait(full, parity);
             parity ^= 1u;
             float p[R][4], vx[R][4], vy[R][4];
@@ -461,7 +499,103 @@ namespace pvc
             const int next = tile + gridDim.x;
             if (next < numTiles) prefetch(next);
 
-            computeTile<NW, R>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot);
+            computeTile<NW, R, false>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, nullptr, tile);
+            tile = next;
+        }
+    }
+
+    // ---- persistent, TMA-fed variant -------------------------------------------------------------------------
+    // One CTA per SM pulls tiles from a global counter (cost-sorted order, dynamic balancing).  While the CTA steps
+    // tile i in registers, ONE elected thread has already asked the TMA engine for tile i+1: three 3-D tensor copies
+    // (cp.async.bulk.tensor, box 128 x TR x 1 of the p / vx / vy planes) that complete on an mbarrier.  Switching
+    // tiles is then 3R conflict-free LDS.128 per thread.  General-path warps stage their coefficient rows in shared
+    // memory with cp.async (computeTile<.., CS = true>).
+    __device__ __forceinline__ void tmaLoadTile3d(void* dstSmem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+    {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smemAddr(dstSmem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar)) : "memory");
+    }
+
+    template <int NW, int R, bool CS>
+    __global__ void __launch_bounds__(NW * 32, 1)
+    fusedStepTmaKernel(const Layout L, const FusedArgs A, const int numTiles, int* __restrict__ tileCounter,
+                       const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapVx,
+                       const __grid_constant__ CUtensorMap mapVy)
+    {
+        constexpr int TR = NW * R;
+        constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
+        extern __shared__ __align__(128) unsigned char smemRaw[];
+        float* stage = reinterpret_cast<float*>(smemRaw);                                        // [3][TR][128]
+        float4* sCoef = reinterpret_cast<float4*>(smemRaw + 3 * kPlaneBytes);                  // [3][TR][32] (CS only)
+        unsigned char* tail = smemRaw + 3 * kPlaneBytes + (CS ? 3 * kPlaneBytes : 0);
+        float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(tail);
+        float4 (*sPBot)[32] = sVxTop + (NW + 1);
+        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));
+        volatile int* sNext = reinterpret_cast<volatile int*>(full + 1);
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+
+        auto decode = [&](int order, int& s, int& tx, int& ty) {
+            s = order % A.nsrc;
+            const int id = A.tileOrder[order / A.nsrc];
+            ty = id / L.tiles_x; tx = id - ty * L.tiles_x;
+        };
+        auto issue = [&](int order) {                           // thread 0 only
+            int s, tx, ty;
+            decode(order, s, tx, ty);
+            mbarExpectTx(full, 3u * kPlaneBytes);
+            tmaLoadTile3d(stage, &mapP, tx * kValidCols, ty * L.valid_rows, s, full);
+            tmaLoadTile3d(stage + (size_t)TR * kTileCols, &mapVx, tx * kValidCols, ty * L.valid_rows, s, full);
+            tmaLoadTile3d(stage + (size_t)2 * TR * kTileCols, &mapVy, tx * kValidCols, ty * L.valid_rows, s, full);
+        };
+
+        int pending = 0;                                        // thread 0: the tile index after next, fetched early
+        if (threadIdx.x == 0)
+        {
+            mbarInit(full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const int first = atomicAdd(tileCounter, 1);
+            *sNext = first;
+            if (first < numTiles) issue(first);
+            pending = atomicAdd(tileCounter, 1);
+        }
+        if (wp == 0)
+        {
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        int tile = *sNext;
+        uint32_t parity = 0;
+        while (tile < numTiles)
+        {
+            int s, tx, ty;
+            decode(tile, s, tx, ty);
+            stamp(A, 0, tile);
+            mbarWait(full, parity);
+            parity ^= 1u;
+            float p[R][4], vx[R][4], vy[R][4];
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const int row = wp * R + j;
+                const float4 a = *reinterpret_cast<const float4*>(stage + ((size_t)(0 * TR + row)) * kTileCols + lane * 4);
+                const float4 b = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + row)) * kTileCols + lane * 4);
+                const float4 c = *reinterpret_cast<const float4*>(stage + ((size_t)(2 * TR + row)) * kTileCols + lane * 4);
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
+            if (threadIdx.x == 0) *sNext = pending;
+            __syncthreads();                                   // stage drained by every thread; next index visible
+            const int next = *sNext;
+            if (threadIdx.x == 0)
+            {
+                if (next < numTiles) issue(next);
+                pending = atomicAdd(tileCounter, 1);
+            }
+            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile);
             tile = next;
         }
     }
@@ -547,9 +681,11 @@ namespace pvc
 
     // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, persistent TMA-prefetch
     struct Variant { int nw, r, minBlocks, persistent; };
-    static const Variant kVariants[] = { {20, 4, 1, 0}, {8, 8, 2, 0}, {16, 4, 2, 0}, {16, 8, 1, 0}, {8, 4, 4, 0}, {8, 8, 1, 0},
+    static const Variant kVariants[] = { {8, 6, 2, 0}, {8, 8, 2, 0}, {16, 4, 2, 0}, {16, 8, 1, 0}, {8, 4, 4, 0}, {8, 8, 1, 0},
                                          {16, 4, 1, 0}, {12, 8, 1, 0}, {8, 8, 1, 1}, {14, 8, 1, 1},
-                                         {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1} };
+                                         {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
+                                         {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
+                                         {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -571,19 +707,28 @@ namespace pvc
         A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
         A.courant = s->cfg.courant;
         A.timeline = s->timeline;
+        if (s->timeline) { static const char* dbg = getenv("PVC_DEBUG_NSTEPS"); if (dbg) A.nsteps = atoi(dbg); }   // debug: memory-floor probe
         return A;
     }
 
-    template <int NW, int R, int MINB>
+    template <int NW, int R, int MINB, bool CS = false>
     static int launchVariant(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
         dim3 grid(L.tiles_x * L.tiles_y * nsrc), block(NW * 32);
+        const size_t smem = CS ? (size_t)3 * NW * R * 32 * sizeof(float4) : 0;
+        static bool configured[64] = {};
+        if (!configured[s->device & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(fusedStepKernel<NW, R, MINB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { setError("fused kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            configured[s->device & 63] = true;
+        }
         for (int t = t0; t < t1; t += kTileK)
         {
             FusedArgs A = makeArgs(s, hist, t, t1);
             A.nsrc = nsrc;
-            fusedStepKernel<NW, R, MINB><<<grid, block, 0, s->stream>>>(L, A);
+            fusedStepKernel<NW, R, MINB, CS><<<grid, block, smem, s->stream>>>(L, A);
             s->cur ^= 1;
             *launches += 1;
         }
@@ -617,6 +762,71 @@ namespace pvc
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("persistent fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    template <int NW, int R, bool CS>
+    static int launchTma(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
+    {
+        const Layout& L = s->L;
+        constexpr int TR = NW * R;
+        if (!s->tmaReady || s->tmaTileRows != TR) { setError("TMA variant: tensor maps not built for %d-row tiles", TR); return PVC_ERR_INVALID; }
+        const size_t plane = (size_t)TR * kTileCols * sizeof(float);
+        const size_t smem = 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 32;
+        static bool configured[64] = {};
+        if (!configured[s->device & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(fusedStepTmaKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { setError("TMA kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            configured[s->device & 63] = true;
+        }
+        const int numTiles = L.tiles_x * L.tiles_y * nsrc;
+        const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;
+        const int nLaunch = (t1 - t0 + kTileK - 1) / kTileK;
+        if (nLaunch > s->tileCounterCount) { setError("TMA variant: %d launches exceed the counter pool", nLaunch); return PVC_ERR_INVALID; }
+        cudaMemsetAsync(s->tileCounters, 0, sizeof(int) * (size_t)nLaunch, s->stream);
+        int k = 0;
+        for (int t = t0; t < t1; t += kTileK, ++k)
+        {
+            FusedArgs A = makeArgs(s, hist, t, t1);
+            A.nsrc = nsrc;
+            const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(s->tensorMaps) + 3 * s->cur;
+            fusedStepTmaKernel<NW, R, CS><<<grid, NW * 32, smem, s->stream>>>(L, A, numTiles, s->tileCounters + k, m[0], m[1], m[2]);
+            s->cur ^= 1;
+            *launches += 1;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("TMA fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    // 3-D tensor maps {pitch, rows_alloc, sources} of the six state planes, box 128 x tileRows x 1 (driver entry point
+    // fetched through the runtime, no libcuda link)
+    int buildTensorMaps(pvc_solver* s)
+    {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+        { cudaGetLastError(); s->tmaReady = 0; return PVC_OK; }           // TMA variants unavailable; the default kernel does not need them
+        const Layout& L = s->L;
+        CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(s->tensorMaps);
+        for (int b = 0; b < 2; ++b)
+            for (int f = 0; f < 3; ++f)
+            {
+                const cuuint64_t dims[3] = { (cuuint64_t)L.pitch, (cuuint64_t)L.rows_alloc, (cuuint64_t)s->cfg.max_sources };
+                const cuuint64_t strides[2] = { (cuuint64_t)L.pitch * sizeof(float), (cuuint64_t)L.plane * sizeof(float) };
+                const cuuint32_t box[3] = { (cuuint32_t)kTileCols, (cuuint32_t)L.tile_rows, 1u };
+                const cuuint32_t estr[3] = { 1u, 1u, 1u };
+                const CUresult r = ((EncodeFn)fn)(&maps[b * 3 + f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->state[b][f], dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { s->tmaReady = 0; return PVC_OK; }
+            }
+        s->tmaReady = 1;
+        s->tmaTileRows = L.tile_rows;
         return PVC_OK;
     }
 
@@ -670,7 +880,18 @@ namespace pvc
             case 13: return launchPersistent<24, 4>(s, nsrc, t0, t1, hist, launches);
             case 14: return launchPersistent<16, 6>(s, nsrc, t0, t1, hist, launches);
             case 15: return launchPersistent<12, 8>(s, nsrc, t0, t1, hist, launches);
-            default: return launchVariant<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 16: return launchVariant<10, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 17: return launchVariant<12, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 18: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
+            case 19: return launchVariant<10, 6, 2>(s, nsrc, t0, t1, hist, launches);
+            case 20: return launchVariant<8, 6, 2, true>(s, nsrc, t0, t1, hist, launches);
+            case 21: return launchVariant<20, 4, 1, true>(s, nsrc, t0, t1, hist, launches);
+            case 22: return launchTma<16, 4, true>(s, nsrc, t0, t1, hist, launches);
+            case 23: return launchTma<12, 6, false>(s, nsrc, t0, t1, hist, launches);
+            case 24: return launchTma<20, 4, false>(s, nsrc, t0, t1, hist, launches);
+            case 25: return launchTma<16, 4, false>(s, nsrc, t0, t1, hist, launches);
+            case 26: return launchTma<12, 8, false>(s, nsrc, t0, t1, hist, launches);
+            default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }
 
@@ -688,6 +909,11 @@ namespace pvc
             case 2404: return maskVariant<24, 4, 1>(s);
             case 1606: return maskVariant<16, 6, 1>(s);
             case 2004: return maskVariant<20, 4, 1>(s);
+            case 1004: return maskVariant<10, 4, 1>(s);
+            case 1204: return maskVariant<12, 4, 1>(s);
+            case 806: return maskVariant<8, 6, 1>(s);
+            case 1006: return maskVariant<10, 6, 1>(s);
+            case 1206: return maskVariant<12, 6, 1>(s);
             default: return maskVariant<12, 8, 1>(s);
         }
     }

@@ -48,6 +48,19 @@ namespace pvc
         return L;
     }
 
+    // variant 0 = auto: the persistent TMA-fed kernel (16 warps x 4 rows, variant 22) once every SM gets at least
+    // four tiles per launch -- that is where its prefetch pipeline pays -- else the plain 8 x 6 kernel (variant 18),
+    // which has the lower latency on small grids / batches (measured on B200, profiles/)
+    static int resolveVariant(const pvc_config& c)
+    {
+        if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+        const int validRows = 16 * 4 - 2 * kTileK;
+        const long tiles = (long)((c.gy + 1 + kValidCols - 1) / kValidCols) * ((c.gx + 1 + validRows - 1) / validRows) * c.max_sources;
+        return tiles >= 4L * sms ? 22 : 18;
+    }
+
     static bool validConfig(const pvc_config* c)
     {
         return c && c->gx >= 2 && c->gy >= 2 && c->T >= 1 && c->fs > 0 && c->resolution > 0 && c->dx > 0.f &&
@@ -212,7 +225,8 @@ const char* pvc_last_error(void) { return g_error; }
 size_t pvc_memory_requirement(const pvc_config* cfg)
 {
     if (!validConfig(cfg)) return 0;
-    const Layout L = makeLayout(*cfg);
+    pvc_config r = *cfg; r.reserved = resolveVariant(*cfg);
+    const Layout L = makeLayout(r);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
     return sizeof(float) * (6 * S * L.plane + 4 * L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 10 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
@@ -231,8 +245,9 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     pvc_solver* s = new pvc_solver();
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
+    s->cfg.reserved = resolveVariant(*cfg);
     s->device = cfg->device;
-    s->L = makeLayout(*cfg);
+    s->L = makeLayout(s->cfg);
     { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device); s->numSMs = sms > 0 ? sms : 148; }
     const Layout& L = s->L;
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
@@ -251,6 +266,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->w, sizeof(float) * L.plane));
     for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->coef[f], sizeof(float) * L.plane));
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
+    PVC_TRY(cudaMemsetAsync(s->slowMask, 0, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));

@@ -567,6 +567,7 @@ namespace pvc
         }
         __syncthreads();
         int tile = *sNext;
+        __syncthreads();                                       // everyone has read the first index before thread 0 overwrites it
         uint32_t parity = 0;
         while (tile < numTiles)
         {

@@ -516,22 +516,23 @@ namespace pvc
                      ::"r"(smemAddr(dstSmem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar)) : "memory");
     }
 
-    template <int NW, int R, bool CS>
+    template <int NW, int R, bool CS, int NS>
     __global__ void __launch_bounds__(NW * 32, 1)
     fusedStepTmaKernel(const Layout L, const FusedArgs A, const int numTiles, int* __restrict__ tileCounter,
                        const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapVx,
                        const __grid_constant__ CUtensorMap mapVy)
     {
+        // NS = number of shared-memory stages = how many tiles ahead the TMA engine runs (1 or 2)
         constexpr int TR = NW * R;
         constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
         extern __shared__ __align__(128) unsigned char smemRaw[];
-        float* stage = reinterpret_cast<float*>(smemRaw);                                        // [3][TR][128]
-        float4* sCoef = reinterpret_cast<float4*>(smemRaw + 3 * kPlaneBytes);                  // [3][TR][32] (CS only)
-        unsigned char* tail = smemRaw + 3 * kPlaneBytes + (CS ? 3 * kPlaneBytes : 0);
+        float* stageBase = reinterpret_cast<float*>(smemRaw);                                    // [NS][3][TR][128]
+        float4* sCoef = reinterpret_cast<float4*>(smemRaw + NS * 3 * kPlaneBytes);             // [3][TR][32] (CS only)
+        unsigned char* tail = smemRaw + NS * 3 * kPlaneBytes + (CS ? 3 * kPlaneBytes : 0);
         float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(tail);
         float4 (*sPBot)[32] = sVxTop + (NW + 1);
-        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));
-        volatile int* sNext = reinterpret_cast<volatile int*>(full + 1);
+        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));                         // [NS]
+        volatile int* sQueue = reinterpret_cast<volatile int*>(full + NS);                      // [NS] tile index held by each stage
 
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
@@ -541,24 +542,28 @@ namespace pvc
             const int id = A.tileOrder[order / A.nsrc];
             ty = id / L.tiles_x; tx = id - ty * L.tiles_x;
         };
-        auto issue = [&](int order) {                           // thread 0 only
+        auto issue = [&](int order, int st) {                   // thread 0 only
             int s, tx, ty;
             decode(order, s, tx, ty);
-            mbarExpectTx(full, 3u * kPlaneBytes);
-            tmaLoadTile3d(stage, &mapP, tx * kValidCols, ty * L.valid_rows, s, full);
-            tmaLoadTile3d(stage + (size_t)TR * kTileCols, &mapVx, tx * kValidCols, ty * L.valid_rows, s, full);
-            tmaLoadTile3d(stage + (size_t)2 * TR * kTileCols, &mapVy, tx * kValidCols, ty * L.valid_rows, s, full);
+            float* stage = stageBase + (size_t)st * 3 * TR * kTileCols;
+            mbarExpectTx(full + st, 3u * kPlaneBytes);
+            tmaLoadTile3d(stage, &mapP, tx * kValidCols, ty * L.valid_rows, s, full + st);
+            tmaLoadTile3d(stage + (size_t)TR * kTileCols, &mapVx, tx * kValidCols, ty * L.valid_rows, s, full + st);
+            tmaLoadTile3d(stage + (size_t)2 * TR * kTileCols, &mapVy, tx * kValidCols, ty * L.valid_rows, s, full + st);
         };
 
-        int pending = 0;                                        // thread 0: the tile index after next, fetched early
         if (threadIdx.x == 0)
         {
-            mbarInit(full, 1);
+            #pragma unroll
+            for (int st = 0; st < NS; ++st) mbarInit(full + st, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const int first = atomicAdd(tileCounter, 1);
-            *sNext = first;
-            if (first < numTiles) issue(first);
-            pending = atomicAdd(tileCounter, 1);
+            #pragma unroll
+            for (int st = 0; st < NS; ++st)
+            {
+                const int t = atomicAdd(tileCounter, 1);
+                sQueue[st] = t;
+                if (t < numTiles) issue(t, st);
+            }
         }
         if (wp == 0)
         {
@@ -566,16 +571,19 @@ namespace pvc
             sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        int tile = *sNext;
-        __syncthreads();                                       // everyone has read the first index before thread 0 overwrites it
-        uint32_t parity = 0;
-        while (tile < numTiles)
+        int pending = 0;                                        // thread 0: next tile index, fetched one tile early
+        if (threadIdx.x == 0) pending = atomicAdd(tileCounter, 1);
+        int st = 0;
+        uint32_t parity = 0;                                    // parity of the stage-0 barrier; stage 1 flips on wrap too
+        while (true)
         {
+            const int tile = sQueue[st];
+            if (tile >= numTiles) break;                        // indices only grow: once a stage is empty every later one is
             int s, tx, ty;
             decode(tile, s, tx, ty);
             stamp(A, 0, tile);
-            mbarWait(full, parity);
-            parity ^= 1u;
+            mbarWait(full + st, parity);
+            const float* stage = stageBase + (size_t)st * 3 * TR * kTileCols;
             float p[R][4], vx[R][4], vy[R][4];
             #pragma unroll
             for (int j = 0; j < R; ++j)
@@ -588,16 +596,15 @@ namespace pvc
                 vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
                 vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
             }
-            if (threadIdx.x == 0) *sNext = pending;
-            __syncthreads();                                   // stage drained by every thread; next index visible
-            const int next = *sNext;
+            __syncthreads();                                   // stage drained by every thread (and sQueue[st] read): refill it
             if (threadIdx.x == 0)
             {
-                if (next < numTiles) issue(next);
+                sQueue[st] = pending;
+                if (pending < numTiles) issue(pending, st);
                 pending = atomicAdd(tileCounter, 1);
             }
-            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile);
-            tile = next;
+            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile);   // its barriers publish sQueue[st]
+            if (++st == NS) { st = 0; parity ^= 1u; }
         }
     }
 
@@ -686,7 +693,8 @@ namespace pvc
                                          {16, 4, 1, 0}, {12, 8, 1, 0}, {8, 8, 1, 1}, {14, 8, 1, 1},
                                          {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
                                          {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
-                                         {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2} };
+                                         {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
+                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -766,18 +774,18 @@ namespace pvc
         return PVC_OK;
     }
 
-    template <int NW, int R, bool CS>
+    template <int NW, int R, bool CS, int NS = 1>
     static int launchTma(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
         constexpr int TR = NW * R;
         if (!s->tmaReady || s->tmaTileRows != TR) { setError("TMA variant: tensor maps not built for %d-row tiles", TR); return PVC_ERR_INVALID; }
         const size_t plane = (size_t)TR * kTileCols * sizeof(float);
-        const size_t smem = 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 32;
+        const size_t smem = NS * 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 64;
         static bool configured[64] = {};
         if (!configured[s->device & 63])
         {
-            cudaError_t e = cudaFuncSetAttribute(fusedStepTmaKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(fusedStepTmaKernel<NW, R, CS, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { setError("TMA kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
             configured[s->device & 63] = true;
         }
@@ -792,7 +800,7 @@ namespace pvc
             FusedArgs A = makeArgs(s, hist, t, t1);
             A.nsrc = nsrc;
             const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(s->tensorMaps) + 3 * s->cur;
-            fusedStepTmaKernel<NW, R, CS><<<grid, NW * 32, smem, s->stream>>>(L, A, numTiles, s->tileCounters + k, m[0], m[1], m[2]);
+            fusedStepTmaKernel<NW, R, CS, NS><<<grid, NW * 32, smem, s->stream>>>(L, A, numTiles, s->tileCounters + k, m[0], m[1], m[2]);
             s->cur ^= 1;
             *launches += 1;
         }
@@ -892,6 +900,9 @@ namespace pvc
             case 24: return launchTma<20, 4, false>(s, nsrc, t0, t1, hist, launches);
             case 25: return launchTma<16, 4, false>(s, nsrc, t0, t1, hist, launches);
             case 26: return launchTma<12, 8, false>(s, nsrc, t0, t1, hist, launches);
+            case 27: return launchTma<16, 4, false, 2>(s, nsrc, t0, t1, hist, launches);
+            case 28: return launchTma<12, 4, false, 2>(s, nsrc, t0, t1, hist, launches);
+            case 29: return launchTma<10, 4, true, 2>(s, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }

@@ -91,7 +91,7 @@ def test_golden_vectors(pv, name):
     gpu.close()
 
 
-@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 7), (0, 8), (0, 9), (0, 10), (0, 11), (0, 12), (0, 13), (0, 14), (0, 15), (0, 16), (0, 18), (0, 20), (0, 22), (0, 23), (0, 24), (0, 25), (0, 26)])
+@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 7), (0, 8), (0, 9), (0, 10), (0, 11), (0, 12), (0, 13), (0, 14), (0, 15), (0, 16), (0, 18), (0, 20), (0, 22), (0, 23), (0, 24), (0, 25), (0, 26), (0, 27), (0, 28), (0, 29)])
 def test_every_step_kernel_variant_matches_oracle(pv, scenes, step_kernel, variant):
     gpu, ora, Ls = run_pair(pv, scenes, "FloorPlanScene", n=250, T=301, step_kernel=step_kernel, variant=variant)
     res, dly = gpu.solve(Ls)
@@ -281,3 +281,76 @@ def test_rt60_tolerance_at_long_response(pv, scenes):
     worst = assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
     print(f"T=4000 rt60 max rel err {worst:.2e}")
     gpu.close()
+
+
+def test_config4_hugeroom_2048_properties(pv, scenes):
+    """BASELINE.json configs[3] grid (2048x2048, HugeRoom.pv) at a bounded step count: the default (auto -> TMA
+    persistent) kernel against the two-launch baseline kernel bit for bit, two batched sources == their single
+    solves, and a CPU-oracle check of the first 120 steps on a 2048-wide pressure plane."""
+    size, scale = common.scaled_config(2048)
+    boxes = common.boxes_of(scenes, "HugeRoom", scale)
+    Ls = common.listeners_for(2, scale)
+    T = 600
+    fused = pv.Scene(size, size, 275, T=T, max_sources=2, efree=0.0447895788)
+    base = pv.Scene(size, size, 275, T=T, max_sources=1, step_kernel=1, efree=0.0447895788)
+    for b in boxes:
+        fused.add_aabb(*b); base.add_aabb(*b)
+    rf, df = fused.solve(Ls)
+    for i, L in enumerate(Ls):
+        base.clear_results(0)
+        rb, db = base.solve([L])
+        assert np.array_equal(db[0], df[i])
+        assert np.array_equal(rb[0].view(np.uint32), rf[i].view(np.uint32))
+        for t in (0, 3, 4, 299, T - 1):
+            assert common.bit_equal(base.pressure(t), fused.pressure(t, i)).all(), (i, t)
+    assert (df[0] < 3e38).sum() > 1000
+    fused.close(); base.close()
+    # oracle on the same 2048 grid, few steps (the pulse has travelled ~80 cells)
+    ora = pvoracle.OracleSim(size, size, 275, T=120, efree=0.0447895788)
+    gpu = pv.Scene(size, size, 275, T=120, max_sources=1, efree=0.0447895788)
+    for b in boxes:
+        ora.add_aabb(*b); gpu.add_aabb(*b)
+    res, dly = gpu.solve([Ls[0]])
+    ora.generate(Ls[0]); ora.analyze(Ls[0])
+    for t in (0, 5, 60, 119):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(2049, 2049)).all(), t
+    assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    gpu.close()
+
+
+def test_config5_dynamic_geometry_frames(pv, scenes):
+    """BASELINE.json configs[4] pattern: FloorPlanScene.pv with one AABB moved every frame (UpdateGeometry =
+    Remove(old) + Add(new) re-voxelised on the device) followed by a full solve; every frame must equal a fresh
+    scene built directly in that configuration, and the oracle on the last frame."""
+    n, T = 256, 300
+    size, scale = common.scaled_config(n)
+    boxes = common.boxes_of(scenes, "FloorPlanScene", scale)
+    L = common.listeners_for(1, scale)
+    live = pv.Scene(size, size, 275, T=T, efree=0.0447895788)
+    for b in boxes:
+        live.add_aabb(*b)
+    door = boxes[3]
+    cur = door
+    for frame in range(4):
+        moved = (door[0] + 0.4 * (frame + 1) * scale, door[1] - 0.3 * (frame + 1) * scale, door[2], door[3], door[4])
+        live.remove_aabb(*cur); live.add_aabb(*moved)
+        cur = moved
+        live.clear_results(0)
+        r_live, d_live = live.solve(L)
+        fresh = pv.Scene(size, size, 275, T=T, efree=0.0447895788)
+        ora = pvoracle.OracleSim(size, size, 275, T=T, efree=0.0447895788)
+        for b in boxes:
+            fresh.add_aabb(*b); ora.add_aabb(*b)
+        c2 = door
+        for k in range(frame + 1):      # the reference has no overlap ref-counting: replay the same edit history
+            m2 = (door[0] + 0.4 * (k + 1) * scale, door[1] - 0.3 * (k + 1) * scale, door[2], door[3], door[4])
+            fresh.remove_aabb(*c2); fresh.add_aabb(*m2)
+            ora.remove_aabb(*c2); ora.add_aabb(*m2)
+            c2 = m2
+        assert np.array_equal(live.coef()[0], ora.coef()[0])
+        r_fresh, d_fresh = fresh.solve(L)
+        assert np.array_equal(d_live, d_fresh) and np.array_equal(r_live.view(np.uint32), r_fresh.view(np.uint32))
+        fresh.close()
+    ora.generate(L[0]); ora.analyze(L[0])
+    assert_results(r_live[0], d_live[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    live.close()

@@ -20,8 +20,8 @@
  * Unity C ABI) and planeverb_b200/pvcuda.py (ctypes, tests and bench).
  *
  * Layout contract: a "plane" is (gx+1) rows of (gy+1) floats, row-major, index r*(gy+1)+c -- the
- * alloc-grid indexing of FDTD.cpp:99.  Results use the analyzer's interior indexing s = r*gx + c
- * (PvDefinitions.h:23-24, Analyzer.cpp:79), 8 floats per cell in AnalyzerResult order
+ * alloc-grid indexing of FDTD.cpp:99.  Results use the analyzer's interior indexing s = r*gy + c (the reference
+ * strides by gx, PvDefinitions.h:23-24 / Analyzer.cpp:79 -- identical on the square grids it supports), 8 floats per cell in AnalyzerResult order
  * (Analyzer.h:13-21): occlusion, wetGain, rt60, lowpass, direction.x, direction.y,
  * sourceDirectivity.x, sourceDirectivity.y.
  */

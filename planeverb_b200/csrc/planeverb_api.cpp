@@ -227,7 +227,7 @@ namespace Planeverb
         {
             std::lock_guard<std::mutex> lock(ctx->publishMutex);
             const std::vector<float>& g = ctx->grid[ctx->readable.load(std::memory_order_acquire)];
-            std::memcpy(v, g.data() + ((size_t)r * ctx->params.gx + c) * 8, sizeof(v));
+            std::memcpy(v, g.data() + ((size_t)r * ctx->params.gy + c) * 8, sizeof(v));
         }
         out.occlusion = v[0];
         out.wetGain = v[1];

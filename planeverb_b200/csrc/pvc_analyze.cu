@@ -120,7 +120,9 @@ namespace pvc
         const int s = blockIdx.z;
         if (c >= L.gy) return;
         const size_t cells = (size_t)L.gx * L.gy;
-        const size_t serial = (size_t)r * L.gx + c;              // INDEX_TO_POS, PvDefinitions.h:24
+        // interior cell (r, c) -> r*gy + c.  The reference strides by the x extent (INDEX_TO_POS, PvDefinitions.h:23-24),
+        // which is the same thing on the square grids it supports and self-overlapping on others.
+        const size_t serial = (size_t)r * L.gy + c;
         float* out = results + ((size_t)s * cells + serial) * 8;
         const int T = A.T;
         // sample t of this cell is H[t * 128]: the 4 warps of the block walk one contiguous 512-byte-per-sample stream
@@ -326,12 +328,12 @@ namespace pvc
         const float samplingRate = (float)A.fs;
         const float thresholdDist = __fmul_rn(0.3f, __fdiv_rn(kSpeedOfSoundA, (float)A.resolution));
 
-        int nextIndex = r0 * gx + c0;
+        int nextIndex = r0 * gy + c0;
         float loudness = res[(size_t)nextIndex * 8];
         float delay = FLT_MAX;
         while (delay > kDelayClose && loudness < kGainThreshold)
         {
-            const int r = nextIndex / gx, c = nextIndex % gx;
+            const int r = nextIndex / gy, c = nextIndex % gy;
             float nextDelay = FLT_MAX;
             #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -340,7 +342,7 @@ namespace pvc
                 const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
                 const int nr = r + dr, nc = c + dc;
                 if (nr < 0 || nc < 0 || nr >= gx || nc >= gy) continue;
-                const int ni = nr * gx + nc;
+                const int ni = nr * gy + nc;
                 const float d = wd[ni];
                 if (d < nextDelay) { nextIndex = ni; nextDelay = d; }
             }
@@ -348,13 +350,13 @@ namespace pvc
             delay = nextDelay;
             loudness = res[(size_t)nextIndex * 8];
             const float geodesic = __fdiv_rn(__fmul_rn(kSpeedOfSoundA, nextDelay), samplingRate);
-            const int r2 = nextIndex / gx, c2 = nextIndex % gx;
+            const int r2 = nextIndex / gy, c2 = nextIndex % gy;
             const float tx = __fsub_rn(__fmul_rn((float)r2, A.dx), sp.x);
             const float ty = __fsub_rn(__fmul_rn((float)c2, A.dx), sp.z);
             const float eu = __fsqrt_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
             if (fabsf(__fsub_rn(geodesic, eu)) < thresholdDist) break;
         }
-        const int r = nextIndex / gx, c = nextIndex % gx;
+        const int r = nextIndex / gy, c = nextIndex % gy;
         float ox = __fsub_rn(__fmul_rn((float)r, A.dx), sp.x);
         float oy = __fsub_rn(__fmul_rn((float)c, A.dx), sp.z);
         float len = __fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy));
@@ -364,7 +366,7 @@ namespace pvc
             ox = __fdiv_rn(ox, len);
             oy = __fdiv_rn(oy, len);
         }
-        float* out = res + ((size_t)r0 * gx + c0) * 8;
+        float* out = res + ((size_t)r0 * gy + c0) * 8;
         out[4] = ox; out[5] = oy;
     }
 

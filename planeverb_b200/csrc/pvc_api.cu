@@ -455,7 +455,7 @@ int pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8)
     { setError("pvc_fetch_result_at: bad argument"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
-    PVC_CUDA(cudaMemcpyAsync(out8, s->results + ((size_t)source * cells + (size_t)r * s->cfg.gx + c) * 8, sizeof(float) * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaMemcpyAsync(out8, s->results + ((size_t)source * cells + (size_t)r * s->cfg.gy + c) * 8, sizeof(float) * 8, cudaMemcpyDeviceToHost, s->stream));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
     return PVC_OK;
 }

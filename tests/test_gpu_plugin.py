@@ -130,3 +130,45 @@ def test_update_and_remove_geometry_take_effect_between_frames(plugin, scenes):
     again = L.PlaneverbGetOutput(e).vec()
     assert common.bit_equal(again[[0, 1, 3, 4, 5, 6, 7]], free[[0, 1, 3, 4, 5, 6, 7]]).all()
     assert L.PlaneverbAddGeometry(1.0, 1.0, 1.0, 1.0, 0.9) == wall   # freed slot is reused
+
+
+def test_headless_cli_links_only_the_cpp_api(tmp_path, scenes):
+    """planeverb_b200/cli/pv_headless.cpp is the Sandbox stand-in: it compiles against include/Planeverb.h only
+    and loads a .pv text scene. Its printed outputs must equal the reference's golden values."""
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(common.ROOT, "planeverb_b200", "lib", "pv_headless")
+    assert os.path.exists(exe), "pv_headless not built (make -C planeverb_b200/csrc)"
+    src = open(os.path.join(common.ROOT, "planeverb_b200", "cli", "pv_headless.cpp")).read()
+    assert "planeverb_cuda.h" not in src and "planeverb_ext.h" not in src and "pvc_" not in src
+    meta, z = common.load_golden("shoebox_70")
+    boxes = scenes["Shoebox"]["boxes"]
+    pvfile = tmp_path / "Shoebox.pv"
+    pvfile.write_text(f"{len(boxes)}\n" + "".join(
+        f"{b['id']} {b['pos'][0]} {b['pos'][1]} {b['width']} {b['height']} {b['absorption']}\n" for b in boxes))
+    emit = [(12.5, 12.5), (6.0, 5.0)]
+    cmd = [exe, str(pvfile), "--size", "25", "--res", "275", "--listener", "5", "4", "--frames", "2", "--ir"]
+    for e in emit:
+        cmd += ["--emitter", str(e[0]), str(e[1])]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    dx = np.float32(z["scalars"][0])
+    lines = [l for l in out.stdout.splitlines() if l.startswith("emitter")]
+    assert len(lines) == 2
+    for line, e in zip(lines, emit):
+        vals = []
+        for tok in line.split(":", 1)[1].split():
+            try:
+                vals.append(float(tok))
+            except ValueError:
+                pass
+        vals = np.float32(vals)
+        assert vals.size == 8
+        cell = int(np.float32(e[0]) / dx) * meta["gx"] + int(np.float32(e[1]) / dx)
+        want = z["results"][cell]
+        assert z["delay"][cell] < 3e38
+        assert common.bit_equal(vals[[0, 1, 2, 4, 5, 6, 7]], want[[0, 1, 2, 4, 5, 6, 7]]).all(), (line, want)
+        assert abs(vals[3] - want[3]) <= 2.5e-7 * abs(want[3])
+    ir = [l.split() for l in out.stdout.splitlines() if l.startswith("ir ") and l.split()[1].isdigit()]
+    assert len(ir) == 64 and "ir samples 435" in out.stdout

@@ -411,3 +411,42 @@ def test_error_paths(pv):
     with pytest.raises(pv.PlaneverbCudaError) as e:
         pv.Scene(25.0, 25.0, 275, T=10)                # free-field probe needs 18 samples (FreeGrid.cpp:100)
     assert "invalid" in str(e.value)
+
+
+def _dsp_gains(rt60, wet):
+    """PlaneverbDSP's RT60 -> three reverb-bus gains (PlaneverbDSP/src/PvDSPContext.cpp:165-229), float32."""
+    f = np.float32
+    T1, T2, T3, TS = f(0.5), f(1.0), f(3.0), f(0.1)
+    term = lambda t: np.power(f(10.0), f(-3.0) * TS / t).astype(np.float32)
+    t2 = term(rt60)
+    a_mid = wet * (term(T2) - t2) / (term(T2) - term(T1))
+    c_mid = wet * (term(T3) - t2) / (term(T3) - term(T2))
+    A = np.where(rt60 > T2, 0, np.where(rt60 < T1, 1, a_mid))
+    B = np.where(rt60 < T1, 0, np.where(rt60 > T2, c_mid, wet - a_mid))
+    Cc = np.where(rt60 > T3, 1, np.where(rt60 < T2, 0, wet - c_mid))
+    return np.stack([A, B, Cc]).astype(np.float32)
+
+
+def test_outputs_are_acceptable_to_the_dsp_consumer(pv, scenes):
+    """PlaneverbDSP only renders a source when lowpass is in [20, 20000] Hz, obstructionGain > 0 and
+    direction != 0 (PvDSPContext.cpp:258-262), then maps rt60/wetGain onto three reverb buses. On an open scene every
+    cell with an onset must pass those gates, and the bus gains computed from the device outputs must equal the ones
+    computed from the reference's golden outputs."""
+    meta, z = common.load_golden("singlewall_95_res375")
+    gpu = pv.Scene(meta["size"], meta["size"], meta["resolution"], T=meta["T_override"])
+    for b in common.golden_boxes(z):
+        gpu.add_aabb(*b)
+    res, dly = gpu.solve([meta["listener"]])
+    valid = (dly[0] < 3e38) & ~common.reference_clamped(meta, z["delay"], gpu.D)
+    r = res[0][valid]
+    assert valid.sum() > 8000
+    assert ((r[:, 3] >= 20.0) & (r[:, 3] <= 20000.0)).all()
+    assert (r[:, 0] > 0).all()
+    lr, lc = int(np.float32(meta["listener"][0]) / gpu.dx), int(np.float32(meta["listener"][2]) / gpu.dx)
+    nonzero_dir = (r[:, 4] != 0) | (r[:, 5] != 0)
+    assert (~nonzero_dir).sum() <= 1                    # only a cell whose walk ends exactly on the listener position
+    finite = np.isfinite(r[:, 2]) & (r[:, 2] > 0)
+    g_dev = _dsp_gains(r[finite, 2], r[finite, 1])
+    g_ref = _dsp_gains(z["results"][valid][finite, 2], z["results"][valid][finite, 1])
+    assert np.array_equal(g_dev.view(np.uint32), g_ref.view(np.uint32))
+    gpu.close()

@@ -109,7 +109,7 @@ namespace pvc
     __global__ void __launch_bounds__(128)
     encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
                          const SourceParams* __restrict__ src, float* __restrict__ results,
-                         float* __restrict__ delay, float* __restrict__ walkDelay)
+                         float* __restrict__ delay, float* __restrict__ walkDelay, const int* __restrict__ firstActive)
     {
         __shared__ LogfEntry sTab[16];
         if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
@@ -138,10 +138,33 @@ namespace pvc
             return;
         }
 
+        // ---- activity hints from the fused step kernel: every recorded sample of this cell before launch `mine` (4 steps
+        //      per launch) is exactly zero, likewise for the up / left neighbours; skipping exact zeros changes no sum ----
+        int onsetBegin = 0, causalBegin = 0;
+        if (firstActive)
+        {
+            const int* fa = firstActive + (size_t)s * L.tiles_x * L.tiles_y * 32;
+            auto blockFirst = [&](int rr, int cc) {
+                const int ty = rr / L.valid_rows, tx = cc / kValidCols;
+                const int wIdx = (rr - ty * L.valid_rows + kTileK) / L.warp_rows;
+                return fa[((size_t)ty * L.tiles_x + tx) * 32 + wIdx];
+            };
+            const int mine = blockFirst(r, c);
+            if (mine >= kNeverActive)
+            {   // never anything but zeros: no onset (Analyzer.cpp:161-165)
+                delay[(size_t)s * cells + serial] = FLT_MAX;
+                walkDelay[(size_t)s * cells + serial] = FLT_MAX;
+                return;
+            }
+            const int up = (r > 0) ? blockFirst(r - 1, c) : mine, left = (c > 0) ? blockFirst(r, c - 1) : mine;
+            onsetBegin = min(mine * kTileK, T);
+            causalBegin = min(min(mine, min(up, left)) * kTileK, T);
+        }
+
         // ---- onset: first sample with |p| > threshold (Analyzer.cpp:146-154); kBatch loads in flight ----
         constexpr int kBatch = 8;
         int onset = -1;
-        for (int t0 = 0; t0 < T && onset < 0; t0 += kBatch)
+        for (int t0 = onsetBegin; t0 < T && onset < 0; t0 += kBatch)
         {
             float v[kBatch];
             #pragma unroll
@@ -171,7 +194,7 @@ namespace pvc
             const ptrdiff_t leftOff = leftEdge ? 0 : (((c & 127) != 0) ? -1 : -(ptrdiff_t)T * kHistChunk + 127);
             float vx = 0.f, vy = 0.f;
             constexpr int kCausalBatch = 4;
-            for (int t0 = 0; t0 < fluxEnd; t0 += kCausalBatch)
+            for (int t0 = causalBegin; t0 < fluxEnd; t0 += kCausalBatch)
             {
                 float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
                 #pragma unroll
@@ -422,7 +445,8 @@ namespace pvc
         const AnalyzeParams A = paramsOf(s);
         dim3 block(128, 1, 1);
         dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
-        encodeResponseKernel<<<grid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay);
+        encodeResponseKernel<<<grid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
+                                                            s->hintsValid ? s->firstActive : nullptr);
         listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
         *launches += 2;
         cudaError_t e = cudaGetLastError();

@@ -34,6 +34,7 @@ namespace pvc
         L.gx = c.gx; L.gy = c.gy;
         L.rows = c.gx + 1; L.cols = c.gy + 1;
         L.tile_rows = fusedTileRows(c.reserved);
+        L.warp_rows = fusedWarpRows(c.reserved);
         L.valid_rows = L.tile_rows - 2 * kTileK;
         L.tiles_x = (L.cols + kValidCols - 1) / kValidCols;
         L.tiles_y = (L.rows + L.valid_rows - 1) / L.valid_rows;
@@ -143,13 +144,18 @@ namespace pvc
     {
         if (n <= 0) return PVC_OK;
         const Layout& L = s->L;
-        pvc_rect* d = nullptr;
-        PVC_CUDA(cudaMallocAsync(&d, sizeof(pvc_rect) * n, s->stream));
-        PVC_CUDA(cudaMemcpyAsync(d, rects_host, sizeof(pvc_rect) * n, cudaMemcpyHostToDevice, s->stream));
+        if (n > s->rectCapacity)
+        {   // persistent edit-list buffer (stream-ordered allocation here cost up to tens of ms per frame in pool trimming)
+            if (s->rects) cudaFree(s->rects);
+            s->rects = nullptr; s->rectCapacity = 0;
+            const int cap = n < 64 ? 64 : 2 * n;
+            PVC_CUDA(cudaMalloc(&s->rects, sizeof(pvc_rect) * (size_t)cap));
+            s->rectCapacity = cap;
+        }
+        PVC_CUDA(cudaMemcpyAsync(s->rects, rects_host, sizeof(pvc_rect) * n, cudaMemcpyHostToDevice, s->stream));
         dim3 block(32, 8), grid((L.cols + 31) / 32, (L.rows + 7) / 8);
-        applyRectsKernel<<<grid, block, 0, s->stream>>>(L, s->w, d, n);
+        applyRectsKernel<<<grid, block, 0, s->stream>>>(L, s->w, s->rects, n);
         PVC_CUDA(cudaGetLastError());
-        PVC_CUDA(cudaFreeAsync(d, s->stream));
         PVC_CUDA(cudaStreamSynchronize(s->stream));      // rects_host may be a caller temporary
         s->slowMaskDirty = 1;
         return PVC_OK;
@@ -268,6 +274,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMemsetAsync(s->slowMask, 0, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
+    PVC_TRY(cudaMalloc(&s->firstActive, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32));
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
@@ -296,7 +303,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->tileCounters); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -411,6 +418,9 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
     PVC_CUDA(cudaEventRecord(s->ev[0], s->stream));
     int rc = zeroState(s, n);
     if (rc) return rc;
+    s->hintsValid = (s->cfg.step_kernel == 0);
+    if (s->hintsValid)
+        PVC_CUDA(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * (size_t)n * s->L.tiles_x * s->L.tiles_y * 32, s->stream));
     rc = runSteps(s, n, s->cfg.T, &launches);
     if (rc) return rc;
     PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));

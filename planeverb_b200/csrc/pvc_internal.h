@@ -47,6 +47,7 @@ namespace pvc
         int tiles_x, tiles_y;  // fused-kernel tile grid
         int tile_rows;         // rows per tile incl. halo (warps * rows per thread)
         int valid_rows;        // tile_rows - 2*kTileK
+        int warp_rows;         // rows per warp (R) of the fused-kernel variant in use
     };
 
     __host__ __device__ inline size_t cellIndex(const Layout& L, int r, int c)
@@ -55,6 +56,7 @@ namespace pvc
     }
 
     constexpr int kHistChunk = 128;
+    constexpr int kNeverActive = 0x7f7f7f7f;     // memset(0x7f) pattern of firstActive
 
     // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*128
     __host__ __device__ inline size_t histCell(const Layout& L, int r, int c)
@@ -92,6 +94,8 @@ struct pvc_solver
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
     int slowMaskDirty;
     int* tileOrder;          // tiles_x*tiles_y tile ids, most expensive first
+    int* firstActive;        // [source][tile][32]: activity hints written by the fused kernels, read by the analyzer
+    int hintsValid;          // the last run's step kernel filled firstActive
     int* tileCounters;       // one work counter per launch of the persistent TMA variant
     int tileCounterCount;
     alignas(64) unsigned char tensorMaps[6 * 128];   // CUtensorMap[2 ping-pong][3 fields] (128 B each)
@@ -102,6 +106,8 @@ struct pvc_solver
     float* delay;            // max_sources * gx*gy
     float* walkDelay;        // max_sources * gx*gy   (delay of selectable cells, FLT_MAX otherwise)
     float* scratch;          // small device scratch (IR fetch)
+    pvc_rect* rects;         // device copy of the current geometry edit list
+    int rectCapacity;
     pvc::SourceParams* src;  // max_sources
     float efree;
     int cur;                 // ping-pong index holding the latest state
@@ -121,6 +127,7 @@ namespace pvc
     int rebuildSlowMask(pvc_solver* s);
     int buildTensorMaps(pvc_solver* s);
     int fusedTileRows(int variant);
+    int fusedWarpRows(int variant);
     // analyzer kernels (pvc_analyze.cu)
     int launchAnalyzer(pvc_solver* s, int nsrc, int* launches);
     int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev);

@@ -44,6 +44,7 @@ namespace pvc
         const float* coefBp; const float* coefGx; const float* coefGy;   // general-path coefficient planes
         const uint32_t* slowMask;
         const int* tileOrder;      // tiles of one source sorted by estimated cost, most expensive first
+        int* firstActive;          // [source][tile][32 warps]: first launch in which the warp's block recorded a non-zero pressure
         int tilesPerSource, nsrc;
         float* hist;               // pressure history of source 0 (null: no record)
         const SourceParams* src;
@@ -140,6 +141,7 @@ namespace pvc
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
                  + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
 
+        uint32_t activity = 0u;
         if (CS && slow) asm volatile("cp.async.wait_group 0;" ::: "memory");
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
         __syncthreads();
@@ -315,6 +317,14 @@ namespace pvc
                     if (j >= jLo && j < jHi)
                         __stcs(reinterpret_cast<float4*>(hist + (size_t)j * L.hist_row), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
                 hist += kHistChunk;
+                // activity hint for the analyzer: has this warp's block recorded anything but zeros yet?  (one 3-input
+                // OR per two cells; conservative -- halo rows and -0 count as activity)
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    activity |= __float_as_uint(p[j][0]) | __float_as_uint(p[j][1]);
+                    activity |= __float_as_uint(p[j][2]) | __float_as_uint(p[j][3]);
+                }
             }
             if (hasSrc)
             {
@@ -349,6 +359,17 @@ namespace pvc
                     *reinterpret_cast<float4*>(gx + (size_t)j * L.pitch) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
                     *reinterpret_cast<float4*>(gy + (size_t)j * L.pitch) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
                 }
+            }
+        }
+        if (A.firstActive && A.hist)
+        {
+            const bool hot = ((activity & 0x7fffffffu) != 0u) && lane >= 1 && lane <= 30;
+            const unsigned any = __ballot_sync(0xffffffffu, hot);
+            if (lane == 0 && any)
+            {
+                int* slot = A.firstActive + ((size_t)s * A.tilesPerSource + (size_t)ty * L.tiles_x + tx) * 32 + wp;
+                const int launchIndex = A.t0 / kTileK;
+                if (*slot > launchIndex) atomicMin(slot, launchIndex);
             }
         }
         __syncthreads();
@@ -710,7 +731,7 @@ namespace pvc
         float** out = s->state[s->cur ^ 1];
         A.inP = in[0]; A.inVx = in[1]; A.inVy = in[2];
         A.outP = out[0]; A.outVx = out[1]; A.outVy = out[2];
-        A.coefBp = s->coef[0]; A.coefGx = s->coef[1]; A.coefGy = s->coef[2]; A.slowMask = s->slowMask; A.tileOrder = s->tileOrder; A.tilesPerSource = s->L.tiles_x * s->L.tiles_y;
+        A.coefBp = s->coef[0]; A.coefGx = s->coef[1]; A.coefGy = s->coef[2]; A.slowMask = s->slowMask; A.tileOrder = s->tileOrder; A.tilesPerSource = s->L.tiles_x * s->L.tiles_y; A.firstActive = s->firstActive;
         A.hist = hist;
         A.src = s->src; A.pulse = s->pulse;
         A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
@@ -718,6 +739,12 @@ namespace pvc
         A.timeline = s->timeline;
         if (s->timeline) { static const char* dbg = getenv("PVC_DEBUG_NSTEPS"); if (dbg) A.nsteps = atoi(dbg); }   // debug: memory-floor probe
         return A;
+    }
+
+    int fusedWarpRows(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants) variant = 0;
+        return kVariants[variant].r;
     }
 
     template <int NW, int R, int MINB, bool CS = false>

@@ -277,6 +277,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->firstActive, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32));
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
+    PVC_TRY(cudaMalloc(&s->doneGen, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
@@ -303,7 +304,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -431,12 +432,23 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
     return PVC_OK;
 }
 
+static int checkAbort(pvc_solver* s)
+{
+    if (!s->checkAbort) return PVC_OK;
+    s->checkAbort = 0;
+    int flag = 0;
+    PVC_CUDA(cudaMemcpyAsync(&flag, s->tileCounters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaStreamSynchronize(s->stream));
+    if (flag) { setError("generational step kernel: a tile dependency wait timed out (results invalid)"); return PVC_ERR_CUDA; }
+    return PVC_OK;
+}
+
 int pvc_synchronize(pvc_solver* s)
 {
     if (!s) { setError("pvc_synchronize: null solver"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
-    return PVC_OK;
+    return checkAbort(s);
 }
 
 int pvc_clear_results(pvc_solver* s, int source)
@@ -456,7 +468,7 @@ int pvc_fetch_results(pvc_solver* s, int source, float* results, float* delay)
     if (results) PVC_CUDA(cudaMemcpyAsync(results, s->results + (size_t)source * cells * 8, sizeof(float) * cells * 8, cudaMemcpyDeviceToHost, s->stream));
     if (delay) PVC_CUDA(cudaMemcpyAsync(delay, s->delay + (size_t)source * cells, sizeof(float) * cells, cudaMemcpyDeviceToHost, s->stream));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
-    return PVC_OK;
+    return checkAbort(s);
 }
 
 int pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8)

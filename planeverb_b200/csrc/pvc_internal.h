@@ -96,7 +96,9 @@ struct pvc_solver
     int* tileOrder;          // tiles_x*tiles_y tile ids, most expensive first
     int* firstActive;        // [source][tile][32]: activity hints written by the fused kernels, read by the analyzer
     int hintsValid;          // the last run's step kernel filled firstActive
-    int* tileCounters;       // one work counter per launch of the persistent TMA variant
+    int* tileCounters;       // one work counter per launch of the persistent TMA variants (slot 0: abort flag of the generational one)
+    int* doneGen;            // generational variant: completed generations per (source, tile)
+    int checkAbort;
     int tileCounterCount;
     alignas(64) unsigned char tensorMaps[6 * 128];   // CUtensorMap[2 ping-pong][3 fields] (128 B each)
     int tmaReady, tmaTileRows;

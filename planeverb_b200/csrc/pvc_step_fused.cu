@@ -28,6 +28,7 @@
 // the history write stream to HBM; see DESIGN.md for the byte accounting.
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -142,6 +143,11 @@ namespace pvc
                  + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
 
         uint32_t activity = 0u;
+        // activity-hint slot of this warp's block, fetched now so its latency hides behind the steps
+        int* const hintSlot = (A.firstActive && A.hist)
+            ? A.firstActive + ((size_t)s * A.tilesPerSource + (size_t)ty * L.tiles_x + tx) * 32 + wp : nullptr;
+        int hintKnown = 0;
+        if (hintSlot && lane == 0) hintKnown = *hintSlot;
         if (CS && slow) asm volatile("cp.async.wait_group 0;" ::: "memory");
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
         __syncthreads();
@@ -361,19 +367,14 @@ namespace pvc
                 }
             }
         }
-        if (A.firstActive && A.hist)
+        if (hintSlot)
         {
             const bool hot = ((activity & 0x7fffffffu) != 0u) && lane >= 1 && lane <= 30;
             const unsigned any = __ballot_sync(0xffffffffu, hot);
-            if (lane == 0 && any)
-            {
-                int* slot = A.firstActive + ((size_t)s * A.tilesPerSource + (size_t)ty * L.tiles_x + tx) * 32 + wp;
-                const int launchIndex = A.t0 / kTileK;
-                if (*slot > launchIndex) atomicMin(slot, launchIndex);
-            }
+            const int launchIndex = A.t0 / kTileK;
+            if (lane == 0 && any && hintKnown > launchIndex) atomicMin(hintSlot, launchIndex);
         }
-        __syncthreads();
-        stamp(A, 6, stampIdx);
+        if (A.timeline) { __syncthreads(); stamp(A, 6, stampIdx); }      // debug only: no barrier at the end of a tile otherwise
     }
 
     // One tile per CTA, state loaded straight from global memory into registers.
@@ -554,6 +555,7 @@ namespace pvc
         float4 (*sPBot)[32] = sVxTop + (NW + 1);
         uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));                         // [NS]
         volatile int* sQueue = reinterpret_cast<volatile int*>(full + NS);                      // [NS] tile index held by each stage
+        volatile int* sCoord = sQueue + NS;                                                     // [NS][3] its (source, tx, ty)
 
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
@@ -566,6 +568,7 @@ namespace pvc
         auto issue = [&](int order, int st) {                   // thread 0 only
             int s, tx, ty;
             decode(order, s, tx, ty);
+            sCoord[st * 3 + 0] = s; sCoord[st * 3 + 1] = tx; sCoord[st * 3 + 2] = ty;
             float* stage = stageBase + (size_t)st * 3 * TR * kTileCols;
             mbarExpectTx(full + st, 3u * kPlaneBytes);
             tmaLoadTile3d(stage, &mapP, tx * kValidCols, ty * L.valid_rows, s, full + st);
@@ -600,8 +603,7 @@ namespace pvc
         {
             const int tile = sQueue[st];
             if (tile >= numTiles) break;                        // indices only grow: once a stage is empty every later one is
-            int s, tx, ty;
-            decode(tile, s, tx, ty);
+            const int s = sCoord[st * 3 + 0], tx = sCoord[st * 3 + 1], ty = sCoord[st * 3 + 2];
             stamp(A, 0, tile);
             mbarWait(full + st, parity);
             const float* stage = stageBase + (size_t)st * 3 * TR * kTileCols;
@@ -627,6 +629,205 @@ namespace pvc
             computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile);   // its barriers publish sQueue[st]
             if (++st == NS) { st = 0; parity ^= 1u; }
         }
+    }
+
+    // ---- generational persistent variant: the whole time loop in one launch, no grid-wide synchronisation ------------
+    // Work items are (generation g, tile): generation g advances every tile from step 4g to 4g+4.  CTAs (one per SM)
+    // pull items from a global counter in (g, cost-sorted tile) order.  An item may start as soon as the tile itself and
+    // its up-to-8 neighbours of the same source have finished generation g-1 (their outputs are this item's halo, and
+    // that also covers the write-after-read on the ping-pong buffer), which is tracked with one completed-generation
+    // counter per tile (st.release / ld.acquire at gpu scope).  Nothing ever waits for "everybody": the expensive wall
+    // tiles of generation g overlap the cheap tiles of g+1, there is no launch ramp or tail every 4 steps, and the TMA
+    // prefetch of the next item runs straight across generation boundaries.  Deadlock-free because all CTAs are
+    // co-resident and an item only depends on items handed out before it; a bounded spin sets an abort flag otherwise.
+    struct GenArgs
+    {
+        float* state[2][3];       // ping-pong planes: generation g reads [g & 1], writes [(g + 1) & 1]
+        int* doneGen;             // [nsrc * tilesPerSource] generations completed by each tile
+        int* workCounter;         // next work item of this launch
+        int* abortFlag;           // set if a dependency wait times out (host reports PVC_ERR_CUDA)
+        int gen0, numGen;         // generations covered by this launch
+        int T;                    // total number of steps (the last generation may be short)
+    };
+    struct TensorMaps6 { CUtensorMap m[6]; };     // [buffer][field]
+
+    __device__ __forceinline__ int loadAcquire(const int* p)
+    {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void storeRelease(int* p, int v)
+    {
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+
+    template <int NW, int R, bool CS>
+    __global__ void __launch_bounds__(NW * 32, 1)
+    fusedStepGenKernel(const Layout L, const FusedArgs A0, const GenArgs G, const int numTiles,
+                       const __grid_constant__ TensorMaps6 maps)
+    {
+        constexpr int TR = NW * R;
+        constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
+        extern __shared__ __align__(128) unsigned char smemRaw[];
+        float* stage = reinterpret_cast<float*>(smemRaw);                                        // [3][TR][128]
+        float4* sCoef = reinterpret_cast<float4*>(smemRaw + 3 * kPlaneBytes);                  // [3][TR][32] (CS only)
+        unsigned char* tail = smemRaw + 3 * kPlaneBytes + (CS ? 3 * kPlaneBytes : 0);
+        float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(tail);
+        float4 (*sPBot)[32] = sVxTop + (NW + 1);
+        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));
+        volatile int* sItem = reinterpret_cast<volatile int*>(full + 1);     // [0] work item, [1] source, [2] tx, [3] ty, [4] generation
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        const int total = G.numGen * numTiles;
+        const int tps = A0.tilesPerSource;
+
+        // ---- thread-0 helpers ----
+        // executed by ALL lanes of warp 0: lane k < 9 probes neighbour k (one L2 round trip for the whole stencil of tiles)
+        auto depsReady = [&](int s, int tx, int ty, int gen, bool block) -> bool {
+            if (gen == 0) return true;
+            const int dx = lane % 3 - 1, dy = lane / 3 - 1;
+            const int nx = tx + dx, ny = ty + dy;
+            const bool mine = lane < 9 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y;
+            const int* slot = G.doneGen + (size_t)s * tps + (mine ? ny * L.tiles_x + nx : 0);
+            unsigned spins = 0;
+            while (true)
+            {
+                const bool ok = !mine || loadAcquire(slot) >= gen;
+                if (__all_sync(0xffffffffu, ok)) return true;
+                if (!block) return false;
+                __nanosleep(64);
+                ++spins;
+                bool giveUp = false;
+                if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)G.abortFlag;
+                if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(G.abortFlag, 1); return false; }
+            }
+        };
+        auto issue = [&](int s, int tx, int ty, int gen) {
+            asm volatile("fence.proxy.async;" ::: "memory");     // order the acquires above before the async-proxy reads below
+            const CUtensorMap* m = maps.m + 3 * (gen & 1);
+            mbarExpectTx(full, 3u * kPlaneBytes);
+            tmaLoadTile3d(stage, m + 0, tx * kValidCols, ty * L.valid_rows, s, full);
+            tmaLoadTile3d(stage + (size_t)TR * kTileCols, m + 1, tx * kValidCols, ty * L.valid_rows, s, full);
+            tmaLoadTile3d(stage + (size_t)2 * TR * kTileCols, m + 2, tx * kValidCols, ty * L.valid_rows, s, full);
+        };
+        auto decodeItem = [&](int w, int& s, int& tx, int& ty, int& gen) {
+            const int order = w % numTiles;
+            gen = G.gen0 + w / numTiles;
+            s = order % A0.nsrc;
+            const int id = A0.tileOrder[order / A0.nsrc];
+            ty = id / L.tiles_x; tx = id - ty * L.tiles_x;
+        };
+        auto publishItem = [&](int w, int s, int tx, int ty, int gen) {
+            sItem[0] = w; sItem[1] = s; sItem[2] = tx; sItem[3] = ty; sItem[4] = gen;
+        };
+
+        // warp-0 state (uniform across its lanes)
+        int pending = 0;                 // next work item index, fetched one tile early
+        bool nextIssued = false;         // TMA for the published next item already in flight
+        int prevSlot = -1, prevGen = 0;  // finished tile whose completion is not published yet
+        auto fetchItem = [&]() -> int {                         // warp 0: one atomic, broadcast
+            int v = 0;
+            if (lane == 0) v = atomicAdd(G.workCounter, 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+
+        if (wp == 0)
+        {
+            if (lane == 0)
+            {
+                mbarInit(full, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+            const int w = fetchItem();
+            int s = 0, tx = 0, ty = 0, gen = 0;
+            bool ok = false;
+            if (w < total)
+            {
+                decodeItem(w, s, tx, ty, gen);
+                ok = depsReady(s, tx, ty, gen, true);
+            }
+            if (lane == 0)
+            {
+                if (ok) { publishItem(w, s, tx, ty, gen); issue(s, tx, ty, gen); }
+                else publishItem(total, 0, 0, 0, 0);
+            }
+            pending = fetchItem();
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        uint32_t parity = 0;
+        while (true)
+        {
+            const int w = sItem[0];
+            if (w >= total) break;
+            const int s = sItem[1], tx = sItem[2], ty = sItem[3], gen = sItem[4];
+            mbarWait(full, parity);
+            parity ^= 1u;
+            float p[R][4], vx[R][4], vy[R][4];
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const int row = wp * R + j;
+                const float4 a = *reinterpret_cast<const float4*>(stage + ((size_t)(0 * TR + row)) * kTileCols + lane * 4);
+                const float4 b = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + row)) * kTileCols + lane * 4);
+                const float4 c = *reinterpret_cast<const float4*>(stage + ((size_t)(2 * TR + row)) * kTileCols + lane * 4);
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
+            __syncthreads();                                   // stage drained; sItem consumed; the previous tile's stores were
+                                                               // all issued before the barrier that ended it
+            if (wp == 0)
+            {
+                // release the previous tile (its stores were issued about a microsecond ago, so the release is cheap by
+                // now): one st.release.gpu by lane 0 after the CTA barrier orders every thread's stores before it
+                if (prevSlot >= 0) { if (lane == 0) storeRelease(G.doneGen + prevSlot, prevGen + 1); prevSlot = -1; }
+                nextIssued = true;
+                if (pending < total)
+                {
+                    int ns, ntx, nty, ngen;
+                    decodeItem(pending, ns, ntx, nty, ngen);
+                    nextIssued = depsReady(ns, ntx, nty, ngen, false);
+                    if (lane == 0)
+                    {
+                        publishItem(pending, ns, ntx, nty, ngen);
+                        if (nextIssued) issue(ns, ntx, nty, ngen);
+                    }
+                }
+                else if (lane == 0) publishItem(total, 0, 0, 0, 0);
+            }
+
+            FusedArgs A = A0;
+            A.t0 = gen * kTileK;
+            A.nsteps = min(kTileK, G.T - gen * kTileK);
+            A.outP = G.state[(gen + 1) & 1][0]; A.outVx = G.state[(gen + 1) & 1][1]; A.outVy = G.state[(gen + 1) & 1][2];
+            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, w);
+
+            const bool needSlowPath = __syncthreads_or(wp == 0 && !nextIssued);      // also: every store of this tile is issued
+            if (wp == 0) { prevSlot = s * tps + ty * L.tiles_x + tx; prevGen = gen; }
+            if (needSlowPath)
+            {   // the next item waits on tiles that were not finished when we probed (possibly on this very tile):
+                // publish our completion now, then wait for real
+                if (wp == 0)
+                {
+                    if (lane == 0) storeRelease(G.doneGen + prevSlot, prevGen + 1);
+                    prevSlot = -1;
+                    const int ns = sItem[1], ntx = sItem[2], nty = sItem[3], ngen = sItem[4];
+                    const bool ok = depsReady(ns, ntx, nty, ngen, true);
+                    if (lane == 0) { if (ok) issue(ns, ntx, nty, ngen); else publishItem(total, 0, 0, 0, 0); }
+                }
+                __syncthreads();
+            }
+            if (wp == 0) pending = fetchItem();
+        }
+        // publish the last tile
+        __syncthreads();
+        if (wp == 0 && lane == 0 && prevSlot >= 0) storeRelease(G.doneGen + prevSlot, prevGen + 1);
     }
 
     // Per-cell coefficients of the general path, rebuilt after every geometry edit from the wall plane w.
@@ -715,7 +916,7 @@ namespace pvc
                                          {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
                                          {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
                                          {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
-                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2} };
+                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -808,7 +1009,7 @@ namespace pvc
         constexpr int TR = NW * R;
         if (!s->tmaReady || s->tmaTileRows != TR) { setError("TMA variant: tensor maps not built for %d-row tiles", TR); return PVC_ERR_INVALID; }
         const size_t plane = (size_t)TR * kTileCols * sizeof(float);
-        const size_t smem = NS * 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 64;
+        const size_t smem = NS * 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 128;
         static bool configured[64] = {};
         if (!configured[s->device & 63])
         {
@@ -833,6 +1034,54 @@ namespace pvc
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("TMA fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    template <int NW, int R, bool CS>
+    static int launchGen(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
+    {
+        const Layout& L = s->L;
+        constexpr int TR = NW * R;
+        if (!s->tmaReady || s->tmaTileRows != TR) { setError("generational variant: tensor maps not built for %d-row tiles", TR); return PVC_ERR_INVALID; }
+        if (t0 != 0 || s->cur != 0) { setError("generational variant: must start at step 0"); return PVC_ERR_INVALID; }
+        const size_t plane = (size_t)TR * kTileCols * sizeof(float);
+        const size_t smem = 3 * plane + (CS ? 3 * plane : 0) + (size_t)2 * (NW + 1) * 32 * sizeof(float4) + 128;
+        static bool configured[64] = {};
+        if (!configured[s->device & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(fusedStepGenKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { setError("generational kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            configured[s->device & 63] = true;
+        }
+        int maxCtas = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtas, fusedStepGenKernel<NW, R, CS>, NW * 32, smem);
+        if (maxCtas < 1) { setError("generational kernel does not fit an SM"); return PVC_ERR_CUDA; }
+        const int numTiles = L.tiles_x * L.tiles_y * nsrc;
+        const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;          // all CTAs must be co-resident
+        const int gens = (t1 + kTileK - 1) / kTileK;
+        const int perLaunch = 256;                                             // generations per launch (bounds kernel time)
+        cudaMemsetAsync(s->doneGen, 0, sizeof(int) * (size_t)numTiles, s->stream);
+        cudaMemsetAsync(s->tileCounters, 0, sizeof(int) * (size_t)((gens + perLaunch - 1) / perLaunch + 1), s->stream);
+        FusedArgs A = makeArgs(s, hist, 0, t1);
+        A.nsrc = nsrc;
+        GenArgs G;
+        for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) G.state[b][f] = s->state[b][f];
+        G.doneGen = s->doneGen; G.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
+        G.T = t1;
+        TensorMaps6 maps;
+        memcpy(&maps, s->tensorMaps, sizeof(maps));
+        int k = 1;
+        for (int g0 = 0; g0 < gens; g0 += perLaunch, ++k)
+        {
+            G.gen0 = g0; G.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
+            G.workCounter = s->tileCounters + k;
+            fusedStepGenKernel<NW, R, CS><<<grid, NW * 32, smem, s->stream>>>(L, A, G, numTiles, maps);
+            *launches += 1;
+        }
+        s->cur = gens & 1;
+        s->checkAbort = 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("generational fused step launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         return PVC_OK;
     }
 
@@ -930,6 +1179,9 @@ namespace pvc
             case 27: return launchTma<16, 4, false, 2>(s, nsrc, t0, t1, hist, launches);
             case 28: return launchTma<12, 4, false, 2>(s, nsrc, t0, t1, hist, launches);
             case 29: return launchTma<10, 4, true, 2>(s, nsrc, t0, t1, hist, launches);
+            case 30: return launchGen<16, 4, true>(s, nsrc, t0, t1, hist, launches);
+            case 31: return launchGen<16, 4, false>(s, nsrc, t0, t1, hist, launches);
+            case 32: return launchGen<12, 6, false>(s, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }

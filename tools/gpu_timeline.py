@@ -23,6 +23,7 @@ for S, var in cases:
     print(f'S={S} var={var} blocks={n}: kernel span {rel[:,6].max():.1f} us; per-CTA phases mean us: load {d[:,0].mean():.2f} steps {d[:,1:5].mean(axis=0).round(2)} store {d[:,5].mean():.2f} total {(rel[:,6]-rel[:,0]).mean():.2f}')
     starts = np.sort(rel[:, 0])
     print('   CTA start quantiles (us)', np.quantile(starts, [0, .25, .5, .75, 1]).round(1), ' end quantiles', np.quantile(rel[:, 6], [0, .25, .5, .75, 1]).round(1))
+    print('   load-phase quantiles (us)', np.quantile(d[:, 0], [0, .1, .25, .5, .75, .9, 1]).round(2), ' first-step quantiles', np.quantile(d[:, 1], [0, .25, .5, .75, 1]).round(2))
     tot = rel[:, 6] - rel[:, 0]
     print('   CTA duration quantiles', np.quantile(tot, [0, .1, .5, .9, 1]).round(2))
     G.close()

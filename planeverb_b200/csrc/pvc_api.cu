@@ -49,17 +49,17 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto: the persistent TMA-fed kernel (16 warps x 4 rows, variant 22) once every SM gets at least
-    // four tiles per launch -- that is where its prefetch pipeline pays -- else the plain 8 x 6 kernel (variant 18),
-    // which has the lower latency on small grids / batches (measured on B200, profiles/)
+    // variant 0 = auto: the warp-specialised generational kernel (15 compute warps x 4 rows + a producer warp, TMA
+    // tensor loads, per-tile dependency counters; variant 36) -- fastest at every batch/grid size measured on B200
+    // (profiles/).  It needs cuTensorMapEncodeTiled from the driver; without it fall back to the plain 8 x 6 kernel.
     static int resolveVariant(const pvc_config& c)
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
-        const int validRows = 16 * 4 - 2 * kTileK;
-        const long tiles = (long)((c.gy + 1 + kValidCols - 1) / kValidCols) * ((c.gx + 1 + validRows - 1) / validRows) * c.max_sources;
-        return tiles >= 4L * sms ? 22 : 18;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
+        if (!tma) cudaGetLastError();
+        return tma ? 36 : 18;
     }
 
     static bool validConfig(const pvc_config* c)
@@ -275,6 +275,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMemsetAsync(s->slowMask, 0, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
     PVC_TRY(cudaMalloc(&s->firstActive, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32));
+    PVC_TRY(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
     PVC_TRY(cudaMalloc(&s->doneGen, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));

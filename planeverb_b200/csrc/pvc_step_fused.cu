@@ -68,10 +68,29 @@ namespace pvc
         }
     }
 
+    // what differs between the tiles a persistent CTA processes: the time window and the output buffers
+    struct TileRun
+    {
+        int t0, nsteps;
+        float* outP; float* outVx; float* outVy;
+    };
+    __device__ __forceinline__ TileRun runOf(const FusedArgs& A)
+    {
+        TileRun r; r.t0 = A.t0; r.nsteps = A.nsteps; r.outP = A.outP; r.outVx = A.outVx; r.outVy = A.outVy;
+        return r;
+    }
+
+    // barrier over the NW compute warps of a CTA (named barrier 1), so that a kernel may run extra, non-compute warps
+    template <int NW>
+    __device__ __forceinline__ void computeBarrier()
+    {
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    }
+
     template <int NW, int R, bool CS>
     __device__ __forceinline__ void computeTile(const Layout& L, const FusedArgs& A, const int tx, const int ty, const int s,
                                                 float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
-                                                float4 (*sVxTop)[32], float4 (*sPBot)[32], float4* sCoefArg, const int stampIdx = -1)
+                                                float4 (*sVxTop)[32], float4 (*sPBot)[32], float4* sCoefArg, const int stampIdx, const TileRun run)
     {
         const int lane = threadIdx.x & 31;
         const int wp = threadIdx.x >> 5;
@@ -140,7 +159,7 @@ namespace pvc
         float* hist = nullptr;
         if (A.hist)
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
-                 + ((ptrdiff_t)(cBase >> 7) * L.T + A.t0) * kHistChunk + (cBase & 127);
+                 + ((ptrdiff_t)(cBase >> 7) * L.T + run.t0) * kHistChunk + (cBase & 127);
 
         uint32_t activity = 0u;
         // activity-hint slot of this warp's block, fetched now so its latency hides behind the steps
@@ -150,11 +169,11 @@ namespace pvc
         if (hintSlot && lane == 0) hintKnown = *hintSlot;
         if (CS && slow) asm volatile("cp.async.wait_group 0;" ::: "memory");
         sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-        __syncthreads();
+        computeBarrier<NW>();
         stamp(A, 1, stampIdx);
 
         #pragma unroll 1
-        for (int step = 0; step < A.nsteps; ++step)
+        for (int step = 0; step < run.nsteps; ++step)
         {
             // ---------------- pressure sub-step (FDTD.cpp:125-141) ----------------
             {
@@ -219,7 +238,7 @@ namespace pvc
                 }
             }
             sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
-            __syncthreads();
+            computeBarrier<NW>();
 
             // ---------------- velocity sub-steps + edge overrides (FDTD.cpp:144-223) ----------------
             {
@@ -335,7 +354,7 @@ namespace pvc
             if (hasSrc)
             {
                 // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
-                const float add = __ldg(A.pulse + A.t0 + step);
+                const float add = __ldg(A.pulse + run.t0 + step);
                 const float a0 = (sk == 0) ? add : 0.f, a1 = (sk == 1) ? add : 0.f;
                 const float a2 = (sk == 2) ? add : 0.f, a3 = (sk == 3) ? add : 0.f;
                 #pragma unroll
@@ -347,15 +366,15 @@ namespace pvc
                     }
             }
             sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-            __syncthreads();
+            computeBarrier<NW>();
             stamp(A, 2 + step, stampIdx);
         }
 
         // ---------------- store the owned cells of the new state ----------------
         {
-            float* gp = A.outP + src0;
-            float* gx = A.outVx + src0;
-            float* gy = A.outVy + src0;
+            float* gp = run.outP + src0;
+            float* gx = run.outVx + src0;
+            float* gy = run.outVy + src0;
             #pragma unroll
             for (int j = 0; j < R; ++j)
             {
@@ -371,10 +390,10 @@ namespace pvc
         {
             const bool hot = ((activity & 0x7fffffffu) != 0u) && lane >= 1 && lane <= 30;
             const unsigned any = __ballot_sync(0xffffffffu, hot);
-            const int launchIndex = A.t0 / kTileK;
+            const int launchIndex = run.t0 / kTileK;
             if (lane == 0 && any && hintKnown > launchIndex) atomicMin(hintSlot, launchIndex);
         }
-        if (A.timeline) { __syncthreads(); stamp(A, 6, stampIdx); }      // debug only: no barrier at the end of a tile otherwise
+        if (A.timeline) { computeBarrier<NW>(); stamp(A, 6, stampIdx); }      // debug only: no barrier at the end of a tile otherwise
     }
 
     // One tile per CTA, state loaded straight from global memory into registers.
@@ -420,7 +439,7 @@ namespace pvc
             sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         extern __shared__ __align__(16) float4 sCoefDyn[];        // [3][NW*R][32] float4
-        computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoefDyn);
+        computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoefDyn, -1, runOf(A));
     }
 
     // ---- persistent variant: TMA bulk-copy prefetch of the next tile through shared memory ----------------
@@ -521,7 +540,7 @@ namespace pvc
             const int next = tile + gridDim.x;
             if (next < numTiles) prefetch(next);
 
-            computeTile<NW, R, false>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, nullptr, tile);
+            computeTile<NW, R, false>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, nullptr, tile, runOf(A));
             tile = next;
         }
     }
@@ -626,7 +645,7 @@ namespace pvc
                 if (pending < numTiles) issue(pending, st);
                 pending = atomicAdd(tileCounter, 1);
             }
-            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile);   // its barriers publish sQueue[st]
+            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, tile, runOf(A));   // its barriers publish sQueue[st]
             if (++st == NS) { st = 0; parity ^= 1u; }
         }
     }
@@ -802,11 +821,11 @@ namespace pvc
                 else if (lane == 0) publishItem(total, 0, 0, 0, 0);
             }
 
-            FusedArgs A = A0;
-            A.t0 = gen * kTileK;
-            A.nsteps = min(kTileK, G.T - gen * kTileK);
-            A.outP = G.state[(gen + 1) & 1][0]; A.outVx = G.state[(gen + 1) & 1][1]; A.outVy = G.state[(gen + 1) & 1][2];
-            computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, w);
+            TileRun run;
+            run.t0 = gen * kTileK;
+            run.nsteps = min(kTileK, G.T - gen * kTileK);
+            run.outP = G.state[(gen + 1) & 1][0]; run.outVx = G.state[(gen + 1) & 1][1]; run.outVy = G.state[(gen + 1) & 1][2];
+            computeTile<NW, R, CS>(L, A0, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, w, run);
 
             const bool needSlowPath = __syncthreads_or(wp == 0 && !nextIssued);      // also: every store of this tile is issued
             if (wp == 0) { prevSlot = s * tps + ty * L.tiles_x + tx; prevGen = gen; }
@@ -828,6 +847,193 @@ namespace pvc
         // publish the last tile
         __syncthreads();
         if (wp == 0 && lane == 0 && prevSlot >= 0) storeRelease(G.doneGen + prevSlot, prevGen + 1);
+    }
+
+    // ---- warp-specialised generational variant -------------------------------------------------------------------
+    // Same work-item / dependency scheme as fusedStepGenKernel, but all scheduling lives in ONE extra producer warp so
+    // the NW compute warps never touch a global counter or flag:
+    //   producer: fetch item -> probe the 9 dependency counters (one lane each) -> wait "stage empty" -> publish the
+    //             item's coordinates in shared memory -> expect_tx + 3 TMA tensor copies;  then wait "tile done" of
+    //             the tile being computed and st.release its completion counter (the producer, not the compute warps,
+    //             absorbs the store-drain latency of the release).
+    //   compute : wait "full" (TMA landed) -> LDS stage into registers -> barrier, arrive "empty" -> 4 steps ->
+    //             barrier, arrive "done".
+    // Three mbarriers (full / empty / done), one shared-memory stage.
+    __device__ __forceinline__ void mbarArrive(uint64_t* bar)
+    {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+    }
+    // bounded wait: returns false (and raises the abort flag) instead of hanging the GPU on a protocol error
+    __device__ __forceinline__ bool mbarWaitBounded(uint64_t* bar, uint32_t parity, int* abortFlag)
+    {
+        for (unsigned spins = 0;; ++spins)
+        {
+            uint32_t ready;
+            asm volatile("{\n.reg .pred r;\nmbarrier.try_wait.parity.shared::cta.b64 r, [%1], %2;\nselp.u32 %0, 1, 0, r;\n}\n"
+                         : "=r"(ready) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+            if (ready) return true;
+            if ((spins & 0x3ffu) == 0x3ffu && (spins > (1u << 24) || *(volatile int*)abortFlag)) { atomicExch(abortFlag, 1); return false; }
+        }
+    }
+
+    template <int NW, int R, bool CS>
+    __global__ void __launch_bounds__((NW + 1) * 32, 1)
+    fusedStepWsKernel(const Layout L, const FusedArgs A0, const GenArgs G, const int numTiles,
+                      const __grid_constant__ TensorMaps6 maps)
+    {
+        constexpr int TR = NW * R;
+        constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
+        extern __shared__ __align__(128) unsigned char smemRaw[];
+        float* stage = reinterpret_cast<float*>(smemRaw);                                        // [3][TR][128]
+        float4* sCoef = reinterpret_cast<float4*>(smemRaw + 3 * kPlaneBytes);                  // [3][TR][32] (CS only)
+        unsigned char* tail = smemRaw + 3 * kPlaneBytes + (CS ? 3 * kPlaneBytes : 0);
+        float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(tail);
+        float4 (*sPBot)[32] = sVxTop + (NW + 1);
+        uint64_t* full = reinterpret_cast<uint64_t*>(sPBot + (NW + 1));
+        uint64_t* empty = full + 1;
+        uint64_t* done = full + 2;
+        volatile int* sItem = reinterpret_cast<volatile int*>(full + 3);     // [0] valid, [1] source, [2] tx, [3] ty, [4] generation
+
+        const int lane = threadIdx.x & 31;
+        const int wp = threadIdx.x >> 5;
+        const int total = G.numGen * numTiles;
+        const int tps = A0.tilesPerSource;
+
+        if (threadIdx.x == 0)
+        {
+            mbarInit(full, 1); mbarInit(empty, 1); mbarInit(done, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (wp == 0)
+        {
+            sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        if (wp == NW)
+        {
+            // ================= producer warp =================
+            auto depsReady = [&](int s, int tx, int ty, int gen, bool block) -> bool {
+                if (gen == 0) return true;
+                const int dx = lane % 3 - 1, dy = lane / 3 - 1;
+                const int nx = tx + dx, ny = ty + dy;
+                const bool mine = lane < 9 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y;
+                const int* slot = G.doneGen + (size_t)s * tps + (mine ? ny * L.tiles_x + nx : 0);
+                unsigned spins = 0;
+                while (true)
+                {
+                    const bool ok = !mine || loadAcquire(slot) >= gen;
+                    if (__all_sync(0xffffffffu, ok)) return true;
+                    if (!block) return false;
+                    __nanosleep(32);
+                    ++spins;
+                    bool giveUp = false;
+                    if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)G.abortFlag;
+                    if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(G.abortFlag, 1); return false; }
+                }
+            };
+            uint32_t emptyParity = 0, doneParity = 0;
+            bool stageBusy = false;                       // a tile has been handed to the compute warps and not yet drained
+            int prevSlot = -1, prevGen = 0;               // tile being computed, completion not yet published
+            bool alive = true;
+            auto publishPrev = [&]() -> bool {            // wait for the compute warps to finish it, then release its counter
+                if (prevSlot < 0) return true;
+                bool ok = true;
+                if (lane == 0) ok = mbarWaitBounded(done, doneParity, G.abortFlag);
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                doneParity ^= 1u;
+                if (ok && lane == 0) storeRelease(G.doneGen + prevSlot, prevGen + 1);
+                prevSlot = -1;
+                return ok;
+            };
+            while (alive)
+            {
+                int w = 0;
+                if (lane == 0) w = atomicAdd(G.workCounter, 1);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if (w >= total) break;
+                const int order = w % numTiles;
+                const int gen = G.gen0 + w / numTiles;
+                const int s = order % A0.nsrc;
+                const int id = A0.tileOrder[order / A0.nsrc];
+                const int ty = id / L.tiles_x, tx = id - ty * L.tiles_x;
+
+                bool ready = depsReady(s, tx, ty, gen, false);
+                if (!ready)
+                {   // it may depend on the tile our own compute warps are working on: publish that first, then wait for real
+                    if (!publishPrev()) { alive = false; break; }
+                    ready = depsReady(s, tx, ty, gen, true);
+                    if (!ready) { alive = false; break; }
+                }
+                if (stageBusy)
+                {
+                    bool ok = true;
+                    if (lane == 0) ok = mbarWaitBounded(empty, emptyParity, G.abortFlag);
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    emptyParity ^= 1u;
+                    if (!ok) { alive = false; break; }
+                }
+                if (lane == 0)
+                {
+                    sItem[0] = 1; sItem[1] = s; sItem[2] = tx; sItem[3] = ty; sItem[4] = gen;
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    const CUtensorMap* m = maps.m + 3 * (gen & 1);
+                    mbarExpectTx(full, 3u * kPlaneBytes);
+                    tmaLoadTile3d(stage, m + 0, tx * kValidCols, ty * L.valid_rows, s, full);
+                    tmaLoadTile3d(stage + (size_t)TR * kTileCols, m + 1, tx * kValidCols, ty * L.valid_rows, s, full);
+                    tmaLoadTile3d(stage + (size_t)2 * TR * kTileCols, m + 2, tx * kValidCols, ty * L.valid_rows, s, full);
+                }
+                __syncwarp();
+                stageBusy = true;
+                // the tile handed over before this one is (or was) being computed: publish it once the compute warps are done
+                if (!publishPrev()) { alive = false; break; }
+                prevSlot = s * tps + ty * L.tiles_x + tx; prevGen = gen;
+            }
+            // drain: publish the last tile, then tell the compute warps to stop
+            if (alive) alive = publishPrev();
+            if (stageBusy && alive)
+            {
+                bool ok = true;
+                if (lane == 0) ok = mbarWaitBounded(empty, emptyParity, G.abortFlag);
+                (void)ok;
+            }
+            if (lane == 0) { sItem[0] = 0; mbarArrive(full); }          // wake the compute warps with "no more work"
+            return;
+        }
+
+        // ================= compute warps =================
+        uint32_t fullParity = 0;
+        while (true)
+        {
+            if (!mbarWaitBounded(full, fullParity, G.abortFlag)) break;
+            fullParity ^= 1u;
+            if (sItem[0] == 0) break;
+            const int s = sItem[1], tx = sItem[2], ty = sItem[3], gen = sItem[4];
+            float p[R][4], vx[R][4], vy[R][4];
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const int row = wp * R + j;
+                const float4 a = *reinterpret_cast<const float4*>(stage + ((size_t)(0 * TR + row)) * kTileCols + lane * 4);
+                const float4 b = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + row)) * kTileCols + lane * 4);
+                const float4 c = *reinterpret_cast<const float4*>(stage + ((size_t)(2 * TR + row)) * kTileCols + lane * 4);
+                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+            }
+            computeBarrier<NW>();                               // every compute thread has drained the stage and read sItem
+            if (threadIdx.x == 0) mbarArrive(empty);
+
+            TileRun run;
+            run.t0 = gen * kTileK;
+            run.nsteps = min(kTileK, G.T - gen * kTileK);
+            run.outP = G.state[(gen + 1) & 1][0]; run.outVx = G.state[(gen + 1) & 1][1]; run.outVy = G.state[(gen + 1) & 1][2];
+            computeTile<NW, R, CS>(L, A0, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoef, -1, run);
+
+            computeBarrier<NW>();                               // every store of this tile has been issued
+            if (threadIdx.x == 0) mbarArrive(done);
+        }
     }
 
     // Per-cell coefficients of the general path, rebuilt after every geometry edit from the wall plane w.
@@ -916,7 +1122,7 @@ namespace pvc
                                          {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
                                          {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
                                          {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
-                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3} };
+                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3}, {16, 4, 1, 4}, {16, 4, 1, 4}, {12, 6, 1, 4}, {15, 4, 1, 4}, {15, 4, 1, 4}, {11, 6, 1, 4} };
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -1037,7 +1243,7 @@ namespace pvc
         return PVC_OK;
     }
 
-    template <int NW, int R, bool CS>
+    template <int NW, int R, bool CS, bool WS = false>
     static int launchGen(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         const Layout& L = s->L;
@@ -1049,12 +1255,15 @@ namespace pvc
         static bool configured[64] = {};
         if (!configured[s->device & 63])
         {
-            cudaError_t e = cudaFuncSetAttribute(fusedStepGenKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e;
+            if constexpr (WS) e = cudaFuncSetAttribute(fusedStepWsKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else e = cudaFuncSetAttribute(fusedStepGenKernel<NW, R, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { setError("generational kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
             configured[s->device & 63] = true;
         }
         int maxCtas = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtas, fusedStepGenKernel<NW, R, CS>, NW * 32, smem);
+        if constexpr (WS) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtas, fusedStepWsKernel<NW, R, CS>, (NW + 1) * 32, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxCtas, fusedStepGenKernel<NW, R, CS>, NW * 32, smem);
         if (maxCtas < 1) { setError("generational kernel does not fit an SM"); return PVC_ERR_CUDA; }
         const int numTiles = L.tiles_x * L.tiles_y * nsrc;
         const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;          // all CTAs must be co-resident
@@ -1075,7 +1284,8 @@ namespace pvc
         {
             G.gen0 = g0; G.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
             G.workCounter = s->tileCounters + k;
-            fusedStepGenKernel<NW, R, CS><<<grid, NW * 32, smem, s->stream>>>(L, A, G, numTiles, maps);
+            if constexpr (WS) fusedStepWsKernel<NW, R, CS><<<grid, (NW + 1) * 32, smem, s->stream>>>(L, A, G, numTiles, maps);
+            else fusedStepGenKernel<NW, R, CS><<<grid, NW * 32, smem, s->stream>>>(L, A, G, numTiles, maps);
             *launches += 1;
         }
         s->cur = gens & 1;
@@ -1182,6 +1392,12 @@ namespace pvc
             case 30: return launchGen<16, 4, true>(s, nsrc, t0, t1, hist, launches);
             case 31: return launchGen<16, 4, false>(s, nsrc, t0, t1, hist, launches);
             case 32: return launchGen<12, 6, false>(s, nsrc, t0, t1, hist, launches);
+            case 33: return launchGen<16, 4, true, true>(s, nsrc, t0, t1, hist, launches);
+            case 34: return launchGen<16, 4, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 35: return launchGen<12, 6, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 36: return launchGen<15, 4, true, true>(s, nsrc, t0, t1, hist, launches);
+            case 37: return launchGen<15, 4, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 38: return launchGen<11, 6, true, true>(s, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }
@@ -1205,6 +1421,8 @@ namespace pvc
             case 806: return maskVariant<8, 6, 1>(s);
             case 1006: return maskVariant<10, 6, 1>(s);
             case 1206: return maskVariant<12, 6, 1>(s);
+            case 1504: return maskVariant<15, 4, 1>(s);
+            case 1106: return maskVariant<11, 6, 1>(s);
             default: return maskVariant<12, 8, 1>(s);
         }
     }

@@ -5,7 +5,7 @@ from planeverb_b200 import pvcuda
 scenes = common.load_scenes()
 size, scale = common.scaled_config(1024)
 for S in (1, 2, 4):
-    for var in (18, 22, 30, 31, 32):
+    for var in (18, 22, 30, 33, 36, 37, 38):
         G = pvcuda.Scene(size, size, 275, T=1000, max_sources=S, variant=var, efree=0.0447895788)
         for b in common.boxes_of(scenes, 'BigRoom', scale): G.add_aabb(*b)
         Ls = common.listeners_for(S, scale)

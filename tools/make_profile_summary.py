@@ -22,8 +22,8 @@ unit = rows[1][hdr.index("Metric Unit")]
 scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1e-3)       # -> microseconds
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(OUT, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -s 3012 -c 1010 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
-    f.write("# one timed bench step (1 solve = 1000 fused launches + analyzer); times are cold-cache and serialised: compare SHARES\n")
+    f.write("# PVC_NO_GRAPHS=1 ncu --metrics gpu__time_duration.sum --clock-control none -s 18 -c 12 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
+    f.write("# two solves of the bench (1 solve = 4 step-kernel launches of <= 256 generations x 4 time steps + 2 analyzer kernels); cold-cache, serialised: compare SHARES\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'total_us':>12s} {'avg_us':>9s} {'share':>7s}\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k[:60]:60s} {n:8d} {t*scale:12.1f} {t*scale/n:9.2f} {100*t/tot:6.1f}%\n")
@@ -63,8 +63,9 @@ with open(os.path.join(OUT, f"{tag}_ncu_kernels.txt"), "w") as f:
                 traffic = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
 print(open(os.path.join(OUT, f"{tag}_ncu_kernels.txt")).read()[:3000])
 if traffic:
-    json.dump({"kernel": "pvc::fusedStepKernel", "dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_ncu_kernels.txt (ncu --set full, cold L2)",
-               "algorithmic_bytes_per_launch": 28 * 1024 * 1024 * 4 * 4}, open(os.path.join(OUT, "fused_step_traffic.json"), "w"), indent=1)
+    json.dump({"kernel": "pvc::fusedStepWsKernel<15,4,true>", "dram_bytes_per_launch": traffic, "generations_in_that_launch": 100,
+               "dram_bytes_per_generation": traffic / 100.0, "source": f"profiles/{tag}_ncu_kernels.txt (ncu --set full, cold L2)",
+               "note": "captured with --T 400: ONE launch = 100 generations x 4 steps, 4 sources, 1024x1024", "algorithmic_bytes_per_launch": 28 * 1024 * 1024 * 4 * 400}, open(os.path.join(OUT, "fused_step_traffic.json"), "w"), indent=1)
 for name in ("bench_default.json", "timeline.txt"):
     src = os.path.join(GO, name)
     if os.path.exists(src):

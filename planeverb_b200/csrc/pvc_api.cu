@@ -49,8 +49,9 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto: the warp-specialised generational kernel (15 compute warps x 4 rows + a producer warp, TMA
-    // tensor loads, per-tile dependency counters; variant 36) -- fastest at every batch/grid size measured on B200
+    // variant 0 = auto: the second warp-specialised generational kernel (pvc_step_ws2.cu, variant 40: 15 compute warps x
+    // 4 rows + a producer warp that prefetches every per-tile input with TMA / into a shared-memory record, source-group
+    // item order that keeps a group's state L2-resident) -- fastest at every batch/grid size measured on B200
     // (profiles/).  It needs cuTensorMapEncodeTiled from the driver; without it fall back to the plain 8 x 6 kernel.
     static int resolveVariant(const pvc_config& c)
     {
@@ -59,7 +60,7 @@ namespace pvc
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
-        return tma ? 36 : 18;
+        return tma ? 40 : 18;
     }
 
     static bool validConfig(const pvc_config* c)
@@ -274,6 +275,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMemsetAsync(s->slowMask, 0, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
+    PVC_TRY(cudaMalloc(&s->bpMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 16 * 32));
     PVC_TRY(cudaMalloc(&s->firstActive, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     s->tileCounterCount = cfg->T / kTileK + 2;
@@ -305,7 +307,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);

@@ -92,8 +92,10 @@ struct pvc_solver
     float* w;                // wall plane (air flag / admittance), the geometry's source of truth
     float* coef[3];          // general-path coefficient planes bp, gx, gy derived from w (pvc_step_fused.cu)
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
+    uint32_t* bpMask;        // per (tile, warp, lane): air flags of the thread's cells (pvc_step_ws2.cu)
     int slowMaskDirty;
-    int* tileOrder;          // tiles_x*tiles_y tile ids, most expensive first
+    int* tileOrder;          // tiles_x*tiles_y tile ids: most expensive first, or row-major (tileOrderNatural)
+    int tileOrderNatural;
     int* firstActive;        // [source][tile][32]: activity hints written by the fused kernels, read by the analyzer
     int hintsValid;          // the last run's step kernel filled firstActive
     int* tileCounters;       // one work counter per launch of the persistent TMA variants (slot 0: abort flag of the generational one)
@@ -127,6 +129,8 @@ namespace pvc
     int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int rebuildSlowMask(pvc_solver* s);
+    int launchWs2Steps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches);
+    int rebuildWs2Descriptors(pvc_solver* s, int variant);
     int buildTensorMaps(pvc_solver* s);
     int fusedTileRows(int variant);
     int fusedWarpRows(int variant);

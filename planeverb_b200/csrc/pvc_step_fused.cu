@@ -1122,7 +1122,8 @@ namespace pvc
                                          {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
                                          {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
                                          {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
-                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3}, {16, 4, 1, 4}, {16, 4, 1, 4}, {12, 6, 1, 4}, {15, 4, 1, 4}, {15, 4, 1, 4}, {11, 6, 1, 4} };
+                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3}, {16, 4, 1, 4}, {16, 4, 1, 4}, {12, 6, 1, 4}, {15, 4, 1, 4}, {15, 4, 1, 4}, {11, 6, 1, 4},
+                                         {14, 4, 1, 5}, {15, 4, 1, 5} };       // 39, 40: pvc_step_ws2.cu
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -1345,7 +1346,16 @@ namespace pvc
             for (int wIdx = 0; wIdx < NW; ++wIdx) { const uint32_t m = modes[(size_t)t * 32 + wIdx]; c += (m == 2u) ? 30 : (m == 1u ? 13 : 10); }
             cost[(size_t)t] = std::make_pair(-c, t);
         }
-        std::sort(cost.begin(), cost.end());
+        // The generational kernels keep the row-major tile order: every dependency of an item is then about one
+        // generation old, whereas "expensive tiles first" makes the wall tiles at the head of generation g wait for
+        // neighbours at the tail of generation g-1 (measured: 7 % slower).  The one-launch-per-4-steps kernels sort by
+        // cost so the expensive tiles do not form the launch's tail.  PVC_TILE_ORDER=natural|cost overrides.
+        static const char* orderEnv = getenv("PVC_TILE_ORDER");
+        int vCur = s->cfg.reserved; if (vCur < 0 || vCur >= kNumVariants) vCur = 0;
+        bool natural = kVariants[vCur].persistent >= 4;
+        if (orderEnv) natural = orderEnv[0] == 'n';
+        if (!natural) std::sort(cost.begin(), cost.end());
+        s->tileOrderNatural = natural ? 1 : 0;
         std::vector<int> order((size_t)tiles);
         for (int t = 0; t < tiles; ++t) order[(size_t)t] = cost[(size_t)t].second;
         if (cudaMemcpyAsync(s->tileOrder, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
@@ -1398,6 +1408,7 @@ namespace pvc
             case 36: return launchGen<15, 4, true, true>(s, nsrc, t0, t1, hist, launches);
             case 37: return launchGen<15, 4, false, true>(s, nsrc, t0, t1, hist, launches);
             case 38: return launchGen<11, 6, true, true>(s, nsrc, t0, t1, hist, launches);
+            case 39: case 40: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }
@@ -1406,8 +1417,10 @@ namespace pvc
     {
         buildCoefficientsKernel<<<(unsigned)((s->L.plane + 255) / 256), 256, 0, s->stream>>>(s->L, s->w, s->coef[0], s->coef[1], s->coef[2]);
         int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
+        if (kVariants[v].persistent == 5) { const int rc = rebuildWs2Descriptors(s, v); if (rc) return rc; }
         switch (kVariants[v].nw * 100 + kVariants[v].r)
         {
+            case 1404: return maskVariant<14, 4, 1>(s);
             case 808: return maskVariant<8, 8, 1>(s);
             case 1604: return maskVariant<16, 4, 1>(s);
             case 1608: return maskVariant<16, 8, 1>(s);

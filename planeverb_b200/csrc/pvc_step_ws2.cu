@@ -1,0 +1,793 @@
+// pvc_step_ws2.cu -- second-generation warp-specialised generational step kernel (variants 39/40).
+//
+// Same numerics, work-item order and dependency protocol as fusedStepWsKernel (pvc_step_fused.cu): K = 4 time
+// steps of Grid::GenerateResponseCPU (ProjectPlaneverb/src/FDTD/FDTD.cpp:122-235) per tile pass with the state
+// in registers, tiles of (NW*R) x 128 cells incl. a 4-cell halo, one persistent CTA per SM pulling (generation,
+// tile) items from a global counter, per-tile completed-generation counters instead of a grid-wide barrier.
+// What changed, all of it read off the ncu source-level stall profile of the first kernel
+// (profiles/r01_ws_stalls.txt: 19 % of the compute warps' time was long-scoreboard waits in the per-tile
+// prologue/epilogue, 4 % CTA barriers outside the step loop):
+//
+//   * The compute warps issue NO global loads.  Everything a tile needs besides its state -- path mode per warp,
+//     activity hint per warp, the source cell, the four pulse samples, the output buffer parity -- is fetched by
+//     the producer warp one tile ahead and handed over in a small shared-memory record (double-buffered by tile
+//     parity) that becomes visible with the TMA "full" barrier.
+//   * The general (wall) path reads its coefficients from shared memory that the PRODUCER fills with TMA: two 2-D
+//     tensor copies (gx, gy planes) plus one 1-D bulk copy of a per-(tile, warp, lane) bit mask of the air flag bp,
+//     on their own mbarrier, CB-deep buffered (CB = 2: the coefficients of the next wall tile land while the
+//     current one computes).  bp travels as 16 bits per thread instead of a third fp32 plane.
+//   * No kernel parameter is indexed dynamically (the first kernel's G.state[(gen+1)&1][f] went through local
+//     memory); buffers are picked with selects.
+//   * Per tile the only CTA-wide synchronisation left is the two named barriers per time step.  The stage drain and
+//     the "tile stored" hand-offs are per-warp mbarrier arrivals (count NW), the first vertical halo row of a pass is
+//     read straight from the TMA stage instead of being exchanged, and the last step's exchange write is skipped.
+//   * One step loop per path (fast / edge / general) instead of a three-way branch inside one loop; the activity
+//     OR is skipped once a warp's block is known to be active.
+//
+// Roofline: HBM; algorithmic bytes 28 B per cell-update.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "pvc_internal.h"
+
+namespace pvc
+{
+    namespace ws2
+    {
+        // ---------------------------------------------------------------- small PTX helpers
+        __device__ __forceinline__ uint32_t smemAddr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+        __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+        }
+        __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+        {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+        }
+        __device__ __forceinline__ void mbarArrive(uint64_t* bar)
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+        }
+        // bounded wait: returns false (and raises the abort flag) instead of hanging the GPU on a protocol error
+        __device__ __forceinline__ bool mbarWaitBounded(uint64_t* bar, uint32_t parity, int* abortFlag)
+        {
+            for (unsigned spins = 0;; ++spins)
+            {
+                uint32_t ready;
+                asm volatile("{\n.reg .pred r;\nmbarrier.try_wait.parity.shared::cta.b64 r, [%1], %2;\nselp.u32 %0, 1, 0, r;\n}\n"
+                             : "=r"(ready) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+                if (ready) return true;
+                if ((spins & 0x3ffu) == 0x3ffu && (spins > (1u << 24) || *(volatile int*)abortFlag)) { atomicExch(abortFlag, 1); return false; }
+            }
+        }
+        __device__ __forceinline__ void tmaLoad3d(void* dstSmem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
+        {
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smemAddr(dstSmem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(bar)) : "memory");
+        }
+        __device__ __forceinline__ void tmaLoad2d(void* dstSmem, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+        {
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smemAddr(dstSmem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smemAddr(bar)) : "memory");
+        }
+        __device__ __forceinline__ void bulkLoad1d(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+        {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+        }
+        __device__ __forceinline__ int loadAcquire(const int* p)
+        {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            return v;
+        }
+        __device__ __forceinline__ void storeRelease(int* p, int v)
+        {
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        }
+        template <int NW>
+        __device__ __forceinline__ void computeBarrier()
+        {
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+        }
+        __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
+
+        // ---------------------------------------------------------------- kernel arguments (never indexed dynamically)
+        struct Args
+        {
+            float* p0; float* vx0; float* vy0;     // ping-pong buffer 0 (generation g reads buffer g & 1, writes the other)
+            float* p1; float* vx1; float* vy1;
+            float* hist;                           // pressure history (null: no record)
+            const uint32_t* mode;                  // [tile][32] path mode per warp (slowMaskKernel)
+            const uint32_t* bpMask;                // [tile][NW][32] bit j*4+k = cell (j,k) of the thread is an interior air cell
+            const int* tileOrder;
+            int* firstActive;                      // [source][tile][32]
+            const SourceParams* src;
+            const float* pulse;
+            int* doneGen;                          // [source][tile] generations completed
+            int* workCounter;
+            int* abortFlag;
+            int tilesPerSource, nsrc, numTiles;    // numTiles = tilesPerSource * nsrc
+            int gen0, numGen, T;
+            int earlyFetch;
+            int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
+            float courant;
+        };
+        struct Maps { CUtensorMap state[6]; CUtensorMap coef[2]; };       // state: [buffer][p,vx,vy]; coef: gx, gy
+
+        // producer -> compute hand-off record of one tile
+        struct Meta
+        {
+            int valid, s, tx, ty, gen;
+            int coefBuf, coefParity;               // coefBuf < 0: no general-path warp in this tile
+            int srcR, srcC;
+            int pad[3];
+            float pulse[4];
+            int mode[16];
+            int hint[16];
+        };
+
+        enum { kFast = 0, kEdge = 1, kGeneral = 2 };
+
+        // One time step of one warp's R x 128 block.  MODE is the warp-uniform path (see slowMaskKernel):
+        //   fast     every cell of the warp, and each one's up/left neighbour, is interior air: 11 fp32 ops per cell
+        //   edge     no wall, but the warp touches the grid edge / padding / guard band: position-only overwrites
+        //   general  some cell or neighbour is a wall: coefficient planes gx, gy from shared memory, bp from a bit mask
+        // All arithmetic is explicit round-to-nearest mul/add/sub in the reference's operation order (no FMA).
+        template <int NW, int R, int MODE>
+        struct Stepper
+        {
+            const Layout& L;
+            const float C;
+            const int lane, wp, rBase;
+            const uint32_t colOut, colPad, colLeft;      // edge path: column classes of the thread's 4 cells
+            const uint32_t bpBits;                       // general path: air flags of the thread's R x 4 cells
+            const float4* cGx; const float4* cGy;        // general path: this thread's coefficient float4s, row stride 32
+
+            __device__ __forceinline__ void pressure(float (&p)[R][4], const float (&vx)[R][4], const float (&vy)[R][4], const float4 vxBelow) const
+            {
+                const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                    bool rowDead = false;
+                    if (MODE == kEdge) { const int r = rBase + j; rowDead = (r < 0) || (r >= L.gx); }
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                        const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                        if (MODE == kFast) p[j][k] = pn;
+                        else if (MODE == kEdge) p[j][k] = (rowDead || (((colOut | colPad) >> k) & 1u)) ? 0.f : pn;
+                        else p[j][k] = ((bpBits >> (j * 4 + k)) & 1u) ? pn : 0.f;
+                    }
+                }
+            }
+
+            __device__ __forceinline__ void velocity(const float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], const float4 pAbove) const
+            {
+                const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                    if (MODE == kFast)
+                    {
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
+                            vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                        }
+                    }
+                    else if (MODE == kEdge)
+                    {
+                        const int r = rBase + j;
+                        const bool rowOut = (r < 0) || (r > L.gx);
+                        const bool rowTop = (r == 0), rowPad = (r == L.gx);
+                        const uint32_t colDeadX = colOut | colPad;          // vx: the padding column is never driven
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            const float pt = p[j][k];
+                            float nx = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
+                            float ny = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
+                            nx = rowTop ? -pt : nx;                                  // FDTD.cpp:208
+                            nx = rowPad ? pu : nx;                                   // FDTD.cpp:209
+                            nx = (rowOut || ((colDeadX >> k) & 1u)) ? 0.f : nx;
+                            ny = ((colLeft >> k) & 1u) ? -pt : ny;                   // FDTD.cpp:220
+                            ny = ((colPad >> k) & 1u) ? pl : ny;                     // FDTD.cpp:221
+                            ny = (rowOut || rowPad || ((colOut >> k) & 1u)) ? 0.f : ny;
+                            vx[j][k] = nx; vy[j][k] = ny;
+                        }
+                    }
+                    else
+                    {
+                        // per-cell coefficients (buildCoefficientsKernel): walls, the absorbing grid edge, padding and the
+                        // guard band are all data here, the code is straight-line
+                        const float4 x4 = cGx[j * 32];
+                        const float4 y4 = cGy[j * 32];
+                        const float ga[4] = { x4.x, x4.y, x4.z, x4.w };
+                        const float ha[4] = { y4.x, y4.y, y4.z, y4.w };
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                            const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                            const float pt = p[j][k];
+                            const bool air = (bpBits >> (j * 4 + k)) & 1u;
+                            const float airX = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
+                            const float airY = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
+                            const float wallX = __fmul_rn(ga[k], air ? pt : pu);
+                            const float wallY = __fmul_rn(ha[k], air ? pt : pl);
+                            vx[j][k] = (air && isAirF(ga[k])) ? airX : wallX;
+                            vy[j][k] = (air && isAirF(ha[k])) ? airY : wallY;
+                        }
+                    }
+                }
+            }
+        };
+
+        // per-thread, per-tile constants of the record / inject / exchange part of a step
+        struct TileCtx
+        {
+            float* hist;              // sample t0 of the thread's 4 cells in row rBase (null: no record)
+            size_t histRow;           // floats between rows of the history
+            uint32_t ownRows;         // bit j: row j of this thread is owned (stored), see computeTile
+            int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
+            const float* pulse;       // 4 samples of this generation (shared memory)
+            bool track;               // this warp's block is not yet known to be active: accumulate the activity OR
+        };
+
+        template <int NW, int R, int MODE>
+        __device__ __forceinline__ void stepLoop(const Stepper<NW, R, MODE>& S, TileCtx& X, const int nsteps,
+                                                 float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], float4 vxBelow,
+                                                 float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
+        {
+            const int lane = S.lane, wp = S.wp;
+            #pragma unroll 1
+            for (int step = 0; step < nsteps; ++step)
+            {
+                // ---- pressure sub-step (FDTD.cpp:125-141)
+                if (step > 0) vxBelow = sVxTop[wp + 1][lane];
+                S.pressure(p, vx, vy, vxBelow);
+                sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+                computeBarrier<NW>();
+                // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
+                S.velocity(p, vx, vy, sPBot[wp][lane]);
+                // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
+                if (X.hist)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if ((X.ownRows >> j) & 1u)
+                            __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                    X.hist += kHistChunk;
+                    if (X.track)
+                    {
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                        {
+                            activity |= __float_as_uint(p[j][0]) | __float_as_uint(p[j][1]);
+                            activity |= __float_as_uint(p[j][2]) | __float_as_uint(p[j][3]);
+                        }
+                    }
+                }
+                if (X.sj >= 0)
+                {
+                    // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
+                    const float add = X.pulse[step];
+                    const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
+                    const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (j == X.sj)
+                        {
+                            p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
+                            p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
+                        }
+                }
+                if (step + 1 < nsteps) sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                // also the write-after-read fence of sPBot for the next pass's first pressure sub-step
+                computeBarrier<NW>();
+            }
+        }
+
+        template <int NW, int R, int CB>
+        struct Smem
+        {
+            static constexpr int TR = NW * R;
+            static constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
+            static constexpr uint32_t kMaskBytes = NW * 32 * sizeof(uint32_t);
+            static constexpr size_t offStage = 0;
+            static constexpr size_t offCoef = offStage + 3 * (size_t)kPlaneBytes;
+            static constexpr size_t offMask = offCoef + (size_t)CB * 2 * kPlaneBytes;
+            static constexpr size_t offVxTop = offMask + (size_t)CB * kMaskBytes;
+            static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
+            static constexpr size_t offMeta = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);
+            static constexpr size_t offBars = offMeta + 2 * sizeof(Meta);
+            static constexpr size_t total = offBars + (4 + CB) * sizeof(uint64_t);
+        };
+
+        template <int NW, int R, int CB>
+        __global__ void __launch_bounds__((NW + 1) * 32, 1)
+        stepKernel(const Layout L, const Args A, const __grid_constant__ Maps maps)
+        {
+            using SM = Smem<NW, R, CB>;
+            constexpr int TR = SM::TR;
+            static_assert(NW <= 16 && R * 4 <= 32, "Meta holds 16 warps; bpMask holds 32 cells per thread");
+            extern __shared__ __align__(128) unsigned char smemRaw[];
+            float* stage = reinterpret_cast<float*>(smemRaw + SM::offStage);                       // [3][TR][128]
+            float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);                      // [CB][2][TR][32]
+            uint32_t* sMask = reinterpret_cast<uint32_t*>(smemRaw + SM::offMask);                  // [CB][NW][32]
+            float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
+            float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
+            Meta* meta = reinterpret_cast<Meta*>(smemRaw + SM::offMeta);                           // [2]
+            uint64_t* full = reinterpret_cast<uint64_t*>(smemRaw + SM::offBars);
+            uint64_t* empty = full + 1;
+            uint64_t* done = full + 2;                                                              // [2], by tile parity
+            uint64_t* fullCoef = full + 4;                                                          // [CB]
+
+            const int lane = threadIdx.x & 31;
+            const int wp = threadIdx.x >> 5;
+            const int total = A.numGen * A.numTiles;
+            const int tps = A.tilesPerSource;
+
+            if (threadIdx.x == 0)
+            {
+                mbarInit(full, 1); mbarInit(empty, NW); mbarInit(done, NW); mbarInit(done + 1, NW);
+                for (int b = 0; b < CB; ++b) mbarInit(fullCoef + b, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            if (wp == 0)
+            {
+                sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+
+            if (wp == NW)
+            {
+                // ================= producer warp =================
+                auto depsReady = [&](int s, int tx, int ty, int gen, bool block) -> bool {
+                    if (gen == 0) return true;
+                    const int dx = lane % 3 - 1, dy = lane / 3 - 1;
+                    const int nx = tx + dx, ny = ty + dy;
+                    const bool mine = lane < 9 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y;
+                    const int* slot = A.doneGen + (size_t)s * tps + (mine ? ny * L.tiles_x + nx : 0);
+                    unsigned spins = 0;
+                    while (true)
+                    {
+                        const bool ok = !mine || loadAcquire(slot) >= gen;
+                        if (__all_sync(0xffffffffu, ok)) return true;
+                        if (!block) return false;
+                        __nanosleep(32);
+                        ++spins;
+                        bool giveUp = false;
+                        if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)A.abortFlag;
+                        if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(A.abortFlag, 1); return false; }
+                    }
+                };
+                // "done" alternates between two mbarriers by tile parity: the producer looks at done(k-1) only after it has
+                // fetched the item after k, and with a single barrier a fast tile k could complete a second phase before the
+                // first one was observed (the parity wait would then never succeed).  Tile k+1, the next user of the same
+                // barrier, is handed out only after done(k-1) has been consumed, so with two barriers no phase can be skipped.
+                uint32_t emptyParity = 0, doneParity[2] = { 0u, 0u };
+                int prevSeq = 0;
+                uint32_t coefPhase = 0;                       // wall tiles handed out so far: buffer = phase % CB, parity = (phase / CB) & 1
+                bool stageBusy = false;                       // a tile has been handed to the compute warps and not yet drained
+                bool prevUsedCoef = false;                    // the tile being computed reads a coefficient buffer
+                int prevSlot = -1, prevGen = 0;               // tile being computed, completion not yet published
+                bool alive = true;
+                int seq = 0;
+                auto publishPrev = [&]() -> bool {            // wait for the compute warps to finish it, then release its counter
+                    if (prevSlot < 0) return true;
+                    bool ok = true;
+                    if (lane == 0) ok = mbarWaitBounded(done + (prevSeq & 1), (prevSeq & 1) ? doneParity[1] : doneParity[0], A.abortFlag);
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (prevSeq & 1) doneParity[1] ^= 1u; else doneParity[0] ^= 1u;
+                    if (ok && lane == 0) storeRelease(A.doneGen + prevSlot, prevGen + 1);
+                    prevSlot = -1;
+                    prevUsedCoef = false;
+                    return ok;
+                };
+                // Fetching a work item costs two dependent L2 round trips: the counter atomic, then -- all in flight
+                // together -- the record loads and the dependency probe.  By default (earlyFetch = 2) the next item is
+                // fetched right after the TMA of the current one has been issued, before waiting for the tile in flight, so
+                // those round trips never sit between a drained stage and the next TMA; the probe is repeated just before
+                // the hand-over if it failed early.  earlyFetch = 0 (PVC_EARLY_FETCH) fetches at the top of the loop.
+                struct Item { int valid, s, id, tx, ty, gen, mode, hint, misc; bool anySlow, ready; } nx;
+                auto fetchNext = [&]() {
+                    int w = 0;
+                    if (lane == 0) w = atomicAdd(A.workCounter, 1);
+                    w = __shfl_sync(0xffffffffu, w, 0);
+                    nx.valid = w < total;
+                    if (!nx.valid) return;
+                    // item order: chunks of genChunk generations; inside a chunk one source group after the other (a group's
+                    // ping-pong state stays L2-resident for the whole chunk); inside a group generation-major, then tile
+                    // order, then source.  Every dependency of an item (same source, neighbour tiles, previous generation)
+                    // precedes it in this order.
+                    const int chunkItems = A.genChunk * A.numTiles;
+                    const int c = w / chunkItems;
+                    int rem = w - c * chunkItems;
+                    const int gc = min(A.genChunk, A.numGen - c * A.genChunk);
+                    const int groupItems = gc * tps * A.srcGroup;
+                    const int q = rem / groupItems;
+                    rem -= q * groupItems;
+                    const int sq = min(A.srcGroup, A.nsrc - q * A.srcGroup);
+                    const int g = rem / (sq * tps);
+                    rem -= g * (sq * tps);
+                    const int o = rem / sq;
+                    nx.s = q * A.srcGroup + (rem - o * sq);
+                    nx.gen = A.gen0 + c * A.genChunk + g;
+                    nx.id = A.tileOrder ? A.tileOrder[o] : o;          // null: row-major order
+                    nx.ty = nx.id / L.tiles_x; nx.tx = nx.id - nx.ty * L.tiles_x;
+                    // the tile's hand-off record, gathered lane-parallel (loads overlap the dependency probe below)
+                    nx.mode = 0; nx.hint = 0; nx.misc = 0;
+                    if (lane < NW)
+                    {
+                        nx.mode = (int)A.mode[(size_t)nx.id * 32 + lane];
+                        nx.hint = (A.firstActive && A.hist) ? A.firstActive[((size_t)nx.s * tps + nx.id) * 32 + lane] : 0;
+                    }
+                    else if (lane == 16) nx.misc = A.src[nx.s].cell_r;
+                    else if (lane == 17) nx.misc = A.src[nx.s].cell_c;
+                    else if (lane >= 20 && lane < 24)
+                    {
+                        const int t = nx.gen * kTileK + (lane - 20);
+                        nx.misc = __float_as_int(t < A.T ? __ldg(A.pulse + t) : 0.f);
+                    }
+                    nx.ready = (A.earlyFetch == 1) ? false : depsReady(nx.s, nx.tx, nx.ty, nx.gen, false);
+                    nx.anySlow = __ballot_sync(0xffffffffu, lane < NW && nx.mode == kGeneral) != 0u;
+                };
+                if (A.earlyFetch) fetchNext();
+                while (alive)
+                {
+                    if (!A.earlyFetch) fetchNext();
+                    if (!nx.valid) break;
+                    const Item it = nx;
+                    const int s = it.s, id = it.id, tx = it.tx, ty = it.ty, gen = it.gen;
+                    const bool anySlow = it.anySlow;
+                    bool ready = it.ready;
+                    if (!ready && A.earlyFetch) ready = depsReady(s, tx, ty, gen, false);
+                    if (!ready)
+                    {   // it may depend on the tile our own compute warps are working on: publish that first, then wait for real
+                        if (!publishPrev()) { alive = false; break; }
+                        ready = depsReady(s, tx, ty, gen, true);
+                        if (!ready) { alive = false; break; }
+                    }
+                    if (stageBusy)
+                    {
+                        bool ok = true;
+                        if (lane == 0) ok = mbarWaitBounded(empty, emptyParity, A.abortFlag);
+                        ok = __shfl_sync(0xffffffffu, ok, 0);
+                        emptyParity ^= 1u;
+                        if (!ok) { alive = false; break; }
+                    }
+                    // single coefficient buffer: the tile being computed may still be reading it
+                    if (CB == 1 && anySlow && prevUsedCoef) { if (!publishPrev()) { alive = false; break; } }
+
+                    Meta* m = meta + (seq & 1);
+                    const int coefBuf = anySlow ? (int)(coefPhase % CB) : -1;
+                    const int coefParity = (int)((coefPhase / CB) & 1u);
+                    if (lane < NW) { m->mode[lane] = it.mode; m->hint[lane] = it.hint; }
+                    else if (lane == 16) m->srcR = it.misc;
+                    else if (lane == 17) m->srcC = it.misc;
+                    else if (lane >= 20 && lane < 24) m->pulse[lane - 20] = __int_as_float(it.misc);
+                    else if (lane == 24) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        if (anySlow)
+                        {
+                            uint64_t* bar = fullCoef + coefBuf;
+                            float4* dst = sCoef + (size_t)coefBuf * 2 * TR * 32;
+                            mbarExpectTx(bar, 2u * SM::kPlaneBytes + SM::kMaskBytes);
+                            tmaLoad2d(dst, &maps.coef[0], tx * kValidCols, ty * L.valid_rows, bar);
+                            tmaLoad2d(dst + (size_t)TR * 32, &maps.coef[1], tx * kValidCols, ty * L.valid_rows, bar);
+                            bulkLoad1d(sMask + (size_t)coefBuf * NW * 32, A.bpMask + (size_t)id * NW * 32, SM::kMaskBytes, bar);
+                        }
+                        const CUtensorMap* mp = (gen & 1) ? &maps.state[3] : &maps.state[0];
+                        mbarExpectTx(full, 3u * SM::kPlaneBytes);
+                        tmaLoad3d(stage, mp + 0, tx * kValidCols, ty * L.valid_rows, s, full);
+                        tmaLoad3d(stage + (size_t)TR * kTileCols, mp + 1, tx * kValidCols, ty * L.valid_rows, s, full);
+                        tmaLoad3d(stage + (size_t)2 * TR * kTileCols, mp + 2, tx * kValidCols, ty * L.valid_rows, s, full);
+                    }
+                    __syncwarp();
+                    if (anySlow) ++coefPhase;
+                    ++seq;
+                    stageBusy = true;
+                    if (A.earlyFetch) fetchNext();                // the next item's fetch overlaps the tile in flight
+                    // the tile handed over before this one is (or was) being computed: publish it once the compute warps are done
+                    if (!publishPrev()) { alive = false; break; }
+                    prevSlot = s * tps + id; prevGen = gen; prevUsedCoef = anySlow; prevSeq = seq - 1;
+                }
+                // drain: publish the last tile, then tell the compute warps to stop
+                if (alive) alive = publishPrev();
+                if (stageBusy && alive)
+                {
+                    bool ok = true;
+                    if (lane == 0) ok = mbarWaitBounded(empty, emptyParity, A.abortFlag);
+                    (void)ok;
+                }
+                if (lane == 0) { meta[seq & 1].valid = 0; mbarArrive(full); }      // wake the compute warps with "no more work"
+                return;
+            }
+
+            // ================= compute warps =================
+            uint32_t fullParity = 0;
+            int seq = 0;
+            while (true)
+            {
+                if (!mbarWaitBounded(full, fullParity, A.abortFlag)) break;
+                fullParity ^= 1u;
+                const Meta* m = meta + (seq & 1);
+                ++seq;
+                if (m->valid == 0) break;
+                const int s = m->s, tx = m->tx, ty = m->ty, gen = m->gen;
+                const int mode = m->mode[wp];
+                const int hintKnown = m->hint[wp];
+                const int coefBuf = m->coefBuf;
+                const uint32_t coefParity = (uint32_t)m->coefParity;
+
+                float p[R][4], vx[R][4], vy[R][4];
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const int row = wp * R + j;
+                    const float4 a = *reinterpret_cast<const float4*>(stage + ((size_t)(0 * TR + row)) * kTileCols + lane * 4);
+                    const float4 b = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + row)) * kTileCols + lane * 4);
+                    const float4 c = *reinterpret_cast<const float4*>(stage + ((size_t)(2 * TR + row)) * kTileCols + lane * 4);
+                    p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                    vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                    vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+                }
+                // first vertical halo row of the pass: vx of the first row of the warp below, straight from the stage
+                float4 vxBelow = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (wp + 1 < NW) vxBelow = *reinterpret_cast<const float4*>(stage + ((size_t)(1 * TR + (wp + 1) * R)) * kTileCols + lane * 4);
+                __syncwarp();
+                if (lane == 0) mbarArrive(empty);                  // this warp has drained the stage and read the record's scalars
+
+                // ---- per-thread tile constants
+                const int rBase = ty * L.valid_rows - kTileK + wp * R;
+                const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+                const size_t src0 = (size_t)s * L.plane + (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
+                uint32_t colOut = 0u, colPad = 0u, colLeft = 0u;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const int cc = cBase + k;
+                    if (cc < 0 || cc > L.gy) colOut |= 1u << k;
+                    if (cc == L.gy) colPad |= 1u << k;
+                    if (cc == 0) colLeft |= 1u << k;
+                }
+                // owned (stored) rows of this thread: not halo, inside the alloc grid; none for the halo lanes 0 and 31
+                // and for columns past the grid
+                int jLo = kTileK - wp * R, jHi = NW * R - kTileK - wp * R;
+                jLo = max(jLo, 0);
+                jHi = min(min(jHi, R), L.rows - rBase);
+                if (lane == 0 || lane == 31 || cBase >= L.cols) jHi = 0;
+                uint32_t ownRows = 0u;
+                #pragma unroll
+                for (int j = 0; j < R; ++j) if (j >= jLo && j < jHi) ownRows |= 1u << j;
+
+                const int t0 = gen * kTileK;
+                const int nsteps = min(kTileK, A.T - t0);
+                TileCtx X;
+                X.hist = nullptr;
+                if (A.hist)
+                    X.hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
+                           + ((ptrdiff_t)(cBase >> 7) * L.T + t0) * kHistChunk + (cBase & 127);
+                X.histRow = L.hist_row;
+                X.ownRows = ownRows;
+                {
+                    const int sj = m->srcR - rBase, sk = m->srcC - cBase;
+                    const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
+                    X.sj = hasSrc ? sj : -1; X.sk = sk;
+                }
+                X.pulse = m->pulse;
+                const bool hints = (A.firstActive != nullptr) && (A.hist != nullptr);
+                X.track = hints && hintKnown > gen;
+                uint32_t activity = 0u;
+
+                if (mode == kFast)
+                {
+                    const Stepper<NW, R, kFast> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
+                    stepLoop<NW, R, kFast>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                }
+                else if (mode == kEdge)
+                {
+                    const Stepper<NW, R, kEdge> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
+                    stepLoop<NW, R, kEdge>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                }
+                else
+                {
+                    // the coefficient buffer of this tile (usually landed long ago: it was requested one tile ahead)
+                    bool ok = mbarWaitBounded(fullCoef + coefBuf, coefParity, A.abortFlag);
+                    (void)ok;
+                    const float4* cg = sCoef + (size_t)coefBuf * 2 * TR * 32 + (size_t)(wp * R) * 32 + lane;
+                    const uint32_t bpBits = sMask[(size_t)coefBuf * NW * 32 + wp * 32 + lane];
+                    const Stepper<NW, R, kGeneral> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, bpBits, cg, cg + (size_t)TR * 32 };
+                    stepLoop<NW, R, kGeneral>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                }
+
+                // ---- store the owned cells of the new state (generation g reads buffer g & 1, writes the other)
+                {
+                    float* gp = ((gen & 1) ? A.p0 : A.p1) + src0;
+                    float* gx = ((gen & 1) ? A.vx0 : A.vx1) + src0;
+                    float* gy = ((gen & 1) ? A.vy0 : A.vy1) + src0;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                    {
+                        if ((ownRows >> j) & 1u)
+                        {
+                            *reinterpret_cast<float4*>(gp + (size_t)j * L.pitch) = make_float4(p[j][0], p[j][1], p[j][2], p[j][3]);
+                            *reinterpret_cast<float4*>(gx + (size_t)j * L.pitch) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
+                            *reinterpret_cast<float4*>(gy + (size_t)j * L.pitch) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
+                        }
+                    }
+                }
+                if (X.track)
+                {
+                    // activity hint for the analyzer: first generation in which this warp's block recorded anything but
+                    // zeros (conservative: halo rows and -0 count as activity)
+                    const bool hot = ((activity & 0x7fffffffu) != 0u) && lane >= 1 && lane <= 30;
+                    const unsigned any = __ballot_sync(0xffffffffu, hot);
+                    if (lane == 0 && any)
+                        atomicMin(A.firstActive + ((size_t)s * tps + (size_t)ty * L.tiles_x + tx) * 32 + wp, gen);
+                }
+                __syncwarp();
+                if (lane == 0) mbarArrive(done + ((seq - 1) & 1));  // every store of this warp for this tile has been issued
+            }
+        }
+
+        // bit j*4+k of word [tile][warp][lane]: cell (j, k) of that thread's block is an interior air cell (reference b = 1)
+        template <int NW, int R>
+        __global__ void bpMaskKernel(const Layout L, const float* __restrict__ w, uint32_t* __restrict__ mask)
+        {
+            const int lane = threadIdx.x & 31;
+            const int wp = threadIdx.x >> 5;
+            const int tx = blockIdx.x, ty = blockIdx.y;
+            const int rBase = ty * L.valid_rows - kTileK + wp * R;
+            const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+            uint32_t bits = 0u;
+            for (int j = 0; j < R; ++j)
+                for (int k = 0; k < 4; ++k)
+                {
+                    const int r = rBase + j, c = cBase + k;
+                    const bool interior = (r >= 0) && (r < L.gx) && (c >= 0) && (c < L.gy);
+                    if (interior && __float_as_uint(w[cellIndex(L, r, c)]) == kAirBits) bits |= 1u << (j * 4 + k);
+                }
+            mask[(((size_t)ty * L.tiles_x + tx) * NW + wp) * 32 + lane] = bits;
+        }
+
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+        // 2-D tensor maps {pitch, rows_alloc} of the gx / gy coefficient planes, box 128 x tileRows
+        static int buildCoefMaps(pvc_solver* s, CUtensorMap* out)
+        {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            { cudaGetLastError(); setError("ws2 step kernel: cuTensorMapEncodeTiled unavailable"); return PVC_ERR_CUDA; }
+            const Layout& L = s->L;
+            for (int f = 0; f < 2; ++f)
+            {
+                const cuuint64_t dims[2] = { (cuuint64_t)L.pitch, (cuuint64_t)L.rows_alloc };
+                const cuuint64_t strides[1] = { (cuuint64_t)L.pitch * sizeof(float) };
+                const cuuint32_t box[2] = { (cuuint32_t)kTileCols, (cuuint32_t)L.tile_rows };
+                const cuuint32_t estr[2] = { 1u, 1u };
+                const CUresult r = ((EncodeFn)fn)(&out[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->coef[1 + f], dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { setError("ws2 step kernel: coefficient tensor map %d failed (%d)", f, (int)r); return PVC_ERR_CUDA; }
+            }
+            return PVC_OK;
+        }
+
+        template <int NW, int R, int CB>
+        static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
+        {
+            using SM = Smem<NW, R, CB>;
+            const Layout& L = s->L;
+            if (!s->tmaReady || s->tmaTileRows != NW * R) { setError("ws2 step kernel: tensor maps not built for %d-row tiles", NW * R); return PVC_ERR_INVALID; }
+            if (t0 != 0 || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
+            if (!s->bpMask) { setError("ws2 step kernel: descriptor buffer missing"); return PVC_ERR_INVALID; }
+            const size_t smem = SM::total;
+            static bool configured[64] = {};
+            if (!configured[s->device & 63])
+            {
+                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { setError("ws2 step kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+                configured[s->device & 63] = true;
+            }
+            Maps maps;
+            memcpy(maps.state, s->tensorMaps, sizeof(maps.state));
+            int rc = buildCoefMaps(s, maps.coef);
+            if (rc) return rc;
+            const int numTiles = L.tiles_x * L.tiles_y * nsrc;
+            const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;          // all CTAs must be co-resident (1 CTA per SM)
+            const int gens = (t1 + kTileK - 1) / kTileK;
+            const int perLaunch = 256;                                             // generations per launch (bounds kernel time)
+            cudaMemsetAsync(s->doneGen, 0, sizeof(int) * (size_t)numTiles, s->stream);
+            cudaMemsetAsync(s->tileCounters, 0, sizeof(int) * (size_t)((gens + perLaunch - 1) / perLaunch + 1), s->stream);
+            Args A;
+            A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
+            A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
+            A.hist = hist;
+            { static const char* dbg = getenv("PVC_DEBUG_NOHIST"); if (dbg) A.hist = nullptr; }      // debug: memory-floor probe (results invalid)
+            A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder; A.firstActive = s->firstActive;
+            A.src = s->src; A.pulse = s->pulse;
+            A.doneGen = s->doneGen; A.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
+            A.tilesPerSource = L.tiles_x * L.tiles_y; A.nsrc = nsrc; A.numTiles = numTiles;
+            A.T = t1; A.courant = s->cfg.courant;
+            {
+                // sources per group: as many as keep both ping-pong copies of the group's state (2 x 12 B per cell) inside
+                // ~85 MB of the 126 MB L2, groups balanced; the history stream is written evict-first and does not compete
+                static const char* eg = getenv("PVC_GROUP_SRC"); static const char* ec = getenv("PVC_GROUP_GENS");
+                const double perSource = 24.0 * (double)L.plane;
+                int maxSg = (int)(85.0e6 / perSource); if (maxSg < 1) maxSg = 1;
+                const int groups = (nsrc + maxSg - 1) / maxSg;
+                A.srcGroup = (nsrc + groups - 1) / groups;
+                A.genChunk = 16;
+                { static const char* ef = getenv("PVC_EARLY_FETCH"); A.earlyFetch = ef ? atoi(ef) : 2; }
+                if (eg && atoi(eg) > 0) A.srcGroup = atoi(eg);
+                if (ec && atoi(ec) > 0) A.genChunk = atoi(ec);
+                if (A.srcGroup > nsrc) A.srcGroup = nsrc;
+            }
+            int k = 1;
+            for (int g0 = 0; g0 < gens; g0 += perLaunch, ++k)
+            {
+                A.gen0 = g0; A.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
+                A.workCounter = s->tileCounters + k;
+                stepKernel<NW, R, CB><<<grid, (NW + 1) * 32, smem, s->stream>>>(L, A, maps);
+                *launches += 1;
+            }
+            s->cur = gens & 1;
+            s->checkAbort = 1;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { setError("ws2 step kernel launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            return PVC_OK;
+        }
+
+        template <int NW, int R>
+        static int buildMask(pvc_solver* s)
+        {
+            const Layout& L = s->L;
+            bpMaskKernel<NW, R><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->bpMask);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { setError("bp mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+            return PVC_OK;
+        }
+    }
+
+    // ---- entry points used by pvc_step_fused.cu's variant table ----
+    int launchWs2Steps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches)
+    {
+        switch (variant)
+        {
+            case 39: return ws2::launch<14, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 40: return ws2::launch<15, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
+        }
+    }
+    int rebuildWs2Descriptors(pvc_solver* s, int variant)
+    {
+        switch (variant)
+        {
+            case 39: return ws2::buildMask<14, 4>(s);
+            case 40: return ws2::buildMask<15, 4>(s);
+            default: return PVC_OK;
+        }
+    }
+}

@@ -247,12 +247,13 @@ def main():
     time.sleep(0.3)
     t_wall0 = time.perf_counter()
     scene.mark(0)
-    step_ms, ana_ms, launches = 0.0, 0.0, 0
+    step_ms, ana_ms, launches, step_launches = 0.0, 0.0, 0, 0
     for _ in range(args.steps):
         scene.solve_async(listeners)
         gathered = gather_outputs()
         st, an, _, nl = scene.timing()
         step_ms += st; ana_ms += an; launches += nl
+        step_launches += scene.launch_counts()[0]
     scene.mark(1)
     sync_all()
     t_wall1 = time.perf_counter()
@@ -288,7 +289,7 @@ def main():
                 per_gen = json.load(open(traffic_path)).get("dram_bytes_per_generation")
             except Exception:
                 per_gen = None
-        step_launches = max(launches - 2 * args.steps, 1)        # per solve: step-kernel launches + 2 analyzer kernels
+        step_launches = max(step_launches, 1)        # step-kernel launches of the timed solves (the rest of gpu_launches: analyzer kernels)
         # ncu capture (profiles/): DRAM bytes of one generation (4 time steps, this grid, 4 sources), scaled to the
         # generations one launch of this run covers
         gens_per_launch = ((scene.T + 3) // 4) * args.steps / step_launches

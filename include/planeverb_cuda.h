@@ -138,6 +138,8 @@ PVC_API int  pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, flo
 /* timing of the last pvc_run in milliseconds, measured with CUDA events on the solver's stream:
  * out[0] = step kernels, out[1] = analyzer kernels, out[2] = total; launches = kernels launched */
 PVC_API int  pvc_last_timing(pvc_solver* s, float* out3, int* launches);
+/* kernels launched by the last pvc_run, split into the time-step phase (zeroing + step kernels) and the analyzer phase */
+PVC_API int  pvc_last_launch_counts(pvc_solver* s, int* step_launches, int* analyzer_launches);
 /* bracket any sequence of calls with two CUDA events on the solver's stream (which = 0 start, 1 stop);
  * pvc_mark_elapsed waits for the stop event and returns the milliseconds between them */
 PVC_API int  pvc_mark(pvc_solver* s, int which);

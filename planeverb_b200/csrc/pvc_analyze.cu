@@ -16,6 +16,7 @@
 //     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
 // A block is the 128 cells of one history strip: its 4 warps walk one contiguous 512-byte-per-sample stream.
 #include <float.h>
+#include <cstdlib>
 #include "pvc_internal.h"
 
 namespace pvc
@@ -95,6 +96,44 @@ namespace pvc
         return __fmul_rn(__log2f(e), 3.0102999566398120f);
     #else
         return __fmul_rn(10.f, log10fExact(e, tab));
+    #endif
+    }
+
+    // The same value as decibels() for a NORMAL, positive, finite e (the caller checks a whole batch with one
+    // predicate), as straight-line code: no special-case branches, the exponent term of logf picked from
+    // {-ln2, 0, +ln2} instead of an int->double conversion and a multiply (k is -1, 0 or 1 for m in [0.5, 2) and
+    // k*ln2 is then exact), and float->double of the reduced mantissa done with integer ops (exact for normal floats).
+    // Of the reference recipe's three 64-bit conversions (a quarter-rate pipe) only the final rounding remains.
+    __device__ __forceinline__ bool isNormalPositive(float e)
+    {
+        return (__float_as_uint(e) - 0x00800000u) < 0x7f000000u;
+    }
+    __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab)
+    {
+    #ifdef PVC_FAST_LOG10
+        return __fmul_rn(__log2f(e), 3.0102999566398120f);
+    #else
+        const int hx = __float_as_int(e);
+        const int k = (hx >> 23) - 127;
+        const int i = (int)((unsigned)k >> 31);
+        const uint32_t hm = (uint32_t)((hx & 0x007fffff) | ((0x7f - i) << 23));     // m in [1,2) or [0.5,1)
+        const float yk = (float)(k + i);
+        const uint32_t tmp = hm - 0x3f330000u;
+        const int ti = (tmp >> 19) & 15;
+        const int tk = (int)tmp >> 23;                                                // -1, 0 or 1
+        const uint32_t iz = hm - (tmp & 0xff800000u);                                 // z in [~0.7, 1.4)
+        const LogfEntry en = tab[ti];
+        const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
+        const double kln2 = (tk == 0) ? 0.0 : (tk > 0 ? 0x1.62e42fefa39efp-1 : -0x1.62e42fefa39efp-1);
+        const double r = __dsub_rn(__dmul_rn(z, en.invc), 1.0);
+        const double y0 = __dadd_rn(en.logc, kln2);
+        const double r2 = __dmul_rn(r, r);
+        double y = __dadd_rn(__dmul_rn(0x1.5575b0be00b6ap-2, r), -0x1.ffffef20a4123p-2);
+        y = __dadd_rn(__dmul_rn(-0x1.00ea348b88334p-2, r2), y);
+        y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+        const float lf = (float)y;
+        const float zz = __fadd_rn(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(4.3429449201e-01f, lf));
+        return __fmul_rn(10.f, __fadd_rn(zz, __fmul_rn(yk, 3.0102920532e-01f)));
     #endif
     }
 
@@ -299,13 +338,33 @@ namespace pvc
                 float v[kBatch];
                 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - u * hs);
+                // the kBatch Schroeder values first (one dependent add each), then their logarithms, which are
+                // independent of each other: straight-line when all are normal floats (all but a vanishing few batches)
+                float e[kBatch];
+                bool normal = true;
                 #pragma unroll
                 for (int u = 0; u < kBatch; ++u)
                 {
                     edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
-                    const float y = decibels(edc, sTab);
-                    xysum = __fadd_rn(xysum, __fmul_rn(y, x));
-                    ysum = __fadd_rn(ysum, y);
+                    e[u] = edc;
+                    normal = normal && isNormalPositive(edc);
+                }
+                float y[kBatch];
+                if (normal)
+                {
+                    #pragma unroll
+                    for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab);
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int u = 0; u < kBatch; ++u) y[u] = decibels(e[u], sTab);
+                }
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                {
+                    xysum = __fadd_rn(xysum, __fmul_rn(y[u], x));
+                    ysum = __fadd_rn(ysum, y[u]);
                     x = __fsub_rn(x, 1.0f);
                 }
             }
@@ -333,8 +392,146 @@ namespace pvc
         walkDelay[(size_t)s * cells + serial] = (occ > 0.f) ? (float)onset : FLT_MAX;
     }
 
-    // Analyzer.cpp:340-431.  walkDelay holds the onset of every cell a walk may step onto (has an onset
-    // and occlusion > 0, Analyzer.cpp:372-374) and FLT_MAX elsewhere.
+    // ---- Analyzer::EncodeListenerDirection (Analyzer.cpp:340-431) by pointer jumping ----------------------------------
+    // walkDelay holds the onset of every cell a walk may step onto (has an onset and occlusion > 0, Analyzer.cpp:372-374)
+    // and FLT_MAX elsewhere.  The reference walks, from every cell, to the 8-neighbour with the strictly smallest delay
+    // (first wins in the scan order of :332-337) until the delay is <= 5 samples, the loudness >= 0.891, there is no
+    // strictly earlier neighbour (the walk then ends POINTING AT that neighbour, :374-386) or the geodesic matches the
+    // Euclidean distance (:392-407).  Walking costs O(path) per cell -- 25 ms for two 2048 x 2048 sources, more than
+    // the impulse-response analysis itself.  But once a walk stands on a cell u != start, everything that follows is a
+    // pure function of u (its current delay is wd[u], its loudness occ[u]); only the first hop differs (delay = FLT_MAX:
+    // no "no improvement" exit, and the start itself is tested for loudness only).  So:
+    //   1. walkNextKernel    next[u] = the cell the walk ends on if it ends at/after u without another move (DONE bit),
+    //                        else the cell it moves to;
+    //   2. walkJumpKernel    next[u] <- next[next[u]] in place, ceil(log2 T) + 1 jumps in total (delays are integral
+    //                        sample indices that strictly decrease along a walk, so no path is longer than T);
+    //   3. walkResolveKernel the first hop from every start cell, the end cell from next[], the unit vector (:413-430).
+    // Same exits, same tie-breaking, same fp32 expressions as the sequential walk (which remains the cross-check in
+    // tests/test_gpu_parity.py through PVC_WALK=sequential).
+    constexpr int kWalkDone = (int)0x80000000;
+
+    struct WalkConsts { float samplingRate, thresholdDist; };
+    __device__ __forceinline__ WalkConsts walkConsts(const AnalyzeParams& A)
+    {
+        WalkConsts k;
+        k.samplingRate = (float)A.fs;
+        k.thresholdDist = __fmul_rn(0.3f, __fdiv_rn(kSpeedOfSoundA, (float)A.resolution));
+        return k;
+    }
+    // strictly smallest walkDelay among the 8 neighbours of (r, c) inside the lattice, first wins; -1 if none is selectable
+    __device__ __forceinline__ int walkArgmin(const float* __restrict__ wd, int r, int c, int gx, int gy, float& best)
+    {
+        int arg = -1;
+        best = FLT_MAX;
+        #pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+            const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+            const int nr = r + dr, nc = c + dc;
+            if (nr < 0 || nc < 0 || nr >= gx || nc >= gy) continue;
+            const int ni = nr * gy + nc;
+            const float d = wd[ni];
+            if (d < best) { arg = ni; best = d; }
+        }
+        return arg;
+    }
+    // line-of-sight exit of a walk standing on (r, c) with delay d (Analyzer.cpp:392-407)
+    __device__ __forceinline__ bool walkLineOfSight(const AnalyzeParams& A, const WalkConsts& K, const SourceParams& sp, int r, int c, float d)
+    {
+        const float geodesic = __fdiv_rn(__fmul_rn(kSpeedOfSoundA, d), K.samplingRate);
+        const float tx = __fsub_rn(__fmul_rn((float)r, A.dx), sp.x);
+        const float ty = __fsub_rn(__fmul_rn((float)c, A.dx), sp.z);
+        const float eu = __fsqrt_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
+        return fabsf(__fsub_rn(geodesic, eu)) < K.thresholdDist;
+    }
+
+    __global__ void __launch_bounds__(128)
+    walkNextKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, const float* __restrict__ results,
+                   const float* __restrict__ walkDelay, int* __restrict__ next)
+    {
+        const int c = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r = blockIdx.y;
+        const int s = blockIdx.z;
+        if (c >= L.gy) return;
+        const int gx = L.gx, gy = L.gy;
+        const size_t cells = (size_t)gx * gy;
+        const float* wd = walkDelay + (size_t)s * cells;
+        const int u = r * gy + c;
+        const float d = wd[u];
+        int out = u | kWalkDone;
+        if (d != FLT_MAX)                    // cells no walk can stand on keep a harmless self link
+        {
+            const WalkConsts K = walkConsts(A);
+            const float loud = results[((size_t)s * cells + u) * 8];
+            const bool goOn = (d > kDelayClose && loud < kGainThreshold) && !walkLineOfSight(A, K, src[s], r, c, d);
+            if (goOn)
+            {
+                float best;
+                const int v = walkArgmin(wd, r, c, gx, gy, best);
+                if (v >= 0) out = (best >= d) ? (v | kWalkDone) : v;
+            }
+        }
+        next[(size_t)s * cells + u] = out;
+    }
+
+    __global__ void __launch_bounds__(256)
+    walkJumpKernel(size_t cells, int jumps, int* __restrict__ nextAll)
+    {
+        const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (u >= cells) return;
+        int* next = nextAll + (size_t)blockIdx.y * cells;
+        int n = next[u];
+        if (n < 0) return;
+        // in place: a link read here may already have been shortened by another thread -- it then only points
+        // further along the same walk
+        for (int k = 0; k < jumps && n >= 0; ++k) n = *((volatile int*)next + n);
+        next[u] = n;
+    }
+
+    __global__ void __launch_bounds__(128)
+    walkResolveKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, float* __restrict__ results,
+                      const float* __restrict__ walkDelay, const int* __restrict__ nextAll)
+    {
+        const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r0 = blockIdx.y;
+        const int s = blockIdx.z;
+        if (c0 >= L.gy) return;
+        const int gx = L.gx, gy = L.gy;
+        const size_t cells = (size_t)gx * gy;
+        float* res = results + (size_t)s * cells * 8;
+        const float* wd = walkDelay + (size_t)s * cells;
+        const int* next = nextAll + (size_t)s * cells;
+        const SourceParams sp = src[s];
+        int target = r0 * gy + c0;
+        // first hop: delay = FLT_MAX, so only the start's loudness can stop the walk before it moves, and any selectable
+        // neighbour is an improvement (Analyzer.cpp:357-386)
+        if (res[(size_t)target * 8] < kGainThreshold)
+        {
+            float best;
+            const int v = walkArgmin(wd, r0, c0, gx, gy, best);
+            if (v >= 0)
+            {
+                int n = next[v];
+                while (n >= 0) n = next[n];            // already resolved by the jump rounds; a safety net, not a loop
+                target = n & 0x7fffffff;
+            }
+        }
+        const int r = target / gy, c = target % gy;
+        float ox = __fsub_rn(__fmul_rn((float)r, A.dx), sp.x);
+        float oy = __fsub_rn(__fmul_rn((float)c, A.dx), sp.z);
+        float len = __fadd_rn(__fmul_rn(ox, ox), __fmul_rn(oy, oy));
+        if (len != 0.f)
+        {
+            len = __fsqrt_rn(len);
+            ox = __fdiv_rn(ox, len);
+            oy = __fdiv_rn(oy, len);
+        }
+        float* out = res + ((size_t)r0 * gy + c0) * 8;
+        out[4] = ox; out[5] = oy;
+    }
+
+    // The reference's walk, one thread per start cell (cross-check of the pointer-jumping kernels: PVC_WALK=sequential)
     __global__ void __launch_bounds__(128)
     listenerDirectionKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src,
                             float* __restrict__ results, const float* __restrict__ walkDelay)
@@ -348,8 +545,7 @@ namespace pvc
         float* res = results + (size_t)s * cells * 8;
         const float* wd = walkDelay + (size_t)s * cells;
         const SourceParams sp = src[s];
-        const float samplingRate = (float)A.fs;
-        const float thresholdDist = __fmul_rn(0.3f, __fdiv_rn(kSpeedOfSoundA, (float)A.resolution));
+        const WalkConsts K = walkConsts(A);
 
         int nextIndex = r0 * gy + c0;
         float loudness = res[(size_t)nextIndex * 8];
@@ -357,27 +553,13 @@ namespace pvc
         while (delay > kDelayClose && loudness < kGainThreshold)
         {
             const int r = nextIndex / gy, c = nextIndex % gy;
-            float nextDelay = FLT_MAX;
-            #pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
-                const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
-                const int nr = r + dr, nc = c + dc;
-                if (nr < 0 || nc < 0 || nr >= gx || nc >= gy) continue;
-                const int ni = nr * gy + nc;
-                const float d = wd[ni];
-                if (d < nextDelay) { nextIndex = ni; nextDelay = d; }
-            }
+            float nextDelay;
+            const int v = walkArgmin(wd, r, c, gx, gy, nextDelay);
+            if (v >= 0) nextIndex = v;
             if (nextDelay == FLT_MAX || nextDelay >= delay) break;
             delay = nextDelay;
             loudness = res[(size_t)nextIndex * 8];
-            const float geodesic = __fdiv_rn(__fmul_rn(kSpeedOfSoundA, nextDelay), samplingRate);
-            const int r2 = nextIndex / gy, c2 = nextIndex % gy;
-            const float tx = __fsub_rn(__fmul_rn((float)r2, A.dx), sp.x);
-            const float ty = __fsub_rn(__fmul_rn((float)c2, A.dx), sp.z);
-            const float eu = __fsqrt_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)));
-            if (fabsf(__fsub_rn(geodesic, eu)) < thresholdDist) break;
+            if (walkLineOfSight(A, K, sp, nextIndex / gy, nextIndex % gy, nextDelay)) break;
         }
         const int r = nextIndex / gy, c = nextIndex % gy;
         float ox = __fsub_rn(__fmul_rn((float)r, A.dx), sp.x);
@@ -447,8 +629,29 @@ namespace pvc
         dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
         encodeResponseKernel<<<grid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
                                                             s->hintsValid ? s->firstActive : nullptr);
-        listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
-        *launches += 2;
+        const char* walkEnv = getenv("PVC_WALK");           // read per call: the tests switch it
+        if (walkEnv && walkEnv[0] == 's')
+        {
+            listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
+            *launches += 2;
+        }
+        else
+        {
+            const size_t cells = (size_t)L.gx * L.gy;
+            walkNextKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
+            int jumpsLeft = 1;
+            while ((1 << jumpsLeft) < A.T) ++jumpsLeft;          // ceil(log2 T)
+            jumpsLeft += 1;
+            int rounds = 0;
+            while (jumpsLeft > 0)
+            {
+                const int j = jumpsLeft < 3 ? jumpsLeft : 3;     // a few jumps per pass: fewer passes over the link array
+                walkJumpKernel<<<dim3((unsigned)((cells + 255) / 256), nsrc), 256, 0, s->stream>>>(cells, j, s->walkNext);
+                jumpsLeft -= j; ++rounds;
+            }
+            walkResolveKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
+            *launches += 3 + rounds;
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         return PVC_OK;

@@ -236,7 +236,7 @@ size_t pvc_memory_requirement(const pvc_config* cfg)
     const Layout L = makeLayout(r);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
     return sizeof(float) * (6 * S * L.plane + 4 * L.plane + S * L.hist_source + (size_t)cfg->T +
-                            S * cells * 10 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
+                            S * cells * 11 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
 int pvc_create(const pvc_config* cfg, pvc_solver** out)
@@ -275,7 +275,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMemsetAsync(s->slowMask, 0, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     PVC_TRY(cudaMalloc(&s->tileOrder, sizeof(int) * (size_t)L.tiles_x * L.tiles_y));
-    PVC_TRY(cudaMalloc(&s->bpMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 16 * 32));
+    PVC_TRY(cudaMalloc(&s->bpMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32 * 32));
     PVC_TRY(cudaMalloc(&s->firstActive, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32));
     PVC_TRY(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y * 32, s->stream));
     s->tileCounterCount = cfg->T / kTileK + 2;
@@ -288,6 +288,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMemsetAsync(s->results, 0, sizeof(float) * S * cells * 8, s->stream));
     PVC_TRY(cudaMalloc(&s->delay, sizeof(float) * S * cells));
     PVC_TRY(cudaMalloc(&s->walkDelay, sizeof(float) * S * cells));
+    PVC_TRY(cudaMalloc(&s->walkNext, sizeof(int) * S * cells));
     PVC_TRY(cudaMalloc(&s->scratch, sizeof(float) * 3 * (size_t)cfg->T));
     PVC_TRY(cudaMalloc(&s->src, sizeof(SourceParams) * S));
     #undef PVC_TRY
@@ -308,7 +309,7 @@ void pvc_destroy(pvc_solver* s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
     cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
-    cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->scratch); cudaFree(s->src);
+    cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->walkNext); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     for (int i = 0; i < 2; ++i) if (s->mark[i]) cudaEventDestroy(s->mark[i]);
@@ -427,6 +428,7 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
         PVC_CUDA(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * (size_t)n * s->L.tiles_x * s->L.tiles_y * 32, s->stream));
     rc = runSteps(s, n, s->cfg.T, &launches);
     if (rc) return rc;
+    s->lastStepLaunches = launches;
     PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));
     if (analyze) { rc = launchAnalyzer(s, n, &launches); if (rc) return rc; }
     PVC_CUDA(cudaEventRecord(s->ev[2], s->stream));
@@ -538,6 +540,14 @@ int pvc_last_timing(pvc_solver* s, float* out3, int* launches)
     PVC_CUDA(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
     if (out3) { out3[0] = a; out3[1] = b; out3[2] = a + b; }
     if (launches) *launches = s->lastLaunches;
+    return PVC_OK;
+}
+
+int pvc_last_launch_counts(pvc_solver* s, int* step_launches, int* analyzer_launches)
+{
+    if (!s) { setError("pvc_last_launch_counts: null solver"); return PVC_ERR_INVALID; }
+    if (step_launches) *step_launches = s->lastStepLaunches;
+    if (analyzer_launches) *analyzer_launches = s->lastLaunches - s->lastStepLaunches;
     return PVC_OK;
 }
 

@@ -109,6 +109,7 @@ struct pvc_solver
     float* results;          // max_sources * gx*gy*8
     float* delay;            // max_sources * gx*gy
     float* walkDelay;        // max_sources * gx*gy   (delay of selectable cells, FLT_MAX otherwise)
+    int* walkNext;           // max_sources * gx*gy   (links of the listener-direction walk, pvc_analyze.cu)
     float* scratch;          // small device scratch (IR fetch)
     pvc_rect* rects;         // device copy of the current geometry edit list
     int rectCapacity;
@@ -118,6 +119,7 @@ struct pvc_solver
     int lastSources;
     float lastMs[3];
     int lastLaunches;
+    int lastStepLaunches;
     unsigned long long* timeline;   // debug only
     int useGraphs;
     pvc::GraphSlot graphs[pvc::kMaxGraphBatch + 1];   // captured step-launch sequences, by batch size

@@ -124,8 +124,8 @@ namespace pvc
             int srcR, srcC;
             int pad[3];
             float pulse[4];
-            int mode[16];
-            int hint[16];
+            int mode[32];
+            int hint[32];
         };
 
         enum { kFast = 0, kEdge = 1, kGeneral = 2 };
@@ -323,7 +323,7 @@ namespace pvc
         {
             using SM = Smem<NW, R, CB>;
             constexpr int TR = SM::TR;
-            static_assert(NW <= 16 && R * 4 <= 32, "Meta holds 16 warps; bpMask holds 32 cells per thread");
+            static_assert(NW <= 31 && R * 4 <= 32, "Meta holds 32 warps; bpMask holds 32 cells per thread");
             extern __shared__ __align__(128) unsigned char smemRaw[];
             float* stage = reinterpret_cast<float*>(smemRaw + SM::offStage);                       // [3][TR][128]
             float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);                      // [CB][2][TR][32]
@@ -437,11 +437,11 @@ namespace pvc
                         nx.mode = (int)A.mode[(size_t)nx.id * 32 + lane];
                         nx.hint = (A.firstActive && A.hist) ? A.firstActive[((size_t)nx.s * tps + nx.id) * 32 + lane] : 0;
                     }
-                    else if (lane == 16) nx.misc = A.src[nx.s].cell_r;
-                    else if (lane == 17) nx.misc = A.src[nx.s].cell_c;
-                    else if (lane >= 20 && lane < 24)
+                    if (lane == 0) nx.misc = A.src[nx.s].cell_r;
+                    else if (lane == 1) nx.misc = A.src[nx.s].cell_c;
+                    else if (lane >= 4 && lane < 8)
                     {
-                        const int t = nx.gen * kTileK + (lane - 20);
+                        const int t = nx.gen * kTileK + (lane - 4);
                         nx.misc = __float_as_int(t < A.T ? __ldg(A.pulse + t) : 0.f);
                     }
                     nx.ready = (A.earlyFetch == 1) ? false : depsReady(nx.s, nx.tx, nx.ty, nx.gen, false);
@@ -478,10 +478,10 @@ namespace pvc
                     const int coefBuf = anySlow ? (int)(coefPhase % CB) : -1;
                     const int coefParity = (int)((coefPhase / CB) & 1u);
                     if (lane < NW) { m->mode[lane] = it.mode; m->hint[lane] = it.hint; }
-                    else if (lane == 16) m->srcR = it.misc;
-                    else if (lane == 17) m->srcC = it.misc;
-                    else if (lane >= 20 && lane < 24) m->pulse[lane - 20] = __int_as_float(it.misc);
-                    else if (lane == 24) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
+                    if (lane == 0) m->srcR = it.misc;
+                    else if (lane == 1) m->srcC = it.misc;
+                    else if (lane >= 4 && lane < 8) m->pulse[lane - 4] = __int_as_float(it.misc);
+                    else if (lane == 8) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
                     __syncwarp();
                     if (lane == 0)
                     {
@@ -778,6 +778,8 @@ namespace pvc
         {
             case 39: return ws2::launch<14, 4, 2>(s, nsrc, t0, t1, hist, launches);
             case 40: return ws2::launch<15, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 41: return ws2::launch<30, 2, 1>(s, nsrc, t0, t1, hist, launches);
+            case 42: return ws2::launch<20, 3, 1>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -787,6 +789,8 @@ namespace pvc
         {
             case 39: return ws2::buildMask<14, 4>(s);
             case 40: return ws2::buildMask<15, 4>(s);
+            case 41: return ws2::buildMask<30, 2>(s);
+            case 42: return ws2::buildMask<20, 3>(s);
             default: return PVC_OK;
         }
     }

@@ -26,7 +26,7 @@ PVC_SYMBOLS = [
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
-    "pvc_last_timing", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
+    "pvc_last_timing", "pvc_last_launch_counts", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
     "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline",
 ]
 PVX_SYMBOLS = [
@@ -105,6 +105,7 @@ def lib():
         L.pvc_fetch_state.argtypes = [_vp, _i, _vp, _vp, _vp]
         L.pvc_fetch_coefficients.argtypes = [_vp, _vp, _vp]
         L.pvc_last_timing.argtypes = [_vp, _vp, _vp]
+        L.pvc_last_launch_counts.argtypes = [_vp, _vp, _vp]
         L.pvc_clear_results.argtypes = [_vp, _i]
         L.pvc_synchronize.argtypes = [_vp]
         L.pvc_mark.argtypes = [_vp, _i]
@@ -320,3 +321,9 @@ class Scene:
         n = C.c_int()
         _check(lib().pvc_last_timing(self._solver, _p(out), C.byref(n)), "pvc_last_timing")
         return float(out[0]), float(out[1]), float(out[2]), int(n.value)
+
+    def launch_counts(self):
+        """(step-phase kernel launches, analyzer-phase kernel launches) of the last solve."""
+        a, b = C.c_int(), C.c_int()
+        _check(lib().pvc_last_launch_counts(self._solver, C.byref(a), C.byref(b)), "pvc_last_launch_counts")
+        return int(a.value), int(b.value)

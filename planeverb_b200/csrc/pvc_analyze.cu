@@ -14,7 +14,7 @@
 //   * wet energy: ascending t over its window (Analyzer.cpp:235-247);
 //   * RT60: backward Schroeder integral, descending t, with the running log10 and the two regression
 //     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
-// A block is the 128 cells of one history strip: its 4 warps walk one contiguous 512-byte-per-sample stream.
+// A block is the 120 cells of one history strip: its 4 warps walk one contiguous 480-byte-per-sample stream.
 #include <float.h>
 #include <cstdlib>
 #include "pvc_internal.h"
@@ -154,17 +154,17 @@ namespace pvc
         if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
         __syncthreads();
 
-        const int c = blockIdx.x * blockDim.x + threadIdx.x;      // block = one 128-column history strip of one row
+        const int c = blockIdx.x * kHistChunk + threadIdx.x;      // block = one 120-column history strip of one row (8 spare threads)
         const int r = blockIdx.y;
         const int s = blockIdx.z;
-        if (c >= L.gy) return;
+        if (threadIdx.x >= kHistChunk || c >= L.gy) return;
         const size_t cells = (size_t)L.gx * L.gy;
         // interior cell (r, c) -> r*gy + c.  The reference strides by the x extent (INDEX_TO_POS, PvDefinitions.h:23-24),
         // which is the same thing on the square grids it supports and self-overlapping on others.
         const size_t serial = (size_t)r * L.gy + c;
         float* out = results + ((size_t)s * cells + serial) * 8;
         const int T = A.T;
-        // sample t of this cell is H[t * 128]: the 4 warps of the block walk one contiguous 512-byte-per-sample stream
+        // sample t of this cell is H[t * 120]: the 4 warps of the block walk one contiguous 480-byte-per-sample stream
         const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c);
         constexpr ptrdiff_t hs = kHistChunk;
 
@@ -230,7 +230,7 @@ namespace pvc
             const bool topEdge = (r == 0), leftEdge = (c == 0);
             const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
             const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
-            const ptrdiff_t leftOff = leftEdge ? 0 : (((c & 127) != 0) ? -1 : -(ptrdiff_t)T * kHistChunk + 127);
+            const ptrdiff_t leftOff = leftEdge ? 0 : (((c % kHistChunk) != 0) ? -1 : -(ptrdiff_t)T * kHistChunk + (kHistChunk - 1));
             float vx = 0.f, vy = 0.f;
             constexpr int kCausalBatch = 4;
             for (int t0 = causalBegin; t0 < fluxEnd; t0 += kCausalBatch)
@@ -627,7 +627,8 @@ namespace pvc
         const AnalyzeParams A = paramsOf(s);
         dim3 block(128, 1, 1);
         dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
-        encodeResponseKernel<<<grid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
+        dim3 stripGrid((L.gy + kHistChunk - 1) / kHistChunk, L.gx, nsrc);     // one block per history strip and row
+        encodeResponseKernel<<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
                                                             s->hintsValid ? s->firstActive : nullptr);
         const char* walkEnv = getenv("PVC_WALK");           // read per call: the tests switch it
         if (walkEnv && walkEnv[0] == 's')

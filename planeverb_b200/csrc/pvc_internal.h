@@ -11,8 +11,9 @@
 //       anything else         -> wall cell (b = 0) and the float is its admittance
 //                                Y = (1-R)/(1+R) (FDTD.cpp:153,160); guard cells are walls with Y = 0.
 //   pressure history   hist [source][row][chunk][t][128]: sample t of alloc cell (r, c) lives at
-//       ((r*hist_chunks + c/128)*T + t)*128 + c%128 -- time-major inside each 128-column strip, so the
-//       step kernel appends 512 contiguous bytes per warp-row per step and the analyzer, which walks
+//       ((r*hist_chunks + c/120)*T + t)*120 + c%120 -- time-major inside each 120-column strip (the owned
+//       columns of one step-kernel tile, so a tile's record of one sample is ONE dense box for TMA), so the
+//       step kernel appends 480 contiguous bytes per warp-row per step and the analyzer, which walks
 //       every cell through time, reads each strip as ONE sequential stream.  It is the only per-step
 //       record kept (4 B per cell-step instead of the reference's 16-byte Cell, FDTD.cpp:226-231);
 //       vx/vy of any sample are rebuilt from it.
@@ -41,8 +42,8 @@ namespace pvc
         int rows_alloc;        // state rows incl. guards
         size_t plane;          // rows_alloc * pitch
         int T;                 // samples per impulse response
-        int hist_chunks;       // 128-column strips per row: ceil(cols / 128)
-        size_t hist_row;       // floats between consecutive rows of the history: hist_chunks * T * 128
+        int hist_chunks;       // 120-column strips per row: ceil(cols / 120) = tiles_x
+        size_t hist_row;       // floats between consecutive rows of the history: hist_chunks * T * 120
         size_t hist_source;    // floats between sources: rows * hist_row
         int tiles_x, tiles_y;  // fused-kernel tile grid
         int tile_rows;         // rows per tile incl. halo (warps * rows per thread)
@@ -55,13 +56,13 @@ namespace pvc
         return (size_t)(r + kGuardRows) * L.pitch + (c + kGuardCols);
     }
 
-    constexpr int kHistChunk = 128;
+    constexpr int kHistChunk = kValidCols;       // 120: one history strip = the owned columns of one tile
     constexpr int kNeverActive = 0x7f7f7f7f;     // memset(0x7f) pattern of firstActive
 
-    // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*128
+    // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*kHistChunk
     __host__ __device__ inline size_t histCell(const Layout& L, int r, int c)
     {
-        return (size_t)r * L.hist_row + (size_t)(c >> 7) * L.T * kHistChunk + (c & 127);
+        return (size_t)r * L.hist_row + (size_t)(c / kHistChunk) * L.T * kHistChunk + (c % kHistChunk);
     }
 
     struct SourceParams       // one listener, device copy of pvc_listener plus derived indices

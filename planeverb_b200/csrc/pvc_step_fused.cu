@@ -159,7 +159,7 @@ namespace pvc
         float* hist = nullptr;
         if (A.hist)
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
-                 + ((ptrdiff_t)(cBase >> 7) * L.T + run.t0) * kHistChunk + (cBase & 127);
+                 + ((ptrdiff_t)(cBase / kHistChunk) * L.T + run.t0) * kHistChunk + (cBase % kHistChunk);
 
         uint32_t activity = 0u;
         // activity-hint slot of this warp's block, fetched now so its latency hides behind the steps
@@ -1123,7 +1123,8 @@ namespace pvc
                                          {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
                                          {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
                                          {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3}, {16, 4, 1, 4}, {16, 4, 1, 4}, {12, 6, 1, 4}, {15, 4, 1, 4}, {15, 4, 1, 4}, {11, 6, 1, 4},
-                                         {14, 4, 1, 5}, {15, 4, 1, 5}, {30, 2, 1, 5}, {20, 3, 1, 5} };       // 39..42: pvc_step_ws2.cu
+                                         {14, 4, 1, 5}, {15, 4, 1, 5}, {30, 2, 1, 5}, {20, 3, 1, 5}, {14, 4, 1, 5},
+                                         {10, 8, 1, 5}, {11, 6, 1, 5}, {12, 6, 1, 5} };       // 39..46: pvc_step_ws2.cu
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -1408,7 +1409,7 @@ namespace pvc
             case 36: return launchGen<15, 4, true, true>(s, nsrc, t0, t1, hist, launches);
             case 37: return launchGen<15, 4, false, true>(s, nsrc, t0, t1, hist, launches);
             case 38: return launchGen<11, 6, true, true>(s, nsrc, t0, t1, hist, launches);
-            case 39: case 40: case 41: case 42: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
+            case 39: case 40: case 41: case 42: case 43: case 44: case 45: case 46: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }
@@ -1421,6 +1422,7 @@ namespace pvc
         switch (kVariants[v].nw * 100 + kVariants[v].r)
         {
             case 1404: return maskVariant<14, 4, 1>(s);
+            case 1008: return maskVariant<10, 8, 1>(s);
             case 3002: return maskVariant<30, 2, 1>(s);
             case 2003: return maskVariant<20, 3, 1>(s);
             case 808: return maskVariant<8, 8, 1>(s);

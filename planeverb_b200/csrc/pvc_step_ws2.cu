@@ -26,6 +26,7 @@
 //
 // Roofline: HBM; algorithmic bytes 28 B per cell-update.
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -76,6 +77,34 @@ namespace pvc
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
         }
+        // ---- TMA stores (shared -> global tensor tiles, completion tracked in per-thread bulk async-groups)
+        __device__ __forceinline__ void tmaStore3d(const CUtensorMap* map, const void* srcSmem, int c0, int c1, int c2)
+        {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smemAddr(srcSmem)) : "memory");
+        }
+        __device__ __forceinline__ void tmaStore5dHint(const CUtensorMap* map, const void* srcSmem, int c0, int c1, int c2, int c3, int c4, uint64_t policy)
+        {
+            asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4, %5}], [%6], %7;"
+                         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smemAddr(srcSmem)), "l"(policy) : "memory");
+        }
+        __device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+        template <int N> __device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+        template <int N> __device__ __forceinline__ void bulkWait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+        __device__ __forceinline__ void fenceAsyncShared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        __device__ __forceinline__ uint64_t evictFirstPolicy()
+        {
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            return pol;
+        }
+        __device__ __forceinline__ bool mbarTest(uint64_t* bar, uint32_t parity)
+        {
+            uint32_t ready;
+            asm volatile("{\n.reg .pred r;\nmbarrier.test_wait.parity.shared::cta.b64 r, [%1], %2;\nselp.u32 %0, 1, 0, r;\n}\n"
+                         : "=r"(ready) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+            return ready != 0u;
+        }
         __device__ __forceinline__ int loadAcquire(const int* p)
         {
             int v;
@@ -111,10 +140,14 @@ namespace pvc
             int tilesPerSource, nsrc, numTiles;    // numTiles = tilesPerSource * nsrc
             int gen0, numGen, T;
             int earlyFetch;
+            int tsDebug;                           // debug: bit 0 no history TMA, bit 1 no state TMA, bit 2 never defer the done arrival
+            unsigned long long* debug;             // optional counters (PVC_DEBUG_COUNTERS): tiles, slow-path hand-overs, cycles waiting / total
             int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
             float courant;
         };
-        struct Maps { CUtensorMap state[6]; CUtensorMap coef[2]; };       // state: [buffer][p,vx,vy]; coef: gx, gy
+        // state: loads, [buffer][p,vx,vy], box 128 x tile rows; coef: gx, gy; store: [buffer][p,vx,vy], box 120 x (tile's owned rows), clipped to the
+        // alloc grid; hist: 5-D {120 columns, T, strips, rows, sources}, box 120 x 1 x 1 x owned rows x 1 (TS variants only)
+        struct Maps { CUtensorMap state[6]; CUtensorMap coef[2]; CUtensorMap store[6]; CUtensorMap hist; };
 
         // producer -> compute hand-off record of one tile
         struct Meta
@@ -129,6 +162,16 @@ namespace pvc
         };
 
         enum { kFast = 0, kEdge = 1, kGeneral = 2 };
+        constexpr int kTraceTiles = 64, kTraceSlots = 8, kTraceCtas = 148;
+        __device__ __forceinline__ void trace(unsigned long long* dbg, int seq, int slot)
+        {
+            if (dbg && seq >= 200 && seq < 200 + kTraceTiles && blockIdx.x < kTraceCtas)
+            {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                dbg[4 + ((size_t)blockIdx.x * kTraceTiles + (seq - 200)) * kTraceSlots + slot] = t;
+            }
+        }
 
         // One time step of one warp's R x 128 block.  MODE is the warp-uniform path (see slowMaskKernel):
         //   fast     every cell of the warp, and each one's up/left neighbour, is interior air: 11 fp32 ops per cell
@@ -245,14 +288,69 @@ namespace pvc
             int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
             const float* pulse;       // 4 samples of this generation (shared memory)
             bool track;               // this warp's block is not yet known to be active: accumulate the activity OR
+            // TMA-store variants (TS): the tile's stores go through three [VR][120] staging planes in shared memory and ONE
+            // storer thread (warp 0, lane 0) that issues a tensor store per plane; see stepKernel
+            float* out;               // staging planes (all warps see the same pointer)
+            int outRow;               // first staging row of this warp (< 0: the warp owns no rows)
+            bool storer;
+            const Maps* maps;
+            int tx, ty, s, t0, gen;
+            bool histOn;
+            uint64_t* deferredDone;   // storer: "tile stored" barrier of the PREVIOUS tile, still to be arrived on (null: none)
+            uint64_t policy;
+            int tsDebug;
         };
 
-        template <int NW, int R, int MODE>
+        // storer thread: one sample of the tile's VR owned rows.  A history strip is exactly the 120 owned columns of a tile
+        // (kHistChunk == kValidCols), so the record is one dense [VR][120] box: strip tx, sample t, rows from the tile's first
+        // owned row; rows past the grid are clipped by the tensor map.
+        __device__ __forceinline__ void storeHistoryPlane(const TileCtx& X, const Layout& L, const float* plane, int t)
+        {
+            tmaStore5dHint(&X.maps->hist, plane, 0, t, X.tx, X.ty * L.valid_rows, X.s, X.policy);
+        }
+        __device__ __forceinline__ void storeStatePlane(const TileCtx& X, const Layout& L, const float* plane, int field)
+        {
+            const CUtensorMap* m = &X.maps->store[((X.gen & 1) ? 0 : 3) + field];    // generation g writes buffer (g + 1) & 1
+            tmaStore3d(m, plane, X.tx * kValidCols + kGuardCols, X.ty * L.valid_rows + kGuardRows, X.s);
+        }
+        // an owning warp: its R rows of one field into a staging plane
+        template <int R>
+        __device__ __forceinline__ void stageRows(float* plane, int outRow, int lane, const float (&v)[R][4])
+        {
+            if (lane >= 1 && lane <= 30)
+            {
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                    *reinterpret_cast<float4*>(plane + (outRow + j) * kValidCols + (lane - 1) * 4) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+            }
+            fenceAsyncShared();          // generic-proxy writes above -> async-proxy reads of the TMA store (issued after a barrier)
+        }
+        template <int R>
+        __device__ __forceinline__ void injectPulse(const TileCtx& X, float (&p)[R][4], float add)
+        {
+            // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
+            const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
+            const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+                if (j == X.sj)
+                {
+                    p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
+                    p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
+                }
+        }
+
+        template <int NW, int R, int MODE, bool TS>
         __device__ __forceinline__ void stepLoop(const Stepper<NW, R, MODE>& S, TileCtx& X, const int nsteps,
                                                  float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], float4 vxBelow,
                                                  float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
         {
             const int lane = S.lane, wp = S.wp;
+            constexpr int kPlane = (NW - 2) * R * kValidCols;          // floats per staging plane (TS)
+            // TS: the pulse sample of a pass's LAST step is injected at the start of the next pass instead (pulse[0] of the
+            // record is that pending sample): the stored state pressure is then identical to the last recorded sample and
+            // both leave through the same staging plane.  Same additions on the same operands in the same order.
+            if (TS && X.sj >= 0 && X.t0 > 0) injectPulse<R>(X, p, X.pulse[0]);
             #pragma unroll 1
             for (int step = 0; step < nsteps; ++step)
             {
@@ -260,17 +358,39 @@ namespace pvc
                 if (step > 0) vxBelow = sVxTop[wp + 1][lane];
                 S.pressure(p, vx, vy, vxBelow);
                 sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+                if (TS && X.storer)
+                {
+                    // the staging plane(s) written after this barrier must have been read by their previous TMA store.
+                    // Groups in issue order: per pass g0..g2 (samples 0..2, planes 0..2), g3 (sample 3 = state p from plane 0,
+                    // vx from plane 1), g4 (vy from plane 2); see the epilogue in stepKernel.
+                    if (nsteps != kTileK) bulkWaitRead<0>();
+                    else if (step == 0) bulkWaitRead<1>();            // plane 0: previous pass's g3; its g4 may still read
+                    else if (step == 3) bulkWaitRead<1>();            // planes 0, 1: g0, g1; g2 may still read
+                    else bulkWaitRead<2>();                           // plane 1 / 2: previous pass's g3 / g4
+                }
                 computeBarrier<NW>();
                 // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
                 S.velocity(p, vx, vy, sPBot[wp][lane]);
                 // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
-                if (X.hist)
+                const bool last = step + 1 == nsteps;
+                if (TS)
                 {
-                    #pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if ((X.ownRows >> j) & 1u)
-                            __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
-                    X.hist += kHistChunk;
+                    if (X.outRow >= 0)
+                    {
+                        stageRows<R>(X.out + ((step == 3) ? 0 : step) * kPlane, X.outRow, lane, p);
+                        if (last) stageRows<R>(X.out + (((step == 3) ? 0 : step) + 1) % 3 * kPlane, X.outRow, lane, vx);
+                    }
+                }
+                if (TS ? X.histOn : (X.hist != nullptr))
+                {
+                    if (!TS)
+                    {
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            if ((X.ownRows >> j) & 1u)
+                                __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                        X.hist += kHistChunk;
+                    }
                     if (X.track)
                     {
                         #pragma unroll
@@ -281,27 +401,31 @@ namespace pvc
                         }
                     }
                 }
-                if (X.sj >= 0)
-                {
-                    // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
-                    const float add = X.pulse[step];
-                    const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
-                    const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
-                    #pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if (j == X.sj)
-                        {
-                            p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
-                            p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
-                        }
-                }
-                if (step + 1 < nsteps) sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                if (X.sj >= 0 && !(TS && last)) injectPulse<R>(X, p, X.pulse[TS ? step + 1 : step]);
+                if (!last) sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                if (TS && X.storer && last) bulkWaitRead<0>();        // plane for vy (staged after the barrier): g2, one step old
                 // also the write-after-read fence of sPBot for the next pass's first pressure sub-step
                 computeBarrier<NW>();
+                if (TS && X.storer)
+                {
+                    const float* plane = X.out + ((step == 3) ? 0 : step) * kPlane;
+                    if (X.histOn && !(X.tsDebug & 1)) storeHistoryPlane(X, S.L, plane, X.t0 + step);
+                    if (last && !(X.tsDebug & 2))
+                    {
+                        storeStatePlane(X, S.L, plane, 0);                                             // the new state's pressure IS the last sample
+                        storeStatePlane(X, S.L, X.out + (((step == 3) ? 0 : step) + 1) % 3 * kPlane, 1);
+                    }
+                    bulkCommit();
+                    if (step == 0 && X.deferredDone)
+                    {   // the previous pass's stores: everything but the group just committed has completed
+                        bulkWait<1>();
+                        mbarArrive(X.deferredDone);
+                    }
+                }
             }
         }
 
-        template <int NW, int R, int CB>
+        template <int NW, int R, int CB, bool TS = false>
         struct Smem
         {
             static constexpr int TR = NW * R;
@@ -312,16 +436,19 @@ namespace pvc
             static constexpr size_t offMask = offCoef + (size_t)CB * 2 * kPlaneBytes;
             static constexpr size_t offVxTop = offMask + (size_t)CB * kMaskBytes;
             static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
-            static constexpr size_t offMeta = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);
+            static constexpr size_t offOut = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);      // [3][(NW - 2) * R][120] (TS only)
+            static constexpr uint32_t kOutPlaneBytes = (NW - 2) * R * kValidCols * sizeof(float);
+            static constexpr size_t offMeta = offOut + (TS ? (size_t)3 * kOutPlaneBytes : 0);
             static constexpr size_t offBars = offMeta + 2 * sizeof(Meta);
             static constexpr size_t total = offBars + (4 + CB) * sizeof(uint64_t);
         };
 
-        template <int NW, int R, int CB>
+        template <int NW, int R, int CB, bool TS>
         __global__ void __launch_bounds__((NW + 1) * 32, 1)
         stepKernel(const Layout L, const Args A, const __grid_constant__ Maps maps)
         {
-            using SM = Smem<NW, R, CB>;
+            using SM = Smem<NW, R, CB, TS>;
+            static_assert(!TS || R == kTileK, "TMA-store variants: the halo rows must be exactly the first and the last warp");
             constexpr int TR = SM::TR;
             static_assert(NW <= 31 && R * 4 <= 32, "Meta holds 32 warps; bpMask holds 32 cells per thread");
             extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -343,7 +470,7 @@ namespace pvc
 
             if (threadIdx.x == 0)
             {
-                mbarInit(full, 1); mbarInit(empty, NW); mbarInit(done, NW); mbarInit(done + 1, NW);
+                mbarInit(full, 1); mbarInit(empty, NW); mbarInit(done, TS ? 1 : NW); mbarInit(done + 1, TS ? 1 : NW);
                 for (int b = 0; b < CB; ++b) mbarInit(fullCoef + b, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
@@ -358,7 +485,7 @@ namespace pvc
             {
                 // ================= producer warp =================
                 auto depsReady = [&](int s, int tx, int ty, int gen, bool block) -> bool {
-                    if (gen == 0) return true;
+                    if (gen == 0) return true;                 // generation 0 reads the zeroed state: written by a memset before the launch
                     const int dx = lane % 3 - 1, dy = lane / 3 - 1;
                     const int nx = tx + dx, ny = ty + dy;
                     const bool mine = lane < 9 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y;
@@ -367,7 +494,14 @@ namespace pvc
                     while (true)
                     {
                         const bool ok = !mine || loadAcquire(slot) >= gen;
-                        if (__all_sync(0xffffffffu, ok)) return true;
+                        if (__all_sync(0xffffffffu, ok))
+                        {
+                            // order the acquires above before the async-proxy (TMA) reads of the neighbours' cells.  Done
+                            // here, a tile ahead of the TMA issue, because the fence waits out the CTA's outstanding
+                            // stores (~1-2 us measured): at the issue site it sat between a drained stage and the next load.
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            return true;
+                        }
                         if (!block) return false;
                         __nanosleep(32);
                         ++spins;
@@ -441,8 +575,8 @@ namespace pvc
                     else if (lane == 1) nx.misc = A.src[nx.s].cell_c;
                     else if (lane >= 4 && lane < 8)
                     {
-                        const int t = nx.gen * kTileK + (lane - 4);
-                        nx.misc = __float_as_int(t < A.T ? __ldg(A.pulse + t) : 0.f);
+                        const int t = nx.gen * kTileK + (lane - 4) - (TS ? 1 : 0);          // TS: [pending sample of the previous pass, samples 0..2]
+                        nx.misc = __float_as_int((t >= 0 && t < A.T) ? __ldg(A.pulse + t) : 0.f);
                     }
                     nx.ready = (A.earlyFetch == 1) ? false : depsReady(nx.s, nx.tx, nx.ty, nx.gen, false);
                     nx.anySlow = __ballot_sync(0xffffffffu, lane < NW && nx.mode == kGeneral) != 0u;
@@ -457,6 +591,7 @@ namespace pvc
                     const bool anySlow = it.anySlow;
                     bool ready = it.ready;
                     if (!ready && A.earlyFetch) ready = depsReady(s, tx, ty, gen, false);
+                    if (A.debug && lane == 0) { atomicAdd(A.debug + 0, 1ull); if (!ready) atomicAdd(A.debug + 1, 1ull); }
                     if (!ready)
                     {   // it may depend on the tile our own compute warps are working on: publish that first, then wait for real
                         if (!publishPrev()) { alive = false; break; }
@@ -471,6 +606,7 @@ namespace pvc
                         emptyParity ^= 1u;
                         if (!ok) { alive = false; break; }
                     }
+                    if (lane == 0) trace(A.debug, seq, 7);
                     // single coefficient buffer: the tile being computed may still be reading it
                     if (CB == 1 && anySlow && prevUsedCoef) { if (!publishPrev()) { alive = false; break; } }
 
@@ -485,7 +621,6 @@ namespace pvc
                     __syncwarp();
                     if (lane == 0)
                     {
-                        asm volatile("fence.proxy.async;" ::: "memory");
                         if (anySlow)
                         {
                             uint64_t* bar = fullCoef + coefBuf;
@@ -502,12 +637,15 @@ namespace pvc
                         tmaLoad3d(stage + (size_t)2 * TR * kTileCols, mp + 2, tx * kValidCols, ty * L.valid_rows, s, full);
                     }
                     __syncwarp();
+                    if (lane == 0) trace(A.debug, seq, 0);
                     if (anySlow) ++coefPhase;
                     ++seq;
                     stageBusy = true;
                     if (A.earlyFetch) fetchNext();                // the next item's fetch overlaps the tile in flight
                     // the tile handed over before this one is (or was) being computed: publish it once the compute warps are done
+                    if (lane == 0) trace(A.debug, seq - 1, 1);
                     if (!publishPrev()) { alive = false; break; }
+                    if (lane == 0) trace(A.debug, seq - 1, 2);
                     prevSlot = s * tps + id; prevGen = gen; prevUsedCoef = anySlow; prevSeq = seq - 1;
                 }
                 // drain: publish the last tile, then tell the compute warps to stop
@@ -525,10 +663,21 @@ namespace pvc
             // ================= compute warps =================
             uint32_t fullParity = 0;
             int seq = 0;
+            long long tStart = A.debug ? clock64() : 0;
+            const bool owner = TS && wp >= 1 && wp <= NW - 2;
+            const bool storer = TS && threadIdx.x == 0;
+            float* const outBuf = reinterpret_cast<float*>(smemRaw + SM::offOut);
+            uint64_t* deferredDone = nullptr;
+            const uint64_t histPolicy = TS ? evictFirstPolicy() : 0ull;
             while (true)
             {
+                long long tw0 = 0;
+                if (A.debug) tw0 = clock64();
+                if (threadIdx.x == 32 * 7) trace(A.debug, seq, 3);
                 if (!mbarWaitBounded(full, fullParity, A.abortFlag)) break;
+                if (A.debug && threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(A.debug + 2, (unsigned long long)(t1 - tw0)); atomicAdd(A.debug + 3, (unsigned long long)(t1 - tStart)); tStart = t1; }
                 fullParity ^= 1u;
+                if (threadIdx.x == 32 * 7) trace(A.debug, seq, 4);
                 const Meta* m = meta + (seq & 1);
                 ++seq;
                 if (m->valid == 0) break;
@@ -585,7 +734,7 @@ namespace pvc
                 X.hist = nullptr;
                 if (A.hist)
                     X.hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
-                           + ((ptrdiff_t)(cBase >> 7) * L.T + t0) * kHistChunk + (cBase & 127);
+                           + ((ptrdiff_t)(cBase / kHistChunk) * L.T + t0) * kHistChunk + (cBase % kHistChunk);
                 X.histRow = L.hist_row;
                 X.ownRows = ownRows;
                 {
@@ -597,16 +746,21 @@ namespace pvc
                 const bool hints = (A.firstActive != nullptr) && (A.hist != nullptr);
                 X.track = hints && hintKnown > gen;
                 uint32_t activity = 0u;
+                X.out = outBuf; X.outRow = owner ? (wp - 1) * R : -1; X.storer = storer;
+                X.maps = &maps; X.tx = tx; X.ty = ty; X.s = s; X.t0 = t0; X.gen = gen;
+                X.histOn = A.hist != nullptr;
+                X.deferredDone = deferredDone; X.policy = histPolicy; X.tsDebug = A.tsDebug;
+                deferredDone = nullptr;
 
                 if (mode == kFast)
                 {
                     const Stepper<NW, R, kFast> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
-                    stepLoop<NW, R, kFast>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    stepLoop<NW, R, kFast, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
                 else if (mode == kEdge)
                 {
                     const Stepper<NW, R, kEdge> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
-                    stepLoop<NW, R, kEdge>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    stepLoop<NW, R, kEdge, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
                 else
                 {
@@ -616,10 +770,40 @@ namespace pvc
                     const float4* cg = sCoef + (size_t)coefBuf * 2 * TR * 32 + (size_t)(wp * R) * 32 + lane;
                     const uint32_t bpBits = sMask[(size_t)coefBuf * NW * 32 + wp * 32 + lane];
                     const Stepper<NW, R, kGeneral> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, bpBits, cg, cg + (size_t)TR * 32 };
-                    stepLoop<NW, R, kGeneral>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    stepLoop<NW, R, kGeneral, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
 
+                if (threadIdx.x == 32 * 7) trace(A.debug, seq - 1, 5);
                 // ---- store the owned cells of the new state (generation g reads buffer g & 1, writes the other)
+                if (TS)
+                {
+                    // p (= the last sample) and vx left with the last step's group; vy goes through the plane the storer freed
+                    // before the step's closing barrier
+                    constexpr int kPlane = (NW - 2) * R * kValidCols;
+                    const int bLast = (nsteps == kTileK) ? 0 : nsteps - 1;
+                    float* planeVy = outBuf + (bLast + 2) % 3 * kPlane;
+                    if (owner) stageRows<R>(planeVy, X.outRow, lane, vy);
+                    computeBarrier<NW>();
+                    if (storer)
+                    {
+                        if (!(A.tsDebug & 2)) storeStatePlane(X, L, planeVy, 2);
+                        bulkCommit();
+                        if (t0 + nsteps == A.T && A.T > 0)
+                        {
+                            // the very last pass has no successor to inject its last pulse sample: if this tile owns the pulse
+                            // cell, add it to the stored state here (after the stores have completed) so that the final state
+                            // equals the other kernels'
+                            const int sr = m->srcR - (ty * L.valid_rows), sc = m->srcC - tx * kValidCols;
+                            if (sr >= 0 && sr < (NW - 2) * R && sc >= 0 && sc < kValidCols)
+                            {
+                                bulkWait<0>();
+                                float* q = ((gen & 1) ? A.p0 : A.p1) + (size_t)s * L.plane + cellIndex(L, m->srcR, m->srcC);
+                                *q = __fadd_rn(*q, __ldg(A.pulse + (A.T - 1)));
+                            }
+                        }
+                    }
+                }
+                else
                 {
                     float* gp = ((gen & 1) ? A.p0 : A.p1) + src0;
                     float* gx = ((gen & 1) ? A.vx0 : A.vx1) + src0;
@@ -645,7 +829,26 @@ namespace pvc
                         atomicMin(A.firstActive + ((size_t)s * tps + (size_t)ty * L.tiles_x + tx) * 32 + wp, gen);
                 }
                 __syncwarp();
-                if (lane == 0) mbarArrive(done + ((seq - 1) & 1));  // every store of this warp for this tile has been issued
+                if (threadIdx.x == 32 * 7) trace(A.debug, seq - 1, 6);
+                uint64_t* doneBar = done + ((seq - 1) & 1);
+                if (TS)
+                {
+                    if (storer)
+                    {
+                        // The tile counts as stored once the bulk stores have COMPLETED.  If the next tile has already landed,
+                        // do not wait here: arrive after its first step (stepLoop), when only the newest group may still be in
+                        // flight.  If it has not, the producer may be waiting for exactly this arrival before it can hand over
+                        // more work (dependency slow path), so complete now.
+                        if (!(A.tsDebug & 4) && mbarTest(full, fullParity)) deferredDone = doneBar;
+                        else { bulkWait<0>(); mbarArrive(doneBar); }
+                    }
+                }
+                else if (lane == 0) mbarArrive(doneBar);             // every store of this warp for this tile has been issued
+            }
+            if (storer)
+            {
+                bulkWait<0>();
+                if (deferredDone) mbarArrive(deferredDone);
             }
         }
 
@@ -695,10 +898,47 @@ namespace pvc
             return PVC_OK;
         }
 
-        template <int NW, int R, int CB>
+        // TS variants: store maps of the six state planes (dims clipped to the alloc grid, so the hardware drops what the
+        // per-thread predicates of the plain variant drop) and the 5-D history map
+        static int buildStoreMaps(pvc_solver* s, float* hist, int boxRows, CUtensorMap* store, CUtensorMap* histMap)
+        {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            { cudaGetLastError(); setError("ws2 step kernel: cuTensorMapEncodeTiled unavailable"); return PVC_ERR_CUDA; }
+            const Layout& L = s->L;
+            for (int b = 0; b < 2; ++b)
+                for (int f = 0; f < 3; ++f)
+                {
+                    const cuuint64_t dims[3] = { (cuuint64_t)(kGuardCols + L.cols), (cuuint64_t)(kGuardRows + L.rows), (cuuint64_t)s->cfg.max_sources };
+                    const cuuint64_t strides[2] = { (cuuint64_t)L.pitch * sizeof(float), (cuuint64_t)L.plane * sizeof(float) };
+                    const cuuint32_t box[3] = { (cuuint32_t)kValidCols, (cuuint32_t)boxRows, 1u };
+                    const cuuint32_t estr[3] = { 1u, 1u, 1u };
+                    const CUresult r = ((EncodeFn)fn)(&store[b * 3 + f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->state[b][f], dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) { setError("ws2 step kernel: state store tensor map failed (%d)", (int)r); return PVC_ERR_CUDA; }
+                }
+            memset(histMap, 0, sizeof(*histMap));
+            if (hist)
+            {
+                const cuuint64_t dims[5] = { (cuuint64_t)kHistChunk, (cuuint64_t)L.T, (cuuint64_t)L.hist_chunks, (cuuint64_t)L.rows, (cuuint64_t)s->cfg.max_sources };
+                const cuuint64_t strides[4] = { (cuuint64_t)kHistChunk * sizeof(float), (cuuint64_t)L.T * kHistChunk * sizeof(float),
+                                                (cuuint64_t)L.hist_row * sizeof(float), (cuuint64_t)L.hist_source * sizeof(float) };
+                const cuuint32_t box[5] = { (cuuint32_t)kValidCols, 1u, 1u, (cuuint32_t)boxRows, 1u };
+                const cuuint32_t estr[5] = { 1u, 1u, 1u, 1u, 1u };
+                const CUresult r = ((EncodeFn)fn)(histMap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, hist, dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { setError("ws2 step kernel: history tensor map failed (%d)", (int)r); return PVC_ERR_CUDA; }
+            }
+            return PVC_OK;
+        }
+
+        template <int NW, int R, int CB, bool TS = false>
         static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
         {
-            using SM = Smem<NW, R, CB>;
+            using SM = Smem<NW, R, CB, TS>;
             const Layout& L = s->L;
             if (!s->tmaReady || s->tmaTileRows != NW * R) { setError("ws2 step kernel: tensor maps not built for %d-row tiles", NW * R); return PVC_ERR_INVALID; }
             if (t0 != 0 || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
@@ -707,7 +947,7 @@ namespace pvc
             static bool configured[64] = {};
             if (!configured[s->device & 63])
             {
-                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) { setError("ws2 step kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
                 configured[s->device & 63] = true;
             }
@@ -715,6 +955,7 @@ namespace pvc
             memcpy(maps.state, s->tensorMaps, sizeof(maps.state));
             int rc = buildCoefMaps(s, maps.coef);
             if (rc) return rc;
+            memset(maps.store, 0, sizeof(maps.store)); memset(&maps.hist, 0, sizeof(maps.hist));
             const int numTiles = L.tiles_x * L.tiles_y * nsrc;
             const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;          // all CTAs must be co-resident (1 CTA per SM)
             const int gens = (t1 + kTileK - 1) / kTileK;
@@ -726,6 +967,7 @@ namespace pvc
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
             A.hist = hist;
             { static const char* dbg = getenv("PVC_DEBUG_NOHIST"); if (dbg) A.hist = nullptr; }      // debug: memory-floor probe (results invalid)
+            if (TS) { rc = buildStoreMaps(s, A.hist, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
             A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder; A.firstActive = s->firstActive;
             A.src = s->src; A.pulse = s->pulse;
             A.doneGen = s->doneGen; A.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
@@ -741,6 +983,59 @@ namespace pvc
                 A.srcGroup = (nsrc + groups - 1) / groups;
                 A.genChunk = 16;
                 { static const char* ef = getenv("PVC_EARLY_FETCH"); A.earlyFetch = ef ? atoi(ef) : 2; }
+                A.debug = nullptr;
+                { static const char* td = getenv("PVC_TS_DEBUG"); A.tsDebug = td ? atoi(td) : 0; }
+                {
+                    static const char* dbg = getenv("PVC_DEBUG_COUNTERS");
+                    static unsigned long long* counters = nullptr;
+                    if (dbg)
+                    {
+                        const size_t nWords = 4 + (size_t)kTraceCtas * kTraceTiles * kTraceSlots;
+                        if (!counters) { cudaMalloc(&counters, nWords * sizeof(unsigned long long)); }
+                        else
+                        {
+                            std::vector<unsigned long long> hv(nWords);
+                            cudaMemcpy(hv.data(), counters, nWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                            const unsigned long long* h = hv.data();
+                            {
+                                // per-tile phases (ns), averaged over the traced tiles: k = tile, producer slots 0..2, compute (warp 7) slots 3..6
+                                double sum[8] = {}; long cnt = 0;
+                                for (int c = 0; c < kTraceCtas; ++c)
+                                    for (int k = 1; k + 1 < kTraceTiles; ++k)
+                                    {
+                                        const unsigned long long* a = h + 4 + ((size_t)c * kTraceTiles + k) * kTraceSlots;
+                                        const unsigned long long* prev = a - kTraceSlots;
+                                        if (!a[0] || !a[4] || !a[6] || !prev[6] || !a[3] || !a[5] || !a[2]) continue;
+                                        sum[0] += (double)a[4] - (double)a[0];        // TMA issue -> compute sees full
+                                        sum[1] += (double)a[4] - (double)a[3];        // compute wait on full
+                                        sum[2] += (double)a[5] - (double)a[4];        // drain + 4 steps
+                                        sum[3] += (double)a[6] - (double)a[5];        // state stores issued
+                                        sum[4] += (double)a[0] - (double)prev[4];     // previous tile ready -> this TMA issued
+                                        sum[5] += (double)a[1] - (double)a[0];        // fetch of the next item
+                                        sum[6] += (double)a[2] - (double)a[1];        // wait for + publish the previous tile
+                                        sum[7] += (double)a[6] - (double)prev[6];     // tile period
+                                        ++cnt;
+                                    }
+                                for (int c = 5; c < 7; ++c)
+                                {
+                                    const unsigned long long base = h[4 + ((size_t)c * kTraceTiles + 10) * kTraceSlots + 4];
+                                    for (int k = 10; k < 16; ++k)
+                                    {
+                                        const unsigned long long* a = h + 4 + ((size_t)c * kTraceTiles + k) * kTraceSlots;
+                                        fprintf(stderr, "[ws2 raw] cta %d tile %d: P gotempty %6lld issue %6lld fetched %6lld published %6lld | C wait %6lld ready %6lld loopend %6lld stored %6lld\n", c, k,
+                                                (long long)(a[7] - base), (long long)(a[0] - base), (long long)(a[1] - base), (long long)(a[2] - base), (long long)(a[3] - base), (long long)(a[4] - base), (long long)(a[5] - base), (long long)(a[6] - base));
+                                    }
+                                }
+                                if (cnt) fprintf(stderr, "[ws2 trace] n=%ld  issue->ready %.0f  wait-on-full %.0f  drain+steps %.0f  stores %.0f | prevReady->issue %.0f  fetchNext %.0f  publishPrev %.0f | period %.0f ns\n",
+                                                 cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt, sum[6] / cnt, sum[7] / cnt);
+                            }
+                            fprintf(stderr, "[ws2 counters] tiles %llu  slow-path hand-overs %llu (%.2f%%)  compute-warp wait on full: %.1f%% of cycles\n",
+                                    h[0], h[1], h[0] ? 100.0 * h[1] / h[0] : 0.0, h[3] ? 100.0 * h[2] / h[3] : 0.0);
+                        }
+                        cudaMemset(counters, 0, nWords * sizeof(unsigned long long));
+                        A.debug = counters;
+                    }
+                }
                 if (eg && atoi(eg) > 0) A.srcGroup = atoi(eg);
                 if (ec && atoi(ec) > 0) A.genChunk = atoi(ec);
                 if (A.srcGroup > nsrc) A.srcGroup = nsrc;
@@ -750,7 +1045,7 @@ namespace pvc
             {
                 A.gen0 = g0; A.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
                 A.workCounter = s->tileCounters + k;
-                stepKernel<NW, R, CB><<<grid, (NW + 1) * 32, smem, s->stream>>>(L, A, maps);
+                stepKernel<NW, R, CB, TS><<<grid, (NW + 1) * 32, smem, s->stream>>>(L, A, maps);
                 *launches += 1;
             }
             s->cur = gens & 1;
@@ -780,6 +1075,10 @@ namespace pvc
             case 40: return ws2::launch<15, 4, 1>(s, nsrc, t0, t1, hist, launches);
             case 41: return ws2::launch<30, 2, 1>(s, nsrc, t0, t1, hist, launches);
             case 42: return ws2::launch<20, 3, 1>(s, nsrc, t0, t1, hist, launches);
+            case 43: return ws2::launch<14, 4, 1, true>(s, nsrc, t0, t1, hist, launches);
+            case 44: return ws2::launch<10, 8, 1>(s, nsrc, t0, t1, hist, launches);
+            case 45: return ws2::launch<11, 6, 1>(s, nsrc, t0, t1, hist, launches);
+            case 46: return ws2::launch<12, 6, 1>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -791,6 +1090,10 @@ namespace pvc
             case 40: return ws2::buildMask<15, 4>(s);
             case 41: return ws2::buildMask<30, 2>(s);
             case 42: return ws2::buildMask<20, 3>(s);
+            case 43: return ws2::buildMask<14, 4>(s);
+            case 44: return ws2::buildMask<10, 8>(s);
+            case 45: return ws2::buildMask<11, 6>(s);
+            case 46: return ws2::buildMask<12, 6>(s);
             default: return PVC_OK;
         }
     }

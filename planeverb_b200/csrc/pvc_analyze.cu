@@ -14,7 +14,7 @@
 //   * wet energy: ascending t over its window (Analyzer.cpp:235-247);
 //   * RT60: backward Schroeder integral, descending t, with the running log10 and the two regression
 //     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
-// A block is the 120 cells of one history strip: its 4 warps walk one contiguous 480-byte-per-sample stream.
+// A block is the cells of one history strip (128 columns): its 4 warps walk one contiguous 512-byte-per-sample stream.
 #include <float.h>
 #include <cstdlib>
 #include "pvc_internal.h"
@@ -145,6 +145,7 @@ namespace pvc
         int resolution;
     };
 
+    template <int HC>          // history strip width (Layout::hist_chunk) as a compile-time stride
     __global__ void __launch_bounds__(128)
     encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
                          const SourceParams* __restrict__ src, float* __restrict__ results,
@@ -154,19 +155,19 @@ namespace pvc
         if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
         __syncthreads();
 
-        const int c = blockIdx.x * kHistChunk + threadIdx.x;      // block = one 120-column history strip of one row (8 spare threads)
+        const int c = blockIdx.x * HC + threadIdx.x;              // block = one history strip of one row (spare threads if the strip is narrower)
         const int r = blockIdx.y;
         const int s = blockIdx.z;
-        if (threadIdx.x >= kHistChunk || c >= L.gy) return;
+        if ((int)threadIdx.x >= HC || c >= L.gy) return;
         const size_t cells = (size_t)L.gx * L.gy;
         // interior cell (r, c) -> r*gy + c.  The reference strides by the x extent (INDEX_TO_POS, PvDefinitions.h:23-24),
         // which is the same thing on the square grids it supports and self-overlapping on others.
         const size_t serial = (size_t)r * L.gy + c;
         float* out = results + ((size_t)s * cells + serial) * 8;
         const int T = A.T;
-        // sample t of this cell is H[t * 120]: the 4 warps of the block walk one contiguous 480-byte-per-sample stream
+        // sample t of this cell is H[t * hist_chunk]: the 4 warps of the block walk one contiguous stream
         const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c);
-        constexpr ptrdiff_t hs = kHistChunk;
+        constexpr ptrdiff_t hs = HC;
 
         const size_t wi = cellIndex(L, r, c);
         const float wSelf = w[wi];
@@ -230,7 +231,7 @@ namespace pvc
             const bool topEdge = (r == 0), leftEdge = (c == 0);
             const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
             const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
-            const ptrdiff_t leftOff = leftEdge ? 0 : (((c % kHistChunk) != 0) ? -1 : -(ptrdiff_t)T * kHistChunk + (kHistChunk - 1));
+            const ptrdiff_t leftOff = leftEdge ? 0 : (((c % HC) != 0) ? -1 : -(ptrdiff_t)T * hs + (hs - 1));
             float vx = 0.f, vy = 0.f;
             constexpr int kCausalBatch = 4;
             for (int t0 = causalBegin; t0 < fluxEnd; t0 += kCausalBatch)
@@ -589,9 +590,9 @@ namespace pvc
         float vx = 0.f, vy = 0.f;
         for (int t = 0; t < T; ++t)
         {
-            const float p = H[(size_t)t * kHistChunk];
-            const float pu = (r > 0) ? Hu[(size_t)t * kHistChunk] : 0.f;
-            const float pl = (c > 0) ? Hl[(size_t)t * kHistChunk] : 0.f;
+            const float p = H[(size_t)t * L.hist_chunk];
+            const float pu = (r > 0) ? Hu[(size_t)t * L.hist_chunk] : 0.f;
+            const float pl = (c > 0) ? Hl[(size_t)t * L.hist_chunk] : 0.f;
             if (c >= L.gy) vx = 0.f;
             else if (r == 0) vx = -p;
             else if (r == L.gx) vx = pu;
@@ -627,9 +628,14 @@ namespace pvc
         const AnalyzeParams A = paramsOf(s);
         dim3 block(128, 1, 1);
         dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
-        dim3 stripGrid((L.gy + kHistChunk - 1) / kHistChunk, L.gx, nsrc);     // one block per history strip and row
-        encodeResponseKernel<<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
-                                                            s->hintsValid ? s->firstActive : nullptr);
+        dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);     // one block per history strip and row
+        if (L.hist_chunk == kHistChunkDefault)
+            encodeResponseKernel<kHistChunkDefault><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
+                                                                                   s->hintsValid ? s->firstActive : nullptr);
+        else if (L.hist_chunk == kValidCols)
+            encodeResponseKernel<kValidCols><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
+                                                                            s->hintsValid ? s->firstActive : nullptr);
+        else { setError("analyzer: unsupported history strip width %d", L.hist_chunk); return PVC_ERR_INVALID; }
         const char* walkEnv = getenv("PVC_WALK");           // read per call: the tests switch it
         if (walkEnv && walkEnv[0] == 's')
         {

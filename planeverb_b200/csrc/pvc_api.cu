@@ -43,8 +43,9 @@ namespace pvc
         if (L.rows_alloc < L.rows + kGuardRows + 1) L.rows_alloc = L.rows + kGuardRows + 1;
         L.plane = (size_t)L.rows_alloc * L.pitch;
         L.T = c.T;
-        L.hist_chunks = (L.cols + kHistChunk - 1) / kHistChunk;
-        L.hist_row = (size_t)L.hist_chunks * c.T * kHistChunk;
+        L.hist_chunk = fusedHistChunk(c.reserved);
+        L.hist_chunks = (L.cols + L.hist_chunk - 1) / L.hist_chunk;
+        L.hist_row = (size_t)L.hist_chunks * c.T * L.hist_chunk;
         L.hist_source = (size_t)L.rows * L.hist_row;
         return L;
     }
@@ -117,10 +118,10 @@ namespace pvc
         y[(size_t)r * L.cols + c] = air ? 1.f : v;       // air has R = 0 -> Y = 1 in the reference's terms
     }
 
-    __global__ void gatherProbeKernel(const float* __restrict__ hist, size_t offset, int n, float* __restrict__ out)
+    __global__ void gatherProbeKernel(const float* __restrict__ hist, size_t offset, int chunk, int n, float* __restrict__ out)
     {
         const int t = blockIdx.x * blockDim.x + threadIdx.x;
-        if (t < n) out[t] = hist[offset + (size_t)t * kHistChunk];
+        if (t < n) out[t] = hist[offset + (size_t)t * chunk];
     }
 
     // t < 0: a guarded state plane; t >= 0: sample t of a source's pressure history
@@ -129,7 +130,7 @@ namespace pvc
         const int c = blockIdx.x * blockDim.x + threadIdx.x;
         const int r = blockIdx.y;
         if (c > L.gy) return;
-        out[(size_t)r * L.cols + c] = (t < 0) ? plane[cellIndex(L, r, c)] : plane[histCell(L, r, c) + (size_t)t * kHistChunk];
+        out[(size_t)r * L.cols + c] = (t < 0) ? plane[cellIndex(L, r, c)] : plane[histCell(L, r, c) + (size_t)t * L.hist_chunk];
     }
 
     int launchClearGeometry(pvc_solver* s)
@@ -387,7 +388,7 @@ int pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, floa
     std::vector<float> probe((size_t)n);
     if (!rc)
     {
-        gatherProbeKernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->hist, histCell(L, er, ec), n, s->scratch);
+        gatherProbeKernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->hist, histCell(L, er, ec), L.hist_chunk, n, s->scratch);
         if (cudaMemcpyAsync(probe.data(), s->scratch, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
             cudaStreamSynchronize(s->stream) != cudaSuccess)
         { setError("pvc_compute_efree: %s", cudaGetErrorString(cudaGetLastError())); rc = PVC_ERR_CUDA; }

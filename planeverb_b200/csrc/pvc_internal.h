@@ -11,9 +11,9 @@
 //       anything else         -> wall cell (b = 0) and the float is its admittance
 //                                Y = (1-R)/(1+R) (FDTD.cpp:153,160); guard cells are walls with Y = 0.
 //   pressure history   hist [source][row][chunk][t][128]: sample t of alloc cell (r, c) lives at
-//       ((r*hist_chunks + c/120)*T + t)*120 + c%120 -- time-major inside each 120-column strip (the owned
-//       columns of one step-kernel tile, so a tile's record of one sample is ONE dense box for TMA), so the
-//       step kernel appends 480 contiguous bytes per warp-row per step and the analyzer, which walks
+//       ((r*hist_chunks + c/W)*T + t)*W + c%W -- time-major inside each W-column strip (W = 128; 120 for the
+//       TMA-store step variant, where a strip is the owned columns of one tile), so the
+//       step kernel appends 512 contiguous bytes per warp-row per step and the analyzer, which walks
 //       every cell through time, reads each strip as ONE sequential stream.  It is the only per-step
 //       record kept (4 B per cell-step instead of the reference's 16-byte Cell, FDTD.cpp:226-231);
 //       vx/vy of any sample are rebuilt from it.
@@ -42,8 +42,9 @@ namespace pvc
         int rows_alloc;        // state rows incl. guards
         size_t plane;          // rows_alloc * pitch
         int T;                 // samples per impulse response
-        int hist_chunks;       // 120-column strips per row: ceil(cols / 120) = tiles_x
-        size_t hist_row;       // floats between consecutive rows of the history: hist_chunks * T * 120
+        int hist_chunk;        // columns per history strip (128, or 120 for the TMA-store step variant)
+        int hist_chunks;       // strips per row: ceil(cols / hist_chunk)
+        size_t hist_row;       // floats between consecutive rows of the history: hist_chunks * T * hist_chunk
         size_t hist_source;    // floats between sources: rows * hist_row
         int tiles_x, tiles_y;  // fused-kernel tile grid
         int tile_rows;         // rows per tile incl. halo (warps * rows per thread)
@@ -56,13 +57,16 @@ namespace pvc
         return (size_t)(r + kGuardRows) * L.pitch + (c + kGuardCols);
     }
 
-    constexpr int kHistChunk = kValidCols;       // 120: one history strip = the owned columns of one tile
+    // history strip width (Layout::hist_chunk): 128 columns (one aligned 512-byte row per sample and strip) for every kernel
+    // that records with per-thread stores; 120 = the owned columns of one tile for the TMA-store variant, whose record of one
+    // sample must be one dense box
+    constexpr int kHistChunkDefault = 128;
     constexpr int kNeverActive = 0x7f7f7f7f;     // memset(0x7f) pattern of firstActive
 
-    // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*kHistChunk
+    // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*hist_chunk
     __host__ __device__ inline size_t histCell(const Layout& L, int r, int c)
     {
-        return (size_t)r * L.hist_row + (size_t)(c / kHistChunk) * L.T * kHistChunk + (c % kHistChunk);
+        return (size_t)r * L.hist_row + (size_t)(c / L.hist_chunk) * L.T * L.hist_chunk + (c % L.hist_chunk);
     }
 
     struct SourceParams       // one listener, device copy of pvc_listener plus derived indices
@@ -137,6 +141,7 @@ namespace pvc
     int buildTensorMaps(pvc_solver* s);
     int fusedTileRows(int variant);
     int fusedWarpRows(int variant);
+    int fusedHistChunk(int variant);
     // analyzer kernels (pvc_analyze.cu)
     int launchAnalyzer(pvc_solver* s, int nsrc, int* launches);
     int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev);

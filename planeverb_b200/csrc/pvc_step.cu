@@ -70,7 +70,7 @@ namespace pvc
         p4 = make_float4(pv[0], pv[1], pv[2], pv[3]);
         *reinterpret_cast<float4*>(p + base + i) = p4;
         if (hist)
-            __stcs(reinterpret_cast<float4*>(hist + (size_t)s * L.hist_source + histCell(L, r, c) + (size_t)t * kHistChunk), p4);
+            __stcs(reinterpret_cast<float4*>(hist + (size_t)s * L.hist_source + histCell(L, r, c) + (size_t)t * L.hist_chunk), p4);
     }
 
     // both velocity sub-steps + the grid-edge absorbing overrides (FDTD.cpp:144-223)

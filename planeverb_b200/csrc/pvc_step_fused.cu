@@ -159,7 +159,7 @@ namespace pvc
         float* hist = nullptr;
         if (A.hist)
             hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
-                 + ((ptrdiff_t)(cBase / kHistChunk) * L.T + run.t0) * kHistChunk + (cBase % kHistChunk);
+                 + ((ptrdiff_t)(cBase >> 7) * L.T + run.t0) * kHistChunkDefault + (cBase & 127);      // these kernels record 128-column strips
 
         uint32_t activity = 0u;
         // activity-hint slot of this warp's block, fetched now so its latency hides behind the steps
@@ -341,7 +341,7 @@ namespace pvc
                 for (int j = 0; j < R; ++j)
                     if (j >= jLo && j < jHi)
                         __stcs(reinterpret_cast<float4*>(hist + (size_t)j * L.hist_row), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
-                hist += kHistChunk;
+                hist += kHistChunkDefault;
                 // activity hint for the analyzer: has this warp's block recorded anything but zeros yet?  (one 3-input
                 // OR per two cells; conservative -- halo rows and -0 count as activity)
                 #pragma unroll
@@ -1148,6 +1148,11 @@ namespace pvc
         A.timeline = s->timeline;
         if (s->timeline) { static const char* dbg = getenv("PVC_DEBUG_NSTEPS"); if (dbg) A.nsteps = atoi(dbg); }   // debug: memory-floor probe
         return A;
+    }
+
+    int fusedHistChunk(int variant)
+    {
+        return variant == 43 ? kValidCols : kHistChunkDefault;      // the TMA-store variant records dense 120-column boxes
     }
 
     int fusedWarpRows(int variant)

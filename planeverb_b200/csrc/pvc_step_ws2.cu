@@ -162,6 +162,13 @@ namespace pvc
         };
 
         enum { kFast = 0, kEdge = 1, kGeneral = 2 };
+        // Timeline / counter instrumentation (PVC_DEBUG_COUNTERS) is compiled in only with -DPVC_WS2_TRACE: even as dead
+        // branches it costs the step loop ~3 % (registers, predicates).
+    #ifdef PVC_WS2_TRACE
+        #define PVC_DBG(A) ((A).debug)
+    #else
+        #define PVC_DBG(A) ((unsigned long long*)nullptr)
+    #endif
         constexpr int kTraceTiles = 64, kTraceSlots = 8, kTraceCtas = 148;
         __device__ __forceinline__ void trace(unsigned long long* dbg, int seq, int slot)
         {
@@ -302,7 +309,7 @@ namespace pvc
         };
 
         // storer thread: one sample of the tile's VR owned rows.  A history strip is exactly the 120 owned columns of a tile
-        // (kHistChunk == kValidCols), so the record is one dense [VR][120] box: strip tx, sample t, rows from the tile's first
+        // (Layout::hist_chunk == kValidCols for this variant), so the record is one dense [VR][120] box: strip tx, sample t, rows from the tile's first
         // owned row; rows past the grid are clipped by the tensor map.
         __device__ __forceinline__ void storeHistoryPlane(const TileCtx& X, const Layout& L, const float* plane, int t)
         {
@@ -389,7 +396,7 @@ namespace pvc
                         for (int j = 0; j < R; ++j)
                             if ((X.ownRows >> j) & 1u)
                                 __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
-                        X.hist += kHistChunk;
+                        X.hist += kHistChunkDefault;           // compile-time stride (the launcher checks Layout::hist_chunk)
                     }
                     if (X.track)
                     {
@@ -494,14 +501,7 @@ namespace pvc
                     while (true)
                     {
                         const bool ok = !mine || loadAcquire(slot) >= gen;
-                        if (__all_sync(0xffffffffu, ok))
-                        {
-                            // order the acquires above before the async-proxy (TMA) reads of the neighbours' cells.  Done
-                            // here, a tile ahead of the TMA issue, because the fence waits out the CTA's outstanding
-                            // stores (~1-2 us measured): at the issue site it sat between a drained stage and the next load.
-                            asm volatile("fence.proxy.async;" ::: "memory");
-                            return true;
-                        }
+                        if (__all_sync(0xffffffffu, ok)) return true;     // the caller still owes a proxy fence before the TMA (fenceOwed)
                         if (!block) return false;
                         __nanosleep(32);
                         ++spins;
@@ -538,7 +538,7 @@ namespace pvc
                 // fetched right after the TMA of the current one has been issued, before waiting for the tile in flight, so
                 // those round trips never sit between a drained stage and the next TMA; the probe is repeated just before
                 // the hand-over if it failed early.  earlyFetch = 0 (PVC_EARLY_FETCH) fetches at the top of the loop.
-                struct Item { int valid, s, id, tx, ty, gen, mode, hint, misc; bool anySlow, ready; } nx;
+                struct Item { int valid, s, id, tx, ty, gen, mode, hint, misc; bool anySlow, ready, fenced; } nx;
                 auto fetchNext = [&]() {
                     int w = 0;
                     if (lane == 0) w = atomicAdd(A.workCounter, 1);
@@ -579,6 +579,7 @@ namespace pvc
                         nx.misc = __float_as_int((t >= 0 && t < A.T) ? __ldg(A.pulse + t) : 0.f);
                     }
                     nx.ready = (A.earlyFetch == 1) ? false : depsReady(nx.s, nx.tx, nx.ty, nx.gen, false);
+                    nx.fenced = false;
                     nx.anySlow = __ballot_sync(0xffffffffu, lane < NW && nx.mode == kGeneral) != 0u;
                 };
                 if (A.earlyFetch) fetchNext();
@@ -590,8 +591,9 @@ namespace pvc
                     const int s = it.s, id = it.id, tx = it.tx, ty = it.ty, gen = it.gen;
                     const bool anySlow = it.anySlow;
                     bool ready = it.ready;
+                    bool fenced = it.fenced;
                     if (!ready && A.earlyFetch) ready = depsReady(s, tx, ty, gen, false);
-                    if (A.debug && lane == 0) { atomicAdd(A.debug + 0, 1ull); if (!ready) atomicAdd(A.debug + 1, 1ull); }
+                    if (PVC_DBG(A) && lane == 0) { atomicAdd(PVC_DBG(A) + 0, 1ull); if (!ready) atomicAdd(PVC_DBG(A) + 1, 1ull); }
                     if (!ready)
                     {   // it may depend on the tile our own compute warps are working on: publish that first, then wait for real
                         if (!publishPrev()) { alive = false; break; }
@@ -606,7 +608,7 @@ namespace pvc
                         emptyParity ^= 1u;
                         if (!ok) { alive = false; break; }
                     }
-                    if (lane == 0) trace(A.debug, seq, 7);
+                    if (lane == 0) trace(PVC_DBG(A), seq, 7);
                     // single coefficient buffer: the tile being computed may still be reading it
                     if (CB == 1 && anySlow && prevUsedCoef) { if (!publishPrev()) { alive = false; break; } }
 
@@ -619,6 +621,10 @@ namespace pvc
                     else if (lane >= 4 && lane < 8) m->pulse[lane - 4] = __int_as_float(it.misc);
                     else if (lane == 8) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
                     __syncwarp();
+                    // order the dependency acquires before the async-proxy (TMA) reads of the neighbours' cells.  The fence waits
+                    // out the CTA's outstanding stores (~1-2 us measured), so on the fast path it has already been executed a
+                    // tile ahead (after the early probe AND after the previous tile was published, see below)
+                    if (!fenced) asm volatile("fence.proxy.async;" ::: "memory");
                     if (lane == 0)
                     {
                         if (anySlow)
@@ -637,15 +643,16 @@ namespace pvc
                         tmaLoad3d(stage + (size_t)2 * TR * kTileCols, mp + 2, tx * kValidCols, ty * L.valid_rows, s, full);
                     }
                     __syncwarp();
-                    if (lane == 0) trace(A.debug, seq, 0);
+                    if (lane == 0) trace(PVC_DBG(A), seq, 0);
                     if (anySlow) ++coefPhase;
                     ++seq;
                     stageBusy = true;
                     if (A.earlyFetch) fetchNext();                // the next item's fetch overlaps the tile in flight
                     // the tile handed over before this one is (or was) being computed: publish it once the compute warps are done
-                    if (lane == 0) trace(A.debug, seq - 1, 1);
+                    if (lane == 0) trace(PVC_DBG(A), seq - 1, 1);
                     if (!publishPrev()) { alive = false; break; }
-                    if (lane == 0) trace(A.debug, seq - 1, 2);
+                    if (A.earlyFetch && nx.valid && nx.ready) { asm volatile("fence.proxy.async;" ::: "memory"); nx.fenced = true; }
+                    if (lane == 0) trace(PVC_DBG(A), seq - 1, 2);
                     prevSlot = s * tps + id; prevGen = gen; prevUsedCoef = anySlow; prevSeq = seq - 1;
                 }
                 // drain: publish the last tile, then tell the compute warps to stop
@@ -663,7 +670,7 @@ namespace pvc
             // ================= compute warps =================
             uint32_t fullParity = 0;
             int seq = 0;
-            long long tStart = A.debug ? clock64() : 0;
+            long long tStart = PVC_DBG(A) ? clock64() : 0;
             const bool owner = TS && wp >= 1 && wp <= NW - 2;
             const bool storer = TS && threadIdx.x == 0;
             float* const outBuf = reinterpret_cast<float*>(smemRaw + SM::offOut);
@@ -672,12 +679,12 @@ namespace pvc
             while (true)
             {
                 long long tw0 = 0;
-                if (A.debug) tw0 = clock64();
-                if (threadIdx.x == 32 * 7) trace(A.debug, seq, 3);
+                if (PVC_DBG(A)) tw0 = clock64();
+                if (threadIdx.x == 32 * 7) trace(PVC_DBG(A), seq, 3);
                 if (!mbarWaitBounded(full, fullParity, A.abortFlag)) break;
-                if (A.debug && threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(A.debug + 2, (unsigned long long)(t1 - tw0)); atomicAdd(A.debug + 3, (unsigned long long)(t1 - tStart)); tStart = t1; }
+                if (PVC_DBG(A) && threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(PVC_DBG(A) + 2, (unsigned long long)(t1 - tw0)); atomicAdd(PVC_DBG(A) + 3, (unsigned long long)(t1 - tStart)); tStart = t1; }
                 fullParity ^= 1u;
-                if (threadIdx.x == 32 * 7) trace(A.debug, seq, 4);
+                if (threadIdx.x == 32 * 7) trace(PVC_DBG(A), seq, 4);
                 const Meta* m = meta + (seq & 1);
                 ++seq;
                 if (m->valid == 0) break;
@@ -734,7 +741,7 @@ namespace pvc
                 X.hist = nullptr;
                 if (A.hist)
                     X.hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
-                           + ((ptrdiff_t)(cBase / kHistChunk) * L.T + t0) * kHistChunk + (cBase % kHistChunk);
+                           + ((ptrdiff_t)(cBase >> 7) * L.T + t0) * kHistChunkDefault + (cBase & 127);
                 X.histRow = L.hist_row;
                 X.ownRows = ownRows;
                 {
@@ -773,7 +780,7 @@ namespace pvc
                     stepLoop<NW, R, kGeneral, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
 
-                if (threadIdx.x == 32 * 7) trace(A.debug, seq - 1, 5);
+                if (threadIdx.x == 32 * 7) trace(PVC_DBG(A), seq - 1, 5);
                 // ---- store the owned cells of the new state (generation g reads buffer g & 1, writes the other)
                 if (TS)
                 {
@@ -829,7 +836,7 @@ namespace pvc
                         atomicMin(A.firstActive + ((size_t)s * tps + (size_t)ty * L.tiles_x + tx) * 32 + wp, gen);
                 }
                 __syncwarp();
-                if (threadIdx.x == 32 * 7) trace(A.debug, seq - 1, 6);
+                if (threadIdx.x == 32 * 7) trace(PVC_DBG(A), seq - 1, 6);
                 uint64_t* doneBar = done + ((seq - 1) & 1);
                 if (TS)
                 {
@@ -922,8 +929,8 @@ namespace pvc
             memset(histMap, 0, sizeof(*histMap));
             if (hist)
             {
-                const cuuint64_t dims[5] = { (cuuint64_t)kHistChunk, (cuuint64_t)L.T, (cuuint64_t)L.hist_chunks, (cuuint64_t)L.rows, (cuuint64_t)s->cfg.max_sources };
-                const cuuint64_t strides[4] = { (cuuint64_t)kHistChunk * sizeof(float), (cuuint64_t)L.T * kHistChunk * sizeof(float),
+                const cuuint64_t dims[5] = { (cuuint64_t)L.hist_chunk, (cuuint64_t)L.T, (cuuint64_t)L.hist_chunks, (cuuint64_t)L.rows, (cuuint64_t)s->cfg.max_sources };
+                const cuuint64_t strides[4] = { (cuuint64_t)L.hist_chunk * sizeof(float), (cuuint64_t)L.T * L.hist_chunk * sizeof(float),
                                                 (cuuint64_t)L.hist_row * sizeof(float), (cuuint64_t)L.hist_source * sizeof(float) };
                 const cuuint32_t box[5] = { (cuuint32_t)kValidCols, 1u, 1u, (cuuint32_t)boxRows, 1u };
                 const cuuint32_t estr[5] = { 1u, 1u, 1u, 1u, 1u };
@@ -943,6 +950,7 @@ namespace pvc
             if (!s->tmaReady || s->tmaTileRows != NW * R) { setError("ws2 step kernel: tensor maps not built for %d-row tiles", NW * R); return PVC_ERR_INVALID; }
             if (t0 != 0 || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
             if (!s->bpMask) { setError("ws2 step kernel: descriptor buffer missing"); return PVC_ERR_INVALID; }
+            if (L.hist_chunk != (TS ? kValidCols : kHistChunkDefault)) { setError("ws2 step kernel: history strip width %d does not match the variant", L.hist_chunk); return PVC_ERR_INVALID; }
             const size_t smem = SM::total;
             static bool configured[64] = {};
             if (!configured[s->device & 63])

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libplaneverb_b200.so")
+LIB_PATH = os.environ.get("PVC_LIB_PATH") or os.path.join(_HERE, "lib", "libplaneverb_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 PVC_OK, PVC_ERR_INVALID, PVC_ERR_MEMORY, PVC_ERR_CUDA, PVC_ERR_NO_DEVICE = range(5)
@@ -105,7 +105,8 @@ def lib():
         L.pvc_fetch_state.argtypes = [_vp, _i, _vp, _vp, _vp]
         L.pvc_fetch_coefficients.argtypes = [_vp, _vp, _vp]
         L.pvc_last_timing.argtypes = [_vp, _vp, _vp]
-        L.pvc_last_launch_counts.argtypes = [_vp, _vp, _vp]
+        if hasattr(L, "pvc_last_launch_counts"):          # absent from older builds loaded through PVC_LIB_PATH (A/B timing)
+            L.pvc_last_launch_counts.argtypes = [_vp, _vp, _vp]
         L.pvc_clear_results.argtypes = [_vp, _i]
         L.pvc_synchronize.argtypes = [_vp]
         L.pvc_mark.argtypes = [_vp, _i]

@@ -11,7 +11,13 @@ rows = [r for r in csv.reader(open(os.path.join(GO, "launches.csv"))) if len(r) 
 hdr = rows[0]
 ik, iv, im = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
 agg = collections.OrderedDict()
-for r in rows[1:]:
+timed = [r for r in rows[1:] if r[im] == "gpu__time_duration.sum"]
+# the last two solves of the run: cut at the third-from-last encodeResponseKernel's end, i.e. keep everything after the
+# launch that follows it (the step kernels of a solve precede its analyzer kernels)
+enc = [i for i, r in enumerate(timed) if "encodeResponseKernel" in r[ik]]
+resolve = [i for i, r in enumerate(timed) if "walkResolveKernel" in r[ik] or "listenerDirectionKernel" in r[ik]]
+start = (resolve[-3] + 1) if len(resolve) >= 3 else 0
+for r in timed[start:]:
     if r[im] != "gpu__time_duration.sum":
         continue
     name = r[ik].split("(")[0]
@@ -22,8 +28,8 @@ unit = rows[1][hdr.index("Metric Unit")]
 scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1e-3)       # -> microseconds
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(OUT, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write("# PVC_NO_GRAPHS=1 ncu --metrics gpu__time_duration.sum --clock-control none -s 18 -c 12 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
-    f.write("# two solves of the bench (1 solve = 4 step-kernel launches of <= 256 generations x 4 time steps + 2 analyzer kernels); cold-cache, serialised: compare SHARES\n")
+    f.write("# PVC_NO_GRAPHS=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
+    f.write("# the last two solves of that run (1 solve = 4 step-kernel launches of <= 256 generations x 4 time steps + 8 analyzer kernels); cold-cache, serialised: compare SHARES\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'total_us':>12s} {'avg_us':>9s} {'share':>7s}\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k[:60]:60s} {n:8d} {t*scale:12.1f} {t*scale/n:9.2f} {100*t/tot:6.1f}%\n")

@@ -125,6 +125,13 @@ PVC_API int  pvc_synchronize(pvc_solver* s);
 PVC_API int  pvc_clear_results(pvc_solver* s, int source);
 /* results: gx*gy*8 floats, delay: gx*gy floats (FLT_MAX = no onset); either may be NULL. Synchronous. */
 PVC_API int  pvc_fetch_results(pvc_solver* s, int source, float* results, float* delay);
+/* Pipelined form for frame loops: enqueue the copy of the result grids of sources 0..n-1 of the LAST pvc_run (results:
+ * n*gx*gy*8 floats, delay: n*gx*gy floats, either may be NULL; use pvc_host_alloc'd memory) on the solver's copy stream and
+ * return at once.  The copy starts when that run's analyzer has finished and overlaps the time steps of the next pvc_run, whose
+ * analyzer in turn waits for the copy before it overwrites the device grids.  pvc_fetch_wait blocks until the host buffers
+ * are filled (and reports a failed run).  One copy in flight at a time. */
+PVC_API int  pvc_fetch_results_async(pvc_solver* s, int n, float* results, float* delay);
+PVC_API int  pvc_fetch_wait(pvc_solver* s);
 /* the 8 floats of one interior cell (Analyzer::GetResponseResult, Analyzer.cpp:106-116) */
 PVC_API int  pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8);
 /* impulse response of alloc cell (r,c): T x {p, vx, vy} (Grid::GetResponse). vx/vy are rebuilt on the

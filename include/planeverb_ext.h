@@ -50,6 +50,10 @@ PVC_API int  pvx_solve(pvx_scene* sc, const float* listenersXYZ, int n, int anal
 /* asynchronous halves for overlapped multi-device use */
 PVC_API int  pvx_solve_async(pvx_scene* sc, const float* listenersXYZ, int n, int analyze);
 PVC_API int  pvx_wait(pvx_scene* sc);
+/* frame-loop form: solve + enqueue the copy of this solve's result grids into (results, delay) without waiting; the copy
+ * overlaps the next solve.  pvx_fetch_wait returns when the buffers of the last pvx_solve_pipelined are filled. */
+PVC_API int  pvx_solve_pipelined(pvx_scene* sc, const float* listenersXYZ, int n, float* results, float* delay);
+PVC_API int  pvx_fetch_wait(pvx_scene* sc);
 
 /* Analyzer::GetResponseResult for a world-space emitter position: 0 = ok and out8 filled,
  * PVC_ERR_INVALID when the reference would return nullptr (outside the grid) */

@@ -147,18 +147,27 @@ namespace pvc
         if (n <= 0) return PVC_OK;
         const Layout& L = s->L;
         if (n > s->rectCapacity)
-        {   // persistent edit-list buffer (stream-ordered allocation here cost up to tens of ms per frame in pool trimming)
+        {   // persistent edit-list buffers (stream-ordered allocation here cost up to tens of ms per frame in pool trimming)
+            PVC_CUDA(cudaStreamSynchronize(s->stream));
             if (s->rects) cudaFree(s->rects);
-            s->rects = nullptr; s->rectCapacity = 0;
+            if (s->rectsHost) cudaFreeHost(s->rectsHost);
+            s->rects = nullptr; s->rectsHost = nullptr; s->rectCapacity = 0;
             const int cap = n < 64 ? 64 : 2 * n;
             PVC_CUDA(cudaMalloc(&s->rects, sizeof(pvc_rect) * (size_t)cap));
+            PVC_CUDA(cudaMallocHost(&s->rectsHost, sizeof(pvc_rect) * (size_t)cap * 2));
             s->rectCapacity = cap;
         }
-        PVC_CUDA(cudaMemcpyAsync(s->rects, rects_host, sizeof(pvc_rect) * n, cudaMemcpyHostToDevice, s->stream));
+        // the caller's list may be a temporary: stage it in pinned memory instead of waiting for the copy
+        const unsigned slot = s->rectSlot++ & 1u;
+        if (!s->rectCopied[slot]) PVC_CUDA(cudaEventCreateWithFlags(&s->rectCopied[slot], cudaEventDisableTiming));
+        PVC_CUDA(cudaEventSynchronize(s->rectCopied[slot]));
+        pvc_rect* staged = s->rectsHost + (size_t)slot * s->rectCapacity;
+        memcpy(staged, rects_host, sizeof(pvc_rect) * (size_t)n);
+        PVC_CUDA(cudaMemcpyAsync(s->rects, staged, sizeof(pvc_rect) * n, cudaMemcpyHostToDevice, s->stream));
+        PVC_CUDA(cudaEventRecord(s->rectCopied[slot], s->stream));
         dim3 block(32, 8), grid((L.cols + 31) / 32, (L.rows + 7) / 8);
         applyRectsKernel<<<grid, block, 0, s->stream>>>(L, s->w, s->rects, n);
         PVC_CUDA(cudaGetLastError());
-        PVC_CUDA(cudaStreamSynchronize(s->stream));      // rects_host may be a caller temporary
         s->slowMaskDirty = 1;
         return PVC_OK;
     }
@@ -265,6 +274,11 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) PVC_TRY(cudaEventCreate(&s->ev[i]));
     for (int i = 0; i < 2; ++i) PVC_TRY(cudaEventCreate(&s->mark[i]));
+    PVC_TRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+    PVC_TRY(cudaEventCreateWithFlags(&s->evAnalyzed, cudaEventDisableTiming));
+    PVC_TRY(cudaEventCreateWithFlags(&s->evCopied, cudaEventDisableTiming));
+    PVC_TRY(cudaMallocHost(&s->hostAbort, sizeof(int)));
+    *s->hostAbort = 0;
     for (int b = 0; b < 2; ++b)
         for (int f = 0; f < 3; ++f)
         {
@@ -292,6 +306,8 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaMalloc(&s->walkNext, sizeof(int) * S * cells));
     PVC_TRY(cudaMalloc(&s->scratch, sizeof(float) * 3 * (size_t)cfg->T));
     PVC_TRY(cudaMalloc(&s->src, sizeof(SourceParams) * S));
+    PVC_TRY(cudaMallocHost(&s->srcHost, sizeof(SourceParams) * S * 4));
+    for (int i = 0; i < 4; ++i) PVC_TRY(cudaEventCreateWithFlags(&s->srcCopied[i], cudaEventDisableTiming));
     #undef PVC_TRY
     s->efree = 1.f;
     s->useGraphs = getenv("PVC_NO_GRAPHS") ? 0 : 1;
@@ -310,6 +326,14 @@ void pvc_destroy(pvc_solver* s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
     cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
+    if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
+    if (s->evAnalyzed) cudaEventDestroy(s->evAnalyzed);
+    if (s->evCopied) cudaEventDestroy(s->evCopied);
+    if (s->hostAbort) cudaFreeHost(s->hostAbort);
+    if (s->srcHost) cudaFreeHost(s->srcHost);
+    if (s->rectsHost) cudaFreeHost(s->rectsHost);
+    for (int i = 0; i < 2; ++i) if (s->rectCopied[i]) cudaEventDestroy(s->rectCopied[i]);
+    for (int i = 0; i < 4; ++i) if (s->srcCopied[i]) cudaEventDestroy(s->srcCopied[i]);
     cudaFree(s->results); cudaFree(s->delay); cudaFree(s->walkDelay); cudaFree(s->walkNext); cudaFree(s->scratch); cudaFree(s->src);
     for (int i = 0; i <= kMaxGraphBatch; ++i) if (s->graphs[i].exec) cudaGraphExecDestroy(s->graphs[i].exec);
     for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -410,16 +434,23 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
 {
     if (!s || !listeners || n < 1 || n > s->cfg.max_sources) { setError("pvc_run: bad argument (n=%d)", n); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
-    std::vector<SourceParams> sp((size_t)n);
     for (int i = 0; i < n; ++i)
     {
         const pvc_listener& l = listeners[i];
         if (l.cell_r < 0 || l.cell_c < 0 || l.cell_r > s->cfg.gx || l.cell_c > s->cfg.gy)
         { setError("pvc_run: listener %d cell (%d,%d) outside the grid", i, l.cell_r, l.cell_c); return PVC_ERR_INVALID; }
-        sp[(size_t)i] = SourceParams{ l.cell_r, l.cell_c, l.efree_r, l.efree_c, l.x, l.z };
     }
-    PVC_CUDA(cudaMemcpyAsync(s->src, sp.data(), sizeof(SourceParams) * n, cudaMemcpyHostToDevice, s->stream));
-    PVC_CUDA(cudaStreamSynchronize(s->stream));          // sp is a local
+    // staged through a pinned ring so that a frame loop can enqueue run k+1 while run k is still on the device
+    const unsigned slot = s->srcSlot++ & 3u;
+    PVC_CUDA(cudaEventSynchronize(s->srcCopied[slot]));
+    SourceParams* sp = s->srcHost + (size_t)slot * s->cfg.max_sources;
+    for (int i = 0; i < n; ++i)
+    {
+        const pvc_listener& l = listeners[i];
+        sp[i] = SourceParams{ l.cell_r, l.cell_c, l.efree_r, l.efree_c, l.x, l.z };
+    }
+    PVC_CUDA(cudaMemcpyAsync(s->src, sp, sizeof(SourceParams) * n, cudaMemcpyHostToDevice, s->stream));
+    PVC_CUDA(cudaEventRecord(s->srcCopied[slot], s->stream));
     int launches = 0;
     PVC_CUDA(cudaEventRecord(s->ev[0], s->stream));
     int rc = zeroState(s, n);
@@ -431,7 +462,13 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
     if (rc) return rc;
     s->lastStepLaunches = launches;
     PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));
-    if (analyze) { rc = launchAnalyzer(s, n, &launches); if (rc) return rc; }
+    if (analyze)
+    {
+        // a pipelined fetch of the previous run's grids must finish before the analyzer overwrites them
+        if (s->copyPending) PVC_CUDA(cudaStreamWaitEvent(s->stream, s->evCopied, 0));
+        rc = launchAnalyzer(s, n, &launches);
+        if (rc) return rc;
+    }
     PVC_CUDA(cudaEventRecord(s->ev[2], s->stream));
     s->lastSources = n;
     s->lastLaunches = launches;
@@ -475,6 +512,39 @@ int pvc_fetch_results(pvc_solver* s, int source, float* results, float* delay)
     if (delay) PVC_CUDA(cudaMemcpyAsync(delay, s->delay + (size_t)source * cells, sizeof(float) * cells, cudaMemcpyDeviceToHost, s->stream));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
     return checkAbort(s);
+}
+
+int pvc_fetch_results_async(pvc_solver* s, int n, float* results, float* delay)
+{
+    if (!s || n < 1 || n > s->cfg.max_sources) { setError("pvc_fetch_results_async: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    if (s->copyPending) PVC_CUDA(cudaEventSynchronize(s->evCopied));       // one copy in flight at a time
+    const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
+    *s->hostAbort = 0;
+    if (s->checkAbort)
+    {
+        // the abort word is read on the solver's own stream: the next pvc_run resets it there
+        PVC_CUDA(cudaMemcpyAsync(s->hostAbort, s->tileCounters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        s->checkAbort = 0;
+    }
+    PVC_CUDA(cudaEventRecord(s->evAnalyzed, s->stream));
+    PVC_CUDA(cudaStreamWaitEvent(s->copyStream, s->evAnalyzed, 0));
+    if (results) PVC_CUDA(cudaMemcpyAsync(results, s->results, sizeof(float) * cells * 8 * (size_t)n, cudaMemcpyDeviceToHost, s->copyStream));
+    if (delay) PVC_CUDA(cudaMemcpyAsync(delay, s->delay, sizeof(float) * cells * (size_t)n, cudaMemcpyDeviceToHost, s->copyStream));
+    PVC_CUDA(cudaEventRecord(s->evCopied, s->copyStream));
+    s->copyPending = 1;
+    return PVC_OK;
+}
+
+int pvc_fetch_wait(pvc_solver* s)
+{
+    if (!s) { setError("pvc_fetch_wait: null solver"); return PVC_ERR_INVALID; }
+    if (!s->copyPending) return PVC_OK;
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaEventSynchronize(s->evCopied));
+    s->copyPending = 0;
+    if (*s->hostAbort) { *s->hostAbort = 0; setError("generational step kernel: a tile dependency wait timed out (results invalid)"); return PVC_ERR_CUDA; }
+    return PVC_OK;
 }
 
 int pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8)

@@ -92,6 +92,10 @@ struct pvc_solver
     cudaStream_t stream;
     cudaEvent_t ev[4];
     cudaEvent_t mark[2];
+    cudaStream_t copyStream; // pipelined result fetch (pvc_fetch_results_async)
+    cudaEvent_t evAnalyzed, evCopied;
+    int copyPending;
+    int* hostAbort;          // pinned: abort flag of the run whose results are being fetched
 
     float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
     float* w;                // wall plane (air flag / admittance), the geometry's source of truth
@@ -118,7 +122,13 @@ struct pvc_solver
     float* scratch;          // small device scratch (IR fetch)
     pvc_rect* rects;         // device copy of the current geometry edit list
     int rectCapacity;
+    pvc_rect* rectsHost;     // pinned staging, 2 x rectCapacity (alternating halves): applying edits never waits for the stream
+    cudaEvent_t rectCopied[2];
+    unsigned rectSlot;
     pvc::SourceParams* src;  // max_sources
+    pvc::SourceParams* srcHost;     // pinned ring of kSrcRing x max_sources staging slots: pvc_run never waits for the stream
+    cudaEvent_t srcCopied[4];
+    unsigned srcSlot;
     float efree;
     int cur;                 // ping-pong index holding the latest state
     int lastSources;

@@ -1341,6 +1341,15 @@ namespace pvc
         if (e != cudaSuccess) { setError("slow mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         // tile order, most expensive first (general-path warps cost ~3x, edge-path ~1.3x a fast warp)
         const int tiles = L.tiles_x * L.tiles_y;
+        {
+            // row-major order (see below) needs no read-back: a frame loop that edits geometry every frame then never
+            // waits for the device here.  The identity order is uploaded once.
+            static const char* orderEnv0 = getenv("PVC_TILE_ORDER");
+            int v0 = s->cfg.reserved; if (v0 < 0 || v0 >= kNumVariants) v0 = 0;
+            bool natural0 = kVariants[v0].persistent >= 4;
+            if (orderEnv0) natural0 = orderEnv0[0] == 'n';
+            if (natural0 && s->tileOrderNatural == 1) { s->slowMaskDirty = 0; return PVC_OK; }
+        }
         std::vector<uint32_t> modes((size_t)tiles * 32);
         if (cudaMemcpyAsync(modes.data(), s->slowMask, sizeof(uint32_t) * modes.size(), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
             cudaStreamSynchronize(s->stream) != cudaSuccess)

@@ -146,6 +146,19 @@ int pvx_solve(pvx_scene* sc, const float* listenersXYZ, int n, int analyze, floa
     return pvc_synchronize(sc->solver);
 }
 
+int pvx_solve_pipelined(pvx_scene* sc, const float* listenersXYZ, int n, float* results, float* delay)
+{
+    int rc = pvx_solve_async(sc, listenersXYZ, n, 1);
+    if (rc) return rc;
+    return pvc_fetch_results_async(sc->solver, n, results, delay);
+}
+
+int pvx_fetch_wait(pvx_scene* sc)
+{
+    if (!sc) return PVC_ERR_INVALID;
+    return pvc_fetch_wait(sc->solver);
+}
+
 int pvx_lookup(pvx_scene* sc, int source, float x, float y, float z, float* out8)
 {
     (void)y;

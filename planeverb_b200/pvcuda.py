@@ -25,13 +25,13 @@ PVC_SYMBOLS = [
     "pvc_device_count", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
-    "pvc_fetch_results", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
+    "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
     "pvc_last_timing", "pvc_last_launch_counts", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
     "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline",
 ]
 PVX_SYMBOLS = [
     "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
-    "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_lookup",
+    "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup",
     "pvx_impulse_response", "pvx_solver",
     "pvx_derive", "pvx_derive_pulse", "pvx_derive_rect", "pvx_derive_listener", "pvx_derive_emitter_cell",
 ]
@@ -96,6 +96,10 @@ def lib():
         L.pvx_solve.argtypes = [_vp, _vp, _i, _i, _vp, _vp]
         L.pvx_solve_async.argtypes = [_vp, _vp, _i, _i]
         L.pvx_wait.argtypes = [_vp]
+        L.pvx_solve_pipelined.argtypes = [_vp, _vp, _i, _vp, _vp]
+        L.pvx_fetch_wait.argtypes = [_vp]
+        L.pvc_fetch_results_async.argtypes = [_vp, _i, _vp, _vp]
+        L.pvc_fetch_wait.argtypes = [_vp]
         L.pvx_lookup.argtypes = [_vp, _i, _f, _f, _f, _vp]
         L.pvx_impulse_response.argtypes = [_vp, _i, _f, _f, _f, _vp]
         L.pvx_solver.argtypes = [_vp]
@@ -204,6 +208,7 @@ class Scene:
          self.max_sources) = (int(v) for v in ii)
         self.dx, self.dt, self.courant, self.efree = (np.float32(v) for v in ff)
         self.resolution = int(resolution)
+        self.size_x, self.size_y = float(size_x), float(size_y)
         self._solver = lib().pvx_solver(self._h)
 
     def close(self):
@@ -264,6 +269,22 @@ class Scene:
 
     def wait(self):
         _check(lib().pvx_wait(self._h), "pvx_wait")
+
+    def solve_pipelined(self, listeners, out):
+        """Frame-loop form: enqueue the solve and the copy of ITS result grids into out = (results, delay) (pinned_array
+        buffers) and return at once; the copy overlaps the next solve.  fetch_wait() returns when out is filled."""
+        a, n = self._listeners(listeners)
+        res, dly = out
+        cells = self.gx * self.gy
+        assert res.shape == (n, cells, 8) and dly.shape == (n, cells)
+        _check(lib().pvx_solve_pipelined(self._h, _p(a), n, _p(res), _p(dly)), "pvx_solve_pipelined")
+
+    def fetch_wait(self):
+        _check(lib().pvx_fetch_wait(self._h), "pvx_fetch_wait")
+
+    def emitter_cell(self, pos):
+        """Analyzer::GetResponseResult's cell of a world-space emitter position (Analyzer.cpp:106-116), or None outside the grid."""
+        return derive_emitter_cell(self.resolution, self.size_x, self.size_y, pos[0], pos[2])
 
     def fetch_results(self, source=0):
         cells = self.gx * self.gy

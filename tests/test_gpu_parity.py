@@ -356,6 +356,48 @@ def test_config5_dynamic_geometry_frames(pv, scenes):
     live.close()
 
 
+def test_pipelined_frame_loop_equals_synchronous_solves(pv, scenes):
+    """pvx_solve_pipelined / pvx_fetch_wait (the frame-loop form: the D2H copy of frame k's result grids overlaps the time
+    steps of frame k+1, geometry edits and listeners staged through pinned rings so the host never waits for the stream):
+    every frame's host grids must equal, bit for bit, a synchronous solve of a fresh scene in the same state -- including
+    the stale values cells without an onset keep from the frame before (Analyzer.cpp:161-165)."""
+    n, T, S = 256, 300, 2
+    size, scale = common.scaled_config(n)
+    boxes = common.boxes_of(scenes, "FloorPlanScene", scale)
+    door = boxes[3]
+    cells = n * n
+    live = pv.Scene(size, size, 275, T=T, max_sources=S, efree=0.0447895788)
+    sync = pv.Scene(size, size, 275, T=T, max_sources=S, efree=0.0447895788)
+    for b in boxes:
+        live.add_aabb(*b); sync.add_aabb(*b)
+    bufs = [(pv.pinned_array((S, cells, 8)), pv.pinned_array((S, cells))) for _ in range(2)]
+    frames = 5
+    expect = []
+    cur = door
+    for k in range(frames):
+        moved = (door[0] + 0.4 * (k + 1) * scale, door[1] - 0.3 * (k + 1) * scale, door[2], door[3], door[4])
+        L = common.listeners_for(S, scale)
+        L = [(x + 0.2 * k * scale, y, z) for (x, y, z) in L]
+        sync.remove_aabb(*cur); sync.add_aabb(*moved)
+        r, d = sync.solve(L)
+        expect.append((r.copy(), d.copy()))
+        live.remove_aabb(*cur); live.add_aabb(*moved)
+        live.solve_pipelined(L, bufs[k & 1])                    # returns once frame k-1's grids are on the host
+        if k > 0:
+            r0, d0 = bufs[(k - 1) & 1]
+            assert np.array_equal(d0, expect[k - 1][1]), f"frame {k - 1}: delays differ"
+            assert np.array_equal(r0.view(np.uint32), expect[k - 1][0].view(np.uint32)), f"frame {k - 1}: results differ"
+        cur = moved
+    live.fetch_wait()
+    r0, d0 = bufs[(frames - 1) & 1]
+    assert np.array_equal(d0, expect[-1][1]) and np.array_equal(r0.view(np.uint32), expect[-1][0].view(np.uint32))
+    live.fetch_wait()                                           # idempotent
+    # a synchronous call after the pipelined ones still works on the same scene
+    r1, d1 = live.solve(L)
+    assert np.array_equal(r1.view(np.uint32), expect[-1][0].view(np.uint32)) and np.array_equal(d1, expect[-1][1])
+    live.close(); sync.close()
+
+
 def test_non_square_grid_is_consistent(pv):
     """The reference mixes strides on non-square grids; this library indexes them consistently:
     fields must match the oracle's solver (which uses the FDTD stride gy+1 throughout), the fused and baseline

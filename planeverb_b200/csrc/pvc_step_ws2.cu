@@ -120,6 +120,26 @@ namespace pvc
         {
             asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
         }
+        // Neighbour-only synchronisation of the step loop (PVC_PAIR_SYNC): a warp exchanges halo rows only with the warp above
+        // and the warp below, so instead of a CTA-wide barrier per sub-step it meets each neighbour on the named barrier of
+        // their common edge (id = upper warp + 1; 64 threads).  Even warps take the lower edge first, odd warps the upper
+        // one, so every edge is the first meeting of both its warps or the second of both: no cycle.  Warps more than k
+        // edges away from a slow (wall-path) warp may run k sub-steps ahead of it, finish their pass early and issue their
+        // state stores / drain the next stage while the slow warps still compute.
+    #ifndef PVC_PAIR_SYNC
+        #define PVC_PAIR_SYNC 0
+    #endif
+        __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+        template <int NW, bool TS>
+        __device__ __forceinline__ void phaseSync(int wp)
+        {
+            if (PVC_PAIR_SYNC && !TS && NW <= 16)
+            {
+                if (wp & 1) { pairBarrier(wp); if (wp + 1 < NW) pairBarrier(wp + 1); }
+                else { if (wp + 1 < NW) pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
+            }
+            else computeBarrier<NW>();
+        }
         __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
 
         // ---------------------------------------------------------------- kernel arguments (never indexed dynamically)
@@ -140,6 +160,9 @@ namespace pvc
             int tilesPerSource, nsrc, numTiles;    // numTiles = tilesPerSource * nsrc
             int gen0, numGen, T;
             int earlyFetch;
+            int lateRelease;                       // release a tile's generation counter after the next TMA has been issued (1, default)
+            int fenceMode;                         // cross-proxy fence: 0 reader side after the publish, 1 reader side right after the early probe, 2 writer side (with the release)
+            int slowPathPoll;                      // dependency miss: poll deps and own tile together (1, default) or publish own tile first (0)
             int tsDebug;                           // debug: bit 0 no history TMA, bit 1 no state TMA, bit 2 never defer the done arrival
             unsigned long long* debug;             // optional counters (PVC_DEBUG_COUNTERS): tiles, slow-path hand-overs, cycles waiting / total
             int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
@@ -375,7 +398,7 @@ namespace pvc
                     else if (step == 3) bulkWaitRead<1>();            // planes 0, 1: g0, g1; g2 may still read
                     else bulkWaitRead<2>();                           // plane 1 / 2: previous pass's g3 / g4
                 }
-                computeBarrier<NW>();
+                phaseSync<NW, TS>(wp);
                 // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
                 S.velocity(p, vx, vy, sPBot[wp][lane]);
                 // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
@@ -412,7 +435,7 @@ namespace pvc
                 if (!last) sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
                 if (TS && X.storer && last) bulkWaitRead<0>();        // plane for vy (staged after the barrier): g2, one step old
                 // also the write-after-read fence of sPBot for the next pass's first pressure sub-step
-                computeBarrier<NW>();
+                phaseSync<NW, TS>(wp);
                 if (TS && X.storer)
                 {
                     const float* plane = X.out + ((step == 3) ? 0 : step) * kPlane;
@@ -447,11 +470,12 @@ namespace pvc
             static constexpr uint32_t kOutPlaneBytes = (NW - 2) * R * kValidCols * sizeof(float);
             static constexpr size_t offMeta = offOut + (TS ? (size_t)3 * kOutPlaneBytes : 0);
             static constexpr size_t offBars = offMeta + 2 * sizeof(Meta);
-            static constexpr size_t total = offBars + (4 + CB) * sizeof(uint64_t);
+            static constexpr size_t offPub = offBars + (4 + CB) * sizeof(uint64_t);                  // publisher warp: ring[4][2], observed, total
+            static constexpr size_t total = offPub + 16 * sizeof(int);
         };
 
-        template <int NW, int R, int CB, bool TS>
-        __global__ void __launch_bounds__((NW + 1) * 32, 1)
+        template <int NW, int R, int CB, bool TS, bool PUB>
+        __global__ void __launch_bounds__((NW + 1 + (PUB ? 1 : 0)) * 32, 1)
         stepKernel(const Layout L, const Args A, const __grid_constant__ Maps maps)
         {
             using SM = Smem<NW, R, CB, TS>;
@@ -469,6 +493,12 @@ namespace pvc
             uint64_t* empty = full + 1;
             uint64_t* done = full + 2;                                                              // [2], by tile parity
             uint64_t* fullCoef = full + 4;                                                          // [CB]
+            // PUB: a third role, the publisher warp (warp NW + 1).  It owns the "done" barriers: for every tile, in hand-over
+            // order, it observes done(k), bumps pubObserved, executes the cross-proxy fence and releases the tile's generation
+            // counter -- 2-4 us that no longer sit between a drained stage and the producer's next TMA.
+            volatile int* pubRing = reinterpret_cast<volatile int*>(smemRaw + SM::offPub);          // [4][2] = {counter slot, generation}
+            volatile int* pubObserved = pubRing + 8;                                                 // tiles whose done barrier has been consumed
+            volatile int* pubTotal = pubRing + 9;                                                    // tiles handed out in all (-1: still running)
 
             const int lane = threadIdx.x & 31;
             const int wp = threadIdx.x >> 5;
@@ -479,6 +509,7 @@ namespace pvc
             {
                 mbarInit(full, 1); mbarInit(empty, NW); mbarInit(done, TS ? 1 : NW); mbarInit(done + 1, TS ? 1 : NW);
                 for (int b = 0; b < CB; ++b) mbarInit(fullCoef + b, 1);
+                *pubObserved = 0; *pubTotal = -1;
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             if (wp == 0)
@@ -488,9 +519,53 @@ namespace pvc
             }
             __syncthreads();
 
+            if (PUB && wp == NW + 1)
+            {
+                // ================= publisher warp =================
+                uint32_t par0 = 0u, par1 = 0u;
+                for (int k = 0;; ++k)
+                {
+                    int st = 0;                                  // 1: done(k) observed, 2: no tile k (the producer has finished), -1: abort
+                    if (lane == 0)
+                    {
+                        uint64_t* bar = done + (k & 1);
+                        const uint32_t par = (k & 1) ? par1 : par0;
+                        for (unsigned spins = 0; st == 0; ++spins)
+                        {
+                            if (mbarTest(bar, par)) { st = 1; break; }
+                            const int tot = *pubTotal;
+                            if (tot >= 0 && k >= tot) { st = 2; break; }
+                            __nanosleep(20);
+                            if ((spins & 0x3ffu) == 0x3ffu && (spins > (1u << 24) || *(volatile int*)A.abortFlag)) { atomicExch(A.abortFlag, 1); st = -1; }
+                        }
+                    }
+                    st = __shfl_sync(0xffffffffu, st, 0);
+                    if (st != 1) break;
+                    if (k & 1) par1 ^= 1u; else par0 ^= 1u;
+                    if (lane == 0)
+                    {
+                        const int slot = pubRing[(k & 3) * 2], g = pubRing[(k & 3) * 2 + 1];
+                        *pubObserved = k + 1;
+                        asm volatile("fence.proxy.async;" ::: "memory");          // writer-side cross-proxy fence (see fenceMode 2)
+                        storeRelease(A.doneGen + slot, g + 1);
+                    }
+                    __syncwarp();
+                }
+                return;
+            }
             if (wp == NW)
             {
                 // ================= producer warp =================
+                auto waitObserved = [&](int need) -> bool {      // PUB: until the publisher has consumed the done barrier of `need` tiles
+                    int ok = 1;
+                    if (lane == 0)
+                        for (unsigned spins = 0; *pubObserved < need; ++spins)
+                        {
+                            __nanosleep(20);
+                            if ((spins & 0x3ffu) == 0x3ffu && (spins > (1u << 24) || *(volatile int*)A.abortFlag)) { atomicExch(A.abortFlag, 1); ok = 0; break; }
+                        }
+                    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+                };
                 auto depsReady = [&](int s, int tx, int ty, int gen, bool block) -> bool {
                     if (gen == 0) return true;                 // generation 0 reads the zeroed state: written by a memset before the launch
                     const int dx = lane % 3 - 1, dy = lane / 3 - 1;
@@ -514,24 +589,54 @@ namespace pvc
                 // fetched the item after k, and with a single barrier a fast tile k could complete a second phase before the
                 // first one was observed (the parity wait would then never succeed).  Tile k+1, the next user of the same
                 // barrier, is handed out only after done(k-1) has been consumed, so with two barriers no phase can be skipped.
-                uint32_t emptyParity = 0, doneParity[2] = { 0u, 0u };
-                int prevSeq = 0;
+                uint32_t emptyParity = 0, doneParity0 = 0u, doneParity1 = 0u;
                 uint32_t coefPhase = 0;                       // wall tiles handed out so far: buffer = phase % CB, parity = (phase / CB) & 1
                 bool stageBusy = false;                       // a tile has been handed to the compute warps and not yet drained
-                bool prevUsedCoef = false;                    // the tile being computed reads a coefficient buffer
-                int prevSlot = -1, prevGen = 0;               // tile being computed, completion not yet published
                 bool alive = true;
                 int seq = 0;
-                auto publishPrev = [&]() -> bool {            // wait for the compute warps to finish it, then release its counter
-                    if (prevSlot < 0) return true;
-                    bool ok = true;
-                    if (lane == 0) ok = mbarWaitBounded(done + (prevSeq & 1), (prevSeq & 1) ? doneParity[1] : doneParity[0], A.abortFlag);
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (prevSeq & 1) doneParity[1] ^= 1u; else doneParity[0] ^= 1u;
-                    if (ok && lane == 0) storeRelease(A.doneGen + prevSlot, prevGen + 1);
-                    prevSlot = -1;
-                    prevUsedCoef = false;
-                    return ok;
+                // Tiles handed to the compute warps whose completion has not been published yet, oldest first (at most two: the
+                // one being computed and the one before it).  Publishing = (a) observe the tile's "done" mbarrier, (b) release
+                // its generation counter.  (b) waits out the CTA's outstanding stores (1.5-2.5 us), so by default (lateRelease)
+                // it is taken off the hand-over chain: when the compute warps have drained tile n the producer consumes
+                // done(n-1) -- complete by then, the compute warps arrive on it before they touch tile n -- issues the TMA of
+                // tile n+1 at once and only then releases n-1.  (a) always precedes the hand-out of the next user of the same
+                // barrier, so no phase of the two alternating barriers can be skipped.
+                struct Pend { int slot, gen, seq; bool usedCoef, seen; };
+                Pend q0 = { -1, 0, 0, false, false }, q1 = { -1, 0, 0, false, false };
+                int nq = 0;
+                auto observeOldest = [&](bool block) -> int {      // 1: done observed, 0: not yet (non-blocking only), -1: abort
+                    if (q0.seen) return 1;
+                    int r = 0;
+                    if (lane == 0)
+                    {
+                        uint64_t* bar = done + (q0.seq & 1);
+                        const uint32_t par = (q0.seq & 1) ? doneParity1 : doneParity0;
+                        if (block) r = mbarWaitBounded(bar, par, A.abortFlag) ? 1 : -1;
+                        else r = mbarTest(bar, par) ? 1 : 0;
+                    }
+                    r = __shfl_sync(0xffffffffu, r, 0);
+                    if (r == 1) { if (q0.seq & 1) doneParity1 ^= 1u; else doneParity0 ^= 1u; q0.seen = true; }
+                    return r;
+                };
+                auto releaseOldest = [&]() {                       // q0.seen must hold
+                    // fenceMode 2: the generic-proxy -> async-proxy fence of the consumers' TMA reads is executed HERE, on the
+                    // writer side of the causality chain (tile stores -> "done" mbarrier -> this fence -> release -> a
+                    // consumer's acquire -> its TMA), once per tile and back to back with the release, which waits out the same
+                    // outstanding stores; the consumers then issue their TMA straight after the acquire.
+                    if (A.fenceMode == 2) asm volatile("fence.proxy.async;" ::: "memory");
+                    if (lane == 0) storeRelease(A.doneGen + q0.slot, q0.gen + 1);
+                    q0 = q1; q1.slot = -1; q1.seen = false; q1.usedCoef = false;
+                    --nq;
+                };
+                auto publishOldest = [&](bool block) -> int {
+                    if (nq == 0) return 1;
+                    const int r = observeOldest(block);
+                    if (r == 1) releaseOldest();
+                    return r;
+                };
+                auto publishAll = [&]() -> bool {                  // blocking
+                    while (nq > 0) if (publishOldest(true) != 1) return false;
+                    return true;
                 };
                 // Fetching a work item costs two dependent L2 round trips: the counter atomic, then -- all in flight
                 // together -- the record loads and the dependency probe.  By default (earlyFetch = 2) the next item is
@@ -595,9 +700,37 @@ namespace pvc
                     if (!ready && A.earlyFetch) ready = depsReady(s, tx, ty, gen, false);
                     if (PVC_DBG(A) && lane == 0) { atomicAdd(PVC_DBG(A) + 0, 1ull); if (!ready) atomicAdd(PVC_DBG(A) + 1, 1ull); }
                     if (!ready)
-                    {   // it may depend on the tile our own compute warps are working on: publish that first, then wait for real
-                        if (!publishPrev()) { alive = false; break; }
-                        ready = depsReady(s, tx, ty, gen, true);
+                    {
+                        if (A.slowPathPoll)
+                        {
+                            // Poll the dependencies AND our own tiles in flight: a dependency is usually a tile of a lagging CTA
+                            // that completes within a microsecond or two, long before our compute warps finish theirs, so the
+                            // TMA of this item still goes out a good part of a tile ahead.  (Blocking on our own tile first --
+                            // the older path below -- put a whole TMA latency in front of the compute warps on every miss.)
+                            // The item may also depend on our own tiles: publish them as soon as they complete.
+                            unsigned spins = 0;
+                            while (true)
+                            {
+                                ready = depsReady(s, tx, ty, gen, false);
+                                if (ready) break;
+                                if (!PUB)
+                                {
+                                    int r = publishOldest(false);
+                                    if (r == 1 && nq > 0) r = publishOldest(false);
+                                    if (r < 0) break;
+                                }
+                                __nanosleep(64);
+                                ++spins;
+                                bool giveUp = false;
+                                if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)A.abortFlag;
+                                if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(A.abortFlag, 1); break; }
+                            }
+                        }
+                        else
+                        {   // it may depend on the tiles our own compute warps are working on: publish them first, then wait for real
+                            if (!PUB && !publishAll()) { alive = false; break; }
+                            ready = depsReady(s, tx, ty, gen, true);
+                        }
                         if (!ready) { alive = false; break; }
                     }
                     if (stageBusy)
@@ -609,8 +742,22 @@ namespace pvc
                         if (!ok) { alive = false; break; }
                     }
                     if (lane == 0) trace(PVC_DBG(A), seq, 7);
-                    // single coefficient buffer: the tile being computed may still be reading it
-                    if (CB == 1 && anySlow && prevUsedCoef) { if (!publishPrev()) { alive = false; break; } }
+                    // the stage is drained: the compute warps work on the newest pending tile and have arrived on the "done"
+                    // barrier of the one before it.  Observe that one now -- this item is the next user of its barrier.
+                    if (PUB)
+                    {
+                        // this item is the next user of done[seq & 1]: the publisher must have consumed tile seq-2's phase (it has,
+                        // within nanoseconds of the compute warps' arrival, unless it is still busy with an older release).
+                        // Single coefficient buffer: the tile in compute (seq-1) must be finished if both use it.
+                        const bool coefClash = CB == 1 && anySlow && q0.usedCoef;
+                        if (!waitObserved(coefClash ? seq : seq - 1)) { alive = false; break; }
+                    }
+                    else
+                    {
+                        if (nq == 2 && observeOldest(true) != 1) { alive = false; break; }
+                        // single coefficient buffer: the tile being computed may still be reading it
+                        if (CB == 1 && anySlow && ((nq == 2) ? q1.usedCoef : (nq == 1 && q0.usedCoef))) { if (!publishAll()) { alive = false; break; } }
+                    }
 
                     Meta* m = meta + (seq & 1);
                     const int coefBuf = anySlow ? (int)(coefPhase % CB) : -1;
@@ -620,11 +767,12 @@ namespace pvc
                     else if (lane == 1) m->srcC = it.misc;
                     else if (lane >= 4 && lane < 8) m->pulse[lane - 4] = __int_as_float(it.misc);
                     else if (lane == 8) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
+                    else if (PUB && lane == 9) { pubRing[(seq & 3) * 2] = s * tps + id; pubRing[(seq & 3) * 2 + 1] = gen; }
                     __syncwarp();
                     // order the dependency acquires before the async-proxy (TMA) reads of the neighbours' cells.  The fence waits
                     // out the CTA's outstanding stores (~1-2 us measured), so on the fast path it has already been executed a
                     // tile ahead (after the early probe AND after the previous tile was published, see below)
-                    if (!fenced) asm volatile("fence.proxy.async;" ::: "memory");
+                    if (!PUB && !fenced && A.fenceMode != 2) asm volatile("fence.proxy.async;" ::: "memory");
                     if (lane == 0)
                     {
                         if (anySlow)
@@ -647,16 +795,27 @@ namespace pvc
                     if (anySlow) ++coefPhase;
                     ++seq;
                     stageBusy = true;
+                    // the tile before the one in compute has been observed above: release it now, after the TMA has gone out
+                    if (PUB) q0.usedCoef = anySlow;               // only "the tile in compute reads the coefficient buffer" is tracked
+                    else
+                    {
+                        if (nq == 2) releaseOldest();
+                        const Pend me = { s * tps + id, gen, seq - 1, anySlow, false };
+                        if (nq == 0) q0 = me; else q1 = me;
+                        ++nq;
+                    }
                     if (A.earlyFetch) fetchNext();                // the next item's fetch overlaps the tile in flight
-                    // the tile handed over before this one is (or was) being computed: publish it once the compute warps are done
                     if (lane == 0) trace(PVC_DBG(A), seq - 1, 1);
-                    if (!publishPrev()) { alive = false; break; }
-                    if (A.earlyFetch && nx.valid && nx.ready) { asm volatile("fence.proxy.async;" ::: "memory"); nx.fenced = true; }
+                    // fenceMode 1: the proxy fence right after the early probe, before waiting for the tile in compute
+                    if (!PUB && A.fenceMode == 1 && A.earlyFetch && nx.valid && nx.ready) { asm volatile("fence.proxy.async;" ::: "memory"); nx.fenced = true; }
+                    // older order (PVC_LATE_RELEASE=0): the tile handed over before this one is published here, blocking
+                    if (!PUB && !A.lateRelease && nq == 2 && publishOldest(true) != 1) { alive = false; break; }
+                    if (!PUB && A.fenceMode == 0 && A.earlyFetch && nx.valid && nx.ready) { asm volatile("fence.proxy.async;" ::: "memory"); nx.fenced = true; }
                     if (lane == 0) trace(PVC_DBG(A), seq - 1, 2);
-                    prevSlot = s * tps + id; prevGen = gen; prevUsedCoef = anySlow; prevSeq = seq - 1;
                 }
                 // drain: publish the last tile, then tell the compute warps to stop
-                if (alive) alive = publishPrev();
+                if (PUB) { if (lane == 0) *pubTotal = seq; }
+                else if (alive) alive = publishAll();
                 if (stageBusy && alive)
                 {
                     bool ok = true;
@@ -942,7 +1101,7 @@ namespace pvc
             return PVC_OK;
         }
 
-        template <int NW, int R, int CB, bool TS = false>
+        template <int NW, int R, int CB, bool TS = false, bool PUB = false>
         static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
         {
             using SM = Smem<NW, R, CB, TS>;
@@ -955,7 +1114,7 @@ namespace pvc
             static bool configured[64] = {};
             if (!configured[s->device & 63])
             {
-                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB, TS, PUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) { setError("ws2 step kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
                 configured[s->device & 63] = true;
             }
@@ -991,6 +1150,9 @@ namespace pvc
                 A.srcGroup = (nsrc + groups - 1) / groups;
                 A.genChunk = 16;
                 { static const char* ef = getenv("PVC_EARLY_FETCH"); A.earlyFetch = ef ? atoi(ef) : 2; }
+                { static const char* sp = getenv("PVC_SLOW_POLL"); A.slowPathPoll = sp ? atoi(sp) : 1; }
+                { static const char* lr = getenv("PVC_LATE_RELEASE"); A.lateRelease = lr ? atoi(lr) : 0; }
+                { static const char* fm = getenv("PVC_FENCE_MODE"); A.fenceMode = fm ? atoi(fm) : 0; }
                 A.debug = nullptr;
                 { static const char* td = getenv("PVC_TS_DEBUG"); A.tsDebug = td ? atoi(td) : 0; }
                 {
@@ -1053,7 +1215,7 @@ namespace pvc
             {
                 A.gen0 = g0; A.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
                 A.workCounter = s->tileCounters + k;
-                stepKernel<NW, R, CB, TS><<<grid, (NW + 1) * 32, smem, s->stream>>>(L, A, maps);
+                stepKernel<NW, R, CB, TS, PUB><<<grid, (NW + 1 + (PUB ? 1 : 0)) * 32, smem, s->stream>>>(L, A, maps);
                 *launches += 1;
             }
             s->cur = gens & 1;
@@ -1087,6 +1249,8 @@ namespace pvc
             case 44: return ws2::launch<10, 8, 1>(s, nsrc, t0, t1, hist, launches);
             case 45: return ws2::launch<11, 6, 1>(s, nsrc, t0, t1, hist, launches);
             case 46: return ws2::launch<12, 6, 1>(s, nsrc, t0, t1, hist, launches);
+            case 47: return ws2::launch<14, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 48: return ws2::launch<15, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -1102,6 +1266,8 @@ namespace pvc
             case 44: return ws2::buildMask<10, 8>(s);
             case 45: return ws2::buildMask<11, 6>(s);
             case 46: return ws2::buildMask<12, 6>(s);
+            case 47: return ws2::buildMask<14, 4>(s);
+            case 48: return ws2::buildMask<15, 4>(s);
             default: return PVC_OK;
         }
     }

@@ -312,7 +312,8 @@ def main():
         # generations one launch of this run covers
         gens_per_launch = ((scene.T + 3) // 4) * args.steps / step_launches
         traffic = per_gen * gens_per_launch * (S / 4.0) if (os.path.exists(traffic_path) and per_gen and args.variant == 0 and args.step_kernel == 0) else None
-        kernel_name = {0: "pvc::ws2::stepKernel<15,4,1> (default: warp-specialised generational kernel, up to 256 x 4 time steps per launch)",
+        kernel_name = {0: "pvc::ws2::stepKernel<14,4,1,false,true> (default: warp-specialised generational kernel with producer + publisher warps, up to 256 x 4 time steps per launch)",
+                       40: "pvc::ws2::stepKernel<15,4,1,false,false> (ws2 without the publisher warp)",
                        36: "pvc::fusedStepWsKernel<15,4,true> (first warp-specialised generational kernel)",
                        18: "pvc::fusedStepKernel<8,6,2> (one launch per 4 time steps)"}.get(args.variant, f"fused step kernel variant {args.variant}")
         if args.step_kernel == 1:

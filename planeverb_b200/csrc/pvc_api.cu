@@ -50,10 +50,10 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto: the second warp-specialised generational kernel (pvc_step_ws2.cu, variant 40: 15 compute warps x
-    // 4 rows + a producer warp that prefetches every per-tile input with TMA / into a shared-memory record, source-group
-    // item order that keeps a group's state L2-resident) -- fastest at every batch/grid size measured on B200
-    // (profiles/).  It needs cuTensorMapEncodeTiled from the driver; without it fall back to the plain 8 x 6 kernel.
+    // variant 0 = auto: the second warp-specialised generational kernel (pvc_step_ws2.cu, variant 47: 14 compute warps x
+    // 4 rows + a producer warp that prefetches every per-tile input with TMA / into a shared-memory record + a publisher
+    // warp that releases finished tiles, source-group item order that keeps a group's state L2-resident) -- fastest at
+    // every batch/grid size measured on B200 (profiles/).  It needs cuTensorMapEncodeTiled from the driver; without it fall back to the plain 8 x 6 kernel.
     static int resolveVariant(const pvc_config& c)
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
@@ -61,7 +61,7 @@ namespace pvc
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
-        return tma ? 40 : 18;
+        return tma ? 47 : 18;
     }
 
     static bool validConfig(const pvc_config* c)

@@ -127,7 +127,7 @@ namespace pvc
         // edges away from a slow (wall-path) warp may run k sub-steps ahead of it, finish their pass early and issue their
         // state stores / drain the next stage while the slow warps still compute.
     #ifndef PVC_PAIR_SYNC
-        #define PVC_PAIR_SYNC 0
+        #define PVC_PAIR_SYNC 1
     #endif
         __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
         template <int NW, bool TS>

@@ -69,7 +69,7 @@ with open(os.path.join(OUT, f"{tag}_ncu_kernels.txt"), "w") as f:
                 traffic = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
 print(open(os.path.join(OUT, f"{tag}_ncu_kernels.txt")).read()[:3000])
 if traffic:
-    json.dump({"kernel": "pvc::ws2::stepKernel<15,4,1>", "dram_bytes_per_launch": traffic, "generations_in_that_launch": 100,
+    json.dump({"kernel": "pvc::ws2::stepKernel<14,4,1,false,true>", "dram_bytes_per_launch": traffic, "generations_in_that_launch": 100,
                "dram_bytes_per_generation": traffic / 100.0, "source": f"profiles/{tag}_ncu_kernels.txt (ncu --set full, cold L2)",
                "note": "captured with --T 400: ONE launch = 100 generations x 4 steps, 4 sources, 1024x1024", "algorithmic_bytes_per_launch": 28 * 1024 * 1024 * 4 * 400}, open(os.path.join(OUT, "fused_step_traffic.json"), "w"), indent=1)
 for name in ("bench_default.json", "timeline.txt"):

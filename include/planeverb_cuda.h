@@ -134,6 +134,14 @@ PVC_API int  pvc_fetch_results_async(pvc_solver* s, int n, float* results, float
 PVC_API int  pvc_fetch_wait(pvc_solver* s);
 /* the 8 floats of one interior cell (Analyzer::GetResponseResult, Analyzer.cpp:106-116) */
 PVC_API int  pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8);
+/* Frame-loop form of pvc_fetch_result_at: enqueue on the solver's stream -- after the last pvc_run, before the next -- the
+ * copy of the 8 floats of n_cells interior cells (cells[i] = r * gy + c) of sources 0..n-1 into out (n * n_cells * 8
+ * floats, source-major; pvc_host_alloc'd memory; a negative cell index leaves its 8 floats untouched) and return at once
+ * with a ticket (0 or 1).  pvc_gather_wait blocks until
+ * that copy has landed.  Two gathers may be in flight, so frame k's emitter outputs can be consumed (and exchanged between
+ * GPUs) while frame k+1 is being solved. */
+PVC_API int  pvc_gather_results_async(pvc_solver* s, int n, const int* cells, int n_cells, float* out, int* ticket);
+PVC_API int  pvc_gather_wait(pvc_solver* s, int ticket);
 /* impulse response of alloc cell (r,c): T x {p, vx, vy} (Grid::GetResponse). vx/vy are rebuilt on the
  * device from the pressure history with the solver's own update rules. */
 PVC_API int  pvc_fetch_ir(pvc_solver* s, int source, int r, int c, float* out3T);

@@ -54,6 +54,12 @@ PVC_API int  pvx_wait(pvx_scene* sc);
  * overlaps the next solve.  pvx_fetch_wait returns when the buffers of the last pvx_solve_pipelined are filled. */
 PVC_API int  pvx_solve_pipelined(pvx_scene* sc, const float* listenersXYZ, int n, float* results, float* delay);
 PVC_API int  pvx_fetch_wait(pvx_scene* sc);
+/* frame-loop form of pvx_lookup: the outputs of n_emitters world-space emitter positions (x, y, z triples) for sources
+ * 0..n-1 of the last solve, copied into out (n * n_emitters * 8 floats, pvc_host_alloc'd) in stream order, without waiting.
+ * An emitter outside the grid yields eight -1 (Analyzer::GetResponseResult returns nullptr there and FDTD.cpp:33-44 reports
+ * occlusion -1).  pvx_lookup_wait(ticket) blocks until the copy has landed. */
+PVC_API int  pvx_lookup_async(pvx_scene* sc, int n, const float* emittersXYZ, int n_emitters, float* out, int* ticket);
+PVC_API int  pvx_lookup_wait(pvx_scene* sc, int ticket);
 
 /* Analyzer::GetResponseResult for a world-space emitter position: 0 = ok and out8 filled,
  * PVC_ERR_INVALID when the reference would return nullptr (outside the grid) */

@@ -331,6 +331,7 @@ void pvc_destroy(pvc_solver* s)
     if (s->evCopied) cudaEventDestroy(s->evCopied);
     if (s->hostAbort) cudaFreeHost(s->hostAbort);
     if (s->srcHost) cudaFreeHost(s->srcHost);
+    for (int i = 0; i < 2; ++i) if (s->gathered[i]) cudaEventDestroy(s->gathered[i]);
     if (s->rectsHost) cudaFreeHost(s->rectsHost);
     for (int i = 0; i < 2; ++i) if (s->rectCopied[i]) cudaEventDestroy(s->rectCopied[i]);
     for (int i = 0; i < 4; ++i) if (s->srcCopied[i]) cudaEventDestroy(s->srcCopied[i]);
@@ -555,6 +556,35 @@ int pvc_fetch_result_at(pvc_solver* s, int source, int r, int c, float* out8)
     const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
     PVC_CUDA(cudaMemcpyAsync(out8, s->results + ((size_t)source * cells + (size_t)r * s->cfg.gy + c) * 8, sizeof(float) * 8, cudaMemcpyDeviceToHost, s->stream));
     PVC_CUDA(cudaStreamSynchronize(s->stream));
+    return PVC_OK;
+}
+
+int pvc_gather_results_async(pvc_solver* s, int n, const int* cells, int n_cells, float* out, int* ticket)
+{
+    if (!s || !cells || !out || !ticket || n < 1 || n > s->cfg.max_sources || n_cells < 0)
+    { setError("pvc_gather_results_async: bad argument"); return PVC_ERR_INVALID; }
+    PVC_CUDA(cudaSetDevice(s->device));
+    const size_t total = (size_t)s->cfg.gx * s->cfg.gy;
+    for (int i = 0; i < n_cells; ++i)
+        if (cells[i] >= 0 && (size_t)cells[i] >= total) { setError("pvc_gather_results_async: cell %d outside the lattice", cells[i]); return PVC_ERR_INVALID; }
+    const unsigned slot = s->gatherSlot++ & 1u;
+    if (!s->gathered[slot]) PVC_CUDA(cudaEventCreateWithFlags(&s->gathered[slot], cudaEventDisableTiming));
+    for (int src = 0; src < n; ++src)
+        for (int i = 0; i < n_cells; ++i)
+            if (cells[i] >= 0)
+            PVC_CUDA(cudaMemcpyAsync(out + ((size_t)src * n_cells + i) * 8, s->results + ((size_t)src * total + (size_t)cells[i]) * 8,
+                                     sizeof(float) * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVC_CUDA(cudaEventRecord(s->gathered[slot], s->stream));
+    *ticket = (int)slot;
+    return PVC_OK;
+}
+
+int pvc_gather_wait(pvc_solver* s, int ticket)
+{
+    if (!s || ticket < 0 || ticket > 1) { setError("pvc_gather_wait: bad argument"); return PVC_ERR_INVALID; }
+    if (!s->gathered[ticket]) return PVC_OK;
+    PVC_CUDA(cudaSetDevice(s->device));
+    PVC_CUDA(cudaEventSynchronize(s->gathered[ticket]));
     return PVC_OK;
 }
 

@@ -126,6 +126,8 @@ struct pvc_solver
     cudaEvent_t rectCopied[2];
     unsigned rectSlot;
     pvc::SourceParams* src;  // max_sources
+    cudaEvent_t gathered[2];        // pvc_gather_results_async tickets
+    unsigned gatherSlot;
     pvc::SourceParams* srcHost;     // pinned ring of kSrcRing x max_sources staging slots: pvc_run never waits for the stream
     cudaEvent_t srcCopied[4];
     unsigned srcSlot;

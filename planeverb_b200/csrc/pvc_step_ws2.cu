@@ -455,7 +455,7 @@ namespace pvc
             }
         }
 
-        template <int NW, int R, int CB, bool TS = false>
+        template <int NW, int R, int CB, bool TS = false, bool SO = false>
         struct Smem
         {
             static constexpr int TR = NW * R;
@@ -468,17 +468,23 @@ namespace pvc
             static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
             static constexpr size_t offOut = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);      // [3][(NW - 2) * R][120] (TS only)
             static constexpr uint32_t kOutPlaneBytes = (NW - 2) * R * kValidCols * sizeof(float);
-            static constexpr size_t offMeta = offOut + (TS ? (size_t)3 * kOutPlaneBytes : 0);
+            static constexpr size_t offMeta = offOut + ((TS || SO) ? (size_t)3 * kOutPlaneBytes : 0);
             static constexpr size_t offBars = offMeta + 2 * sizeof(Meta);
-            static constexpr size_t offPub = offBars + (4 + CB) * sizeof(uint64_t);                  // publisher warp: ring[4][2], observed, total
-            static constexpr size_t total = offPub + 16 * sizeof(int);
+            static constexpr size_t offPub = offBars + (5 + CB) * sizeof(uint64_t);                  // publisher warp: ring[4][4], observed, total
+            static constexpr size_t total = offPub + 24 * sizeof(int);
         };
 
-        template <int NW, int R, int CB, bool TS, bool PUB>
+        // SO ("state out", needs PUB): the new state of a tile leaves through three [owned rows][120] staging planes in shared
+        // memory and three TMA tensor stores issued by the PUBLISHER warp, instead of 12 STG.128 per compute thread.  The
+        // LSU path from an SM into the crossbar carries 32 B/clk (ncu: l1tex__m_l1tex2xbar_write_bytes peak); at that rate
+        // the 69-86 KB of state per tile took 1.0-1.4 us per 6 us tile with the FP pipes idle, and competed with the
+        // history stores inside the step loop.  The compute warps now spend ~0.3 us on STS and go on to the next tile.
+        template <int NW, int R, int CB, bool TS, bool PUB, bool SO>
         __global__ void __launch_bounds__((NW + 1 + (PUB ? 1 : 0)) * 32, 1)
         stepKernel(const Layout L, const Args A, const __grid_constant__ Maps maps)
         {
-            using SM = Smem<NW, R, CB, TS>;
+            using SM = Smem<NW, R, CB, TS, SO>;
+            static_assert(!SO || (PUB && !TS && R == kTileK), "state-out needs the publisher warp; halo rows = first and last warp");
             static_assert(!TS || R == kTileK, "TMA-store variants: the halo rows must be exactly the first and the last warp");
             constexpr int TR = SM::TR;
             static_assert(NW <= 31 && R * 4 <= 32, "Meta holds 32 warps; bpMask holds 32 cells per thread");
@@ -493,12 +499,13 @@ namespace pvc
             uint64_t* empty = full + 1;
             uint64_t* done = full + 2;                                                              // [2], by tile parity
             uint64_t* fullCoef = full + 4;                                                          // [CB]
+            uint64_t* outFree = full + 4 + CB;                                                      // SO: the staging planes have been read by the TMA stores
             // PUB: a third role, the publisher warp (warp NW + 1).  It owns the "done" barriers: for every tile, in hand-over
             // order, it observes done(k), bumps pubObserved, executes the cross-proxy fence and releases the tile's generation
             // counter -- 2-4 us that no longer sit between a drained stage and the producer's next TMA.
-            volatile int* pubRing = reinterpret_cast<volatile int*>(smemRaw + SM::offPub);          // [4][2] = {counter slot, generation}
-            volatile int* pubObserved = pubRing + 8;                                                 // tiles whose done barrier has been consumed
-            volatile int* pubTotal = pubRing + 9;                                                    // tiles handed out in all (-1: still running)
+            volatile int* pubRing = reinterpret_cast<volatile int*>(smemRaw + SM::offPub);          // [4][4] = {counter slot, generation, source, tile}
+            volatile int* pubObserved = pubRing + 16;                                                // tiles whose done barrier has been consumed
+            volatile int* pubTotal = pubRing + 17;                                                   // tiles handed out in all (-1: still running)
 
             const int lane = threadIdx.x & 31;
             const int wp = threadIdx.x >> 5;
@@ -509,6 +516,7 @@ namespace pvc
             {
                 mbarInit(full, 1); mbarInit(empty, NW); mbarInit(done, TS ? 1 : NW); mbarInit(done + 1, TS ? 1 : NW);
                 for (int b = 0; b < CB; ++b) mbarInit(fullCoef + b, 1);
+                mbarInit(outFree, 1);
                 *pubObserved = 0; *pubTotal = -1;
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
@@ -544,9 +552,26 @@ namespace pvc
                     if (k & 1) par1 ^= 1u; else par0 ^= 1u;
                     if (lane == 0)
                     {
-                        const int slot = pubRing[(k & 3) * 2], g = pubRing[(k & 3) * 2 + 1];
+                        const int slot = pubRing[(k & 3) * 4], g = pubRing[(k & 3) * 4 + 1];
                         *pubObserved = k + 1;
-                        asm volatile("fence.proxy.async;" ::: "memory");          // writer-side cross-proxy fence (see fenceMode 2)
+                        if (SO)
+                        {
+                            // "done" here means "staged": every compute warp has written its rows of the new state into the
+                            // staging planes and executed the generic->async proxy fence.  Generation g writes buffer (g + 1) & 1.
+                            const int s = pubRing[(k & 3) * 4 + 2], id = pubRing[(k & 3) * 4 + 3];
+                            const int ty = id / L.tiles_x, tx = id - ty * L.tiles_x;
+                            const float* planes = reinterpret_cast<const float*>(smemRaw + SM::offOut);
+                            constexpr int kPlane = (NW - 2) * R * kValidCols;
+                            const CUtensorMap* m = &maps.store[(g & 1) ? 0 : 3];
+                            tmaStore3d(m + 0, planes, tx * kValidCols + kGuardCols, ty * L.valid_rows + kGuardRows, s);
+                            tmaStore3d(m + 1, planes + kPlane, tx * kValidCols + kGuardCols, ty * L.valid_rows + kGuardRows, s);
+                            tmaStore3d(m + 2, planes + 2 * kPlane, tx * kValidCols + kGuardCols, ty * L.valid_rows + kGuardRows, s);
+                            bulkCommit();
+                            bulkWaitRead<0>();
+                            mbarArrive(outFree);                                  // the compute warps may stage the next tile
+                            bulkWait<0>();                                        // writes complete: the release below publishes them
+                        }
+                        else asm volatile("fence.proxy.async;" ::: "memory");    // writer-side cross-proxy fence (see fenceMode 2)
                         storeRelease(A.doneGen + slot, g + 1);
                     }
                     __syncwarp();
@@ -767,7 +792,7 @@ namespace pvc
                     else if (lane == 1) m->srcC = it.misc;
                     else if (lane >= 4 && lane < 8) m->pulse[lane - 4] = __int_as_float(it.misc);
                     else if (lane == 8) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
-                    else if (PUB && lane == 9) { pubRing[(seq & 3) * 2] = s * tps + id; pubRing[(seq & 3) * 2 + 1] = gen; }
+                    else if (PUB && lane == 9) { pubRing[(seq & 3) * 4] = s * tps + id; pubRing[(seq & 3) * 4 + 1] = gen; pubRing[(seq & 3) * 4 + 2] = s; pubRing[(seq & 3) * 4 + 3] = id; }
                     __syncwarp();
                     // order the dependency acquires before the async-proxy (TMA) reads of the neighbours' cells.  The fence waits
                     // out the CTA's outstanding stores (~1-2 us measured), so on the fast path it has already been executed a
@@ -969,6 +994,24 @@ namespace pvc
                         }
                     }
                 }
+                else if (SO)
+                {
+                    // the TMA stores of the previous tile must have read the planes (they have, a whole tile ago)
+                    if (seq > 1) { bool ok = mbarWaitBounded(outFree, (uint32_t)(seq & 1), A.abortFlag); (void)ok; }
+                    if (wp >= 1 && wp <= NW - 2 && lane >= 1 && lane <= 30)
+                    {
+                        constexpr int kPlane = (NW - 2) * R * kValidCols;
+                        float* o = outBuf + ((wp - 1) * R) * kValidCols + (lane - 1) * 4;
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                        {
+                            *reinterpret_cast<float4*>(o + j * kValidCols) = make_float4(p[j][0], p[j][1], p[j][2], p[j][3]);
+                            *reinterpret_cast<float4*>(o + kPlane + j * kValidCols) = make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]);
+                            *reinterpret_cast<float4*>(o + 2 * kPlane + j * kValidCols) = make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]);
+                        }
+                    }
+                    fenceAsyncShared();          // generic-proxy writes above -> async-proxy reads of the publisher's TMA stores
+                }
                 else
                 {
                     float* gp = ((gen & 1) ? A.p0 : A.p1) + src0;
@@ -1101,10 +1144,10 @@ namespace pvc
             return PVC_OK;
         }
 
-        template <int NW, int R, int CB, bool TS = false, bool PUB = false>
+        template <int NW, int R, int CB, bool TS = false, bool PUB = false, bool SO = false>
         static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
         {
-            using SM = Smem<NW, R, CB, TS>;
+            using SM = Smem<NW, R, CB, TS, SO>;
             const Layout& L = s->L;
             if (!s->tmaReady || s->tmaTileRows != NW * R) { setError("ws2 step kernel: tensor maps not built for %d-row tiles", NW * R); return PVC_ERR_INVALID; }
             if (t0 != 0 || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
@@ -1114,7 +1157,7 @@ namespace pvc
             static bool configured[64] = {};
             if (!configured[s->device & 63])
             {
-                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB, TS, PUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = cudaFuncSetAttribute(stepKernel<NW, R, CB, TS, PUB, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) { setError("ws2 step kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
                 configured[s->device & 63] = true;
             }
@@ -1134,7 +1177,7 @@ namespace pvc
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
             A.hist = hist;
             { static const char* dbg = getenv("PVC_DEBUG_NOHIST"); if (dbg) A.hist = nullptr; }      // debug: memory-floor probe (results invalid)
-            if (TS) { rc = buildStoreMaps(s, A.hist, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
+            if (TS || SO) { rc = buildStoreMaps(s, TS ? A.hist : nullptr, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
             A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder; A.firstActive = s->firstActive;
             A.src = s->src; A.pulse = s->pulse;
             A.doneGen = s->doneGen; A.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
@@ -1215,7 +1258,7 @@ namespace pvc
             {
                 A.gen0 = g0; A.numGen = (gens - g0 < perLaunch) ? (gens - g0) : perLaunch;
                 A.workCounter = s->tileCounters + k;
-                stepKernel<NW, R, CB, TS, PUB><<<grid, (NW + 1 + (PUB ? 1 : 0)) * 32, smem, s->stream>>>(L, A, maps);
+                stepKernel<NW, R, CB, TS, PUB, SO><<<grid, (NW + 1 + (PUB ? 1 : 0)) * 32, smem, s->stream>>>(L, A, maps);
                 *launches += 1;
             }
             s->cur = gens & 1;
@@ -1251,6 +1294,7 @@ namespace pvc
             case 46: return ws2::launch<12, 6, 1>(s, nsrc, t0, t1, hist, launches);
             case 47: return ws2::launch<14, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 48: return ws2::launch<15, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 49: return ws2::launch<14, 4, 1, false, true, true>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -1268,6 +1312,7 @@ namespace pvc
             case 46: return ws2::buildMask<12, 6>(s);
             case 47: return ws2::buildMask<14, 4>(s);
             case 48: return ws2::buildMask<15, 4>(s);
+            case 49: return ws2::buildMask<14, 4>(s);
             default: return PVC_OK;
         }
     }

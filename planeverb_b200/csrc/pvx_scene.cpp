@@ -168,6 +168,27 @@ int pvx_lookup(pvx_scene* sc, int source, float x, float y, float z, float* out8
     return pvc_fetch_result_at(sc->solver, source, r, c, out8);
 }
 
+int pvx_lookup_async(pvx_scene* sc, int n, const float* emittersXYZ, int n_emitters, float* out, int* ticket)
+{
+    if (!sc || !emittersXYZ || !out || !ticket || n < 1 || n > sc->maxSources || n_emitters < 0) return PVC_ERR_INVALID;
+    std::vector<int> cells((size_t)n_emitters, -1);
+    for (int e = 0; e < n_emitters; ++e)
+    {
+        int r, c;
+        if (pvhost::emitterCell(sc->params, emittersXYZ[3 * e], emittersXYZ[3 * e + 2], r, c)) cells[(size_t)e] = r * sc->params.gy + c;
+        else
+            for (int src = 0; src < n; ++src)
+                for (int k = 0; k < 8; ++k) out[((size_t)src * n_emitters + e) * 8 + k] = -1.f;
+    }
+    return pvc_gather_results_async(sc->solver, n, cells.data(), n_emitters, out, ticket);
+}
+
+int pvx_lookup_wait(pvx_scene* sc, int ticket)
+{
+    if (!sc) return PVC_ERR_INVALID;
+    return pvc_gather_wait(sc->solver, ticket);
+}
+
 int pvx_impulse_response(pvx_scene* sc, int source, float x, float y, float z, float* out3T)
 {
     (void)y;

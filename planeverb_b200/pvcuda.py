@@ -25,13 +25,13 @@ PVC_SYMBOLS = [
     "pvc_device_count", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
-    "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
+    "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_gather_results_async", "pvc_gather_wait", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
     "pvc_last_timing", "pvc_last_launch_counts", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
     "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline",
 ]
 PVX_SYMBOLS = [
     "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
-    "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup",
+    "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup", "pvx_lookup_async", "pvx_lookup_wait",
     "pvx_impulse_response", "pvx_solver",
     "pvx_derive", "pvx_derive_pulse", "pvx_derive_rect", "pvx_derive_listener", "pvx_derive_emitter_cell",
 ]
@@ -101,6 +101,10 @@ def lib():
         L.pvc_fetch_results_async.argtypes = [_vp, _i, _vp, _vp]
         L.pvc_fetch_wait.argtypes = [_vp]
         L.pvx_lookup.argtypes = [_vp, _i, _f, _f, _f, _vp]
+        L.pvx_lookup_async.argtypes = [_vp, _i, _vp, _i, _vp, _vp]
+        L.pvx_lookup_wait.argtypes = [_vp, _i]
+        L.pvc_gather_results_async.argtypes = [_vp, _i, _vp, _i, _vp, _vp]
+        L.pvc_gather_wait.argtypes = [_vp, _i]
         L.pvx_impulse_response.argtypes = [_vp, _i, _f, _f, _f, _vp]
         L.pvx_solver.argtypes = [_vp]
         L.pvc_fetch_results.argtypes = [_vp, _i, _vp, _vp]
@@ -303,6 +307,20 @@ class Scene:
             return None
         _check(rc, "pvx_lookup")
         return out
+
+    def lookup_async(self, emitters, out, n=None):
+        """Frame-loop form of lookup(): enqueue, in stream order after the last solve, the copy of the outputs of the emitter
+        positions [(x, y, z), ...] for sources 0..n-1 into out (pinned_array of shape (n, len(emitters), 8)); returns a ticket
+        for lookup_wait().  Emitters outside the grid read as eight -1."""
+        n = int(n if n is not None else out.shape[0])
+        e = np.ascontiguousarray(np.asarray(emitters, np.float32).reshape(-1, 3))
+        assert out.shape == (n, e.shape[0], 8) and out.dtype == np.float32
+        t = C.c_int(0)
+        _check(lib().pvx_lookup_async(self._h, n, _p(e), int(e.shape[0]), _p(out), C.byref(t)), "pvx_lookup_async")
+        return int(t.value)
+
+    def lookup_wait(self, ticket):
+        _check(lib().pvx_lookup_wait(self._h, int(ticket)), "pvx_lookup_wait")
 
     def impulse_response(self, pos, source=0):
         out = np.zeros((self.T, 3), np.float32)

@@ -23,25 +23,34 @@ def shard(items, world, rank):
     return list(items[lo:hi])
 
 
-def gather_outputs(local, dist=None, device=None):
+def gather_outputs(local, dist=None, device=None, n_total=None):
     """All-gather per-source outputs.  local: float32 array [n_local_sources, n_emitters, 8].
-    Returns the list of every rank's array, in rank order (shards may differ in length)."""
+    Returns the list of every rank's array, in rank order (shards may differ in length).
+    n_total = length of the sharded source list: the shard sizes then follow from shard_bounds and ONE collective is
+    issued (the frame loop's case); without it the sizes are exchanged first."""
     local = np.ascontiguousarray(local, np.float32)
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return [local]
     import torch
     world = dist.get_world_size()
     dev = device if device is not None else torch.device("cpu")
-    count = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(count) for _ in range(world)]
-    dist.all_gather(counts, count)
-    most = max(int(c.item()) for c in counts)
+    if n_total is not None:
+        sizes = [hi - lo for lo, hi in (shard_bounds(n_total, world, r) for r in range(world))]
+        if sizes[dist.get_rank()] != local.shape[0]:
+            raise ValueError(f"rank {dist.get_rank()} holds {local.shape[0]} sources, its shard of {n_total} has {sizes[dist.get_rank()]}")
+    else:
+        count = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(count) for _ in range(world)]
+        dist.all_gather(counts, count)
+        sizes = [int(c) for c in torch.cat(counts).cpu().tolist()]
+    most = max(sizes)
     padded = np.zeros((most,) + local.shape[1:], np.float32)
     padded[:local.shape[0]] = local
     mine = torch.from_numpy(padded).to(dev)
-    everyone = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(everyone, mine)
-    return [t.cpu().numpy()[:int(c.item())] for t, c in zip(everyone, counts)]
+    everyone = torch.empty((world * most,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=dev)      # rank-major concatenation
+    dist.all_gather_into_tensor(everyone, mine)
+    host = everyone.cpu().numpy().reshape((world, most) + tuple(mine.shape[1:]))
+    return [host[r, :sizes[r]] for r in range(world)]
 
 
 def max_over_ranks(values, dist=None, device=None):

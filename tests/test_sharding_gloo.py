@@ -51,6 +51,9 @@ def _worker(rank, world, port, listeners, q):
     mine = sharding.shard(listeners, world, rank)
     local = _solve_with_oracle(mine)
     gathered = sharding.gather_outputs(local, dist)
+    # the frame loop's form: shard sizes derived from the list length, one collective
+    known = sharding.gather_outputs(local, dist, n_total=len(listeners))
+    assert [g.shape for g in known] == [g.shape for g in gathered] and all(np.array_equal(a, b) for a, b in zip(known, gathered))
     times = sharding.max_over_ranks([float(rank + 1), 0.5], dist)
     dist.barrier()
     q.put((rank, [g.copy() for g in gathered], times))

@@ -10,9 +10,9 @@
 //   C ABI                           ProjectPlaneverb/PlaneverbUnityPluginAPI/PlaneverbUnity.cpp:12-135
 // The solve itself (GenerateResponse + AnalyzeResponses) is the device path of pvx_scene.cpp; there is
 // no CPU solver here.  Differences from the reference, all deliberate:
-//   * results are published through a double-buffered host grid swapped atomically after every frame,
-//     so GetOutput on the game/audio thread never reads a half-written frame (the reference races by
-//     design);
+//   * results are published through page-locked host grids swapped atomically after every frame (three of them:
+//     the loop runs one frame deep, a frame's grid is copied out while the next frame is solved), so GetOutput on
+//     the game/audio thread never reads a half-written frame (the reference races by design);
 //   * the listener position and running flag are atomics / mutex-protected;
 //   * errors thrown inside the C ABI are caught there (the reference lets enums escape extern "C").
 #include <atomic>
@@ -51,8 +51,10 @@ namespace Planeverb
             std::mutex listenerMutex;
             vec3 listener;
 
-            // published results: two host grids of gx*gy*8 floats, index of the readable one
-            std::vector<float> grid[2];
+            // published results: three page-locked host grids of gx*gy*8 floats, index of the readable one.  The worker
+            // runs one frame deep: while frame k+1 is solved, frame k's grid is copied into the second buffer
+            // (pvx_solve_pipelined) and the game / audio threads read frame k-1 from the third.
+            float* grid[3] = { nullptr, nullptr, nullptr };
             std::atomic<int> readable{ 0 };
             std::mutex publishMutex;              // held only for the pointer swap / a 32-byte copy
 
@@ -77,7 +79,8 @@ namespace Planeverb
 
         void workerLoop(Context* ctx)
         {
-            const size_t cells = (size_t)ctx->params.gx * ctx->params.gy;
+            int filling = -1;                     // buffer the copy in flight writes to (-1: none)
+            int next = 1;                         // buffer the next frame will be copied into
             while (ctx->running.load(std::memory_order_acquire))
             {
                 vec3 l;
@@ -86,29 +89,45 @@ namespace Planeverb
                     l = ctx->listener;
                 }
                 const float xyz[3] = { l.x, l.y, l.z };
-                const int back = 1 - ctx->readable.load(std::memory_order_acquire);
                 int rc;
                 while (ctx->solverWaiters.load(std::memory_order_acquire) > 0) std::this_thread::yield();
                 {
                     std::lock_guard<std::mutex> lock(ctx->solverMutex);
-                    // queued geometry edits are flushed inside pvx_solve before the solve (the reference
-                    // applies them after the previous frame's analysis, PvContext.cpp:86: same ordering)
-                    rc = pvx_solve(ctx->scene, xyz, 1, 1, ctx->grid[back].data(), nullptr);
+                    // queued geometry edits are flushed inside the solve call before the time steps (the reference
+                    // applies them after the previous frame's analysis, PvContext.cpp:86: same ordering).  The call
+                    // enqueues this frame and returns once the PREVIOUS frame's grid has landed in `filling`.
+                    rc = pvx_solve_pipelined(ctx->scene, xyz, 1, ctx->grid[next], nullptr);
                 }
                 if (rc != PVC_OK)
                 {   // device failure: stop publishing; GetOutput keeps serving the last good frame
                     ctx->running.store(false, std::memory_order_release);
                     break;
                 }
+                if (filling >= 0)
                 {
-                    std::lock_guard<std::mutex> lock(ctx->publishMutex);
-                    ctx->readable.store(back, std::memory_order_release);
+                    int old;
+                    {
+                        std::lock_guard<std::mutex> lock(ctx->publishMutex);
+                        old = ctx->readable.load(std::memory_order_acquire);
+                        ctx->readable.store(filling, std::memory_order_release);
+                    }
+                    // every grid is a full snapshot of the device's persistent result grid, so the stale-result
+                    // semantics of the reference (cells without an onset keep their previous values,
+                    // Analyzer.cpp:161-165) carry over whichever buffer is reused
+                    filling = next;
+                    next = old;
+                    ctx->frames.fetch_add(1, std::memory_order_release);
                 }
-                // the next frame writes into the old front buffer: carry the stale-result semantics of the
-                // reference (cells without an onset keep their previous values, Analyzer.cpp:161-165) -- the
-                // device keeps the persistent grid, the host copy is always a full snapshot of it
-                (void)cells;
-                ctx->frames.fetch_add(1, std::memory_order_release);
+                else
+                {
+                    filling = next;
+                    next = 2;
+                }
+            }
+            if (filling >= 0)
+            {   // drain the copy in flight (Exit joins this thread before it frees the buffers)
+                std::lock_guard<std::mutex> lock(ctx->solverMutex);
+                pvx_fetch_wait(ctx->scene);
             }
         }
 
@@ -123,6 +142,7 @@ namespace Planeverb
             g_context->running.store(false);
             if (g_context->worker.joinable()) g_context->worker.join();
             pvx_destroy(g_context->scene);
+            for (float* g : g_context->grid) pvc_host_free(g);
             g_context.reset();
         }
         // PvContext.cpp:101-107
@@ -145,8 +165,18 @@ namespace Planeverb
             throw (rc == PVC_ERR_MEMORY) ? pv_NotEnoughMemory : pv_InvalidConfig;
         }
         const size_t cells = (size_t)ctx->params.gx * ctx->params.gy;
-        ctx->grid[0].assign(cells * 8, 0.f);      // Context's memset (PvContext.cpp:132)
-        ctx->grid[1].assign(cells * 8, 0.f);
+        for (int i = 0; i < 3; ++i)
+        {
+            ctx->grid[i] = static_cast<float*>(pvc_host_alloc(sizeof(float) * cells * 8));
+            if (!ctx->grid[i])
+            {
+                g_lastError = pvc_last_error();
+                for (int k = 0; k < i; ++k) pvc_host_free(ctx->grid[k]);
+                pvx_destroy(ctx->scene);
+                throw pv_NotEnoughMemory;
+            }
+            std::memset(ctx->grid[i], 0, sizeof(float) * cells * 8);      // Context's memset (PvContext.cpp:132)
+        }
         ctx->worker = std::thread(workerLoop, ctx.get());
         g_context = std::move(ctx);
     }
@@ -158,6 +188,7 @@ namespace Planeverb
         g_context->running.store(false, std::memory_order_release);
         if (g_context->worker.joinable()) g_context->worker.join();
         pvx_destroy(g_context->scene);
+        for (float* g : g_context->grid) pvc_host_free(g);
         g_context.reset();
     }
 
@@ -226,8 +257,8 @@ namespace Planeverb
         float v[8];
         {
             std::lock_guard<std::mutex> lock(ctx->publishMutex);
-            const std::vector<float>& g = ctx->grid[ctx->readable.load(std::memory_order_acquire)];
-            std::memcpy(v, g.data() + ((size_t)r * ctx->params.gy + c) * 8, sizeof(v));
+            const float* g = ctx->grid[ctx->readable.load(std::memory_order_acquire)];
+            std::memcpy(v, g + ((size_t)r * ctx->params.gy + c) * 8, sizeof(v));
         }
         out.occlusion = v[0];
         out.wetGain = v[1];

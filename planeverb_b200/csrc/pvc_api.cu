@@ -61,7 +61,14 @@ namespace pvc
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
-        return tma ? 47 : 18;
+        if (!tma) return 18;
+        // Few work items per generation (single-source plugin use, small grids): the default 56-row tiles leave SMs idle
+        // and every generation waits on the publish -> acquire -> TMA chain of its neighbours; 32-row tiles (variant 50)
+        // double the items.  Measured cross-over on B200: ~1.4 items of the default tiling per SM (profiles/r01_variants.txt).
+        int sms = 148;
+        { int dev = 0, v = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, c.device) == cudaSuccess && v > 0) sms = v; }
+        const long items = (long)((c.gx + 1 + 47) / 48) * ((c.gy + 1 + kValidCols - 1) / kValidCols) * c.max_sources;
+        return (items * 10 <= (long)sms * 14) ? 50 : 47;
     }
 
     static bool validConfig(const pvc_config* c)

@@ -1295,6 +1295,8 @@ namespace pvc
             case 47: return ws2::launch<14, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 48: return ws2::launch<15, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 49: return ws2::launch<14, 4, 1, false, true, true>(s, nsrc, t0, t1, hist, launches);
+            case 50: return ws2::launch<8, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 51: return ws2::launch<10, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -1313,6 +1315,8 @@ namespace pvc
             case 47: return ws2::buildMask<14, 4>(s);
             case 48: return ws2::buildMask<15, 4>(s);
             case 49: return ws2::buildMask<14, 4>(s);
+            case 50: return ws2::buildMask<8, 4>(s);
+            case 51: return ws2::buildMask<10, 4>(s);
             default: return PVC_OK;
         }
     }

@@ -225,18 +225,35 @@ namespace pvc
                 for (int j = 0; j < R; ++j)
                 {
                     const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
-                    bool rowDead = false;
-                    if (MODE == kEdge) { const int r = rBase + j; rowDead = (r < 0) || (r >= L.gx); }
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    if (MODE == kEdge)
                     {
-                        const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
-                        const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
-                        const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
-                        const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
-                        if (MODE == kFast) p[j][k] = pn;
-                        else if (MODE == kEdge) p[j][k] = (rowDead || (((colOut | colPad) >> k) & 1u)) ? 0.f : pn;
-                        else p[j][k] = ((bpBits >> (j * 4 + k)) & 1u) ? pn : 0.f;
+                        // Rows outside the lattice (and the padding row r == gx) hold p == 0 for ever: nothing to do (warp-uniform).
+                        // Columns outside the lattice / the padding column are kept at zero by a per-column Courant factor of 0
+                        // instead of a select per cell: 0 - 0 * div == +0 (div is finite), and the live columns see the same C.
+                        const int r = rBase + j;
+                        if (r < 0 || r >= L.gx) continue;
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float ck = (((colOut | colPad) >> k) & 1u) ? 0.f : C;
+                            const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                            const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                            const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                            p[j][k] = __fsub_rn(p[j][k], __fmul_rn(ck, div));
+                        }
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                            const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                            const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                            const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
+                            if (MODE == kFast) p[j][k] = pn;
+                            else p[j][k] = ((bpBits >> (j * 4 + k)) & 1u) ? pn : 0.f;
+                        }
                     }
                 }
             }
@@ -265,6 +282,30 @@ namespace pvc
                         const bool rowOut = (r < 0) || (r > L.gx);
                         const bool rowTop = (r == 0), rowPad = (r == L.gx);
                         const uint32_t colDeadX = colOut | colPad;          // vx: the padding column is never driven
+                        if (rowOut) continue;                               // outside the alloc grid: zero for ever (warp-uniform)
+                        if (!rowTop && !rowPad)
+                        {
+                            // interior row of an edge tile (warp-uniform branch): the fast-path arithmetic with the per-column
+                            // Courant factor (dead and padding columns stay +0), then the two position-only overwrites of
+                            // FDTD.cpp:220-221 on the ONE lane that holds column 0 / column gy
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                            {
+                                const float ck = ((colDeadX >> k) & 1u) ? 0.f : C;
+                                const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                                const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                                vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(ck, __fsub_rn(p[j][k], pu)));
+                                vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(ck, __fsub_rn(p[j][k], pl)));
+                            }
+                            if (colLeft & 1u) vy[j][0] = -p[j][0];                                       // column 0 is always a thread's first cell
+                            if (colPad)
+                            {
+                                #pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if ((colPad >> k) & 1u) vy[j][k] = (k > 0) ? p[j][k - 1] : pLeft;
+                            }
+                            continue;
+                        }
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {

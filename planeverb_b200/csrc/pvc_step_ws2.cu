@@ -168,9 +168,9 @@ namespace pvc
             int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
             float courant;
         };
-        // state: loads, [buffer][p,vx,vy], box 128 x tile rows; coef: gx, gy; store: [buffer][p,vx,vy], box 120 x (tile's owned rows), clipped to the
+        // state: loads, [buffer][p,vx,vy], box 128 x tile rows; coef: gx, gy, bp; store: [buffer][p,vx,vy], box 120 x (tile's owned rows), clipped to the
         // alloc grid; hist: 5-D {120 columns, T, strips, rows, sources}, box 120 x 1 x 1 x owned rows x 1 (TS variants only)
-        struct Maps { CUtensorMap state[6]; CUtensorMap coef[2]; CUtensorMap store[6]; CUtensorMap hist; };
+        struct Maps { CUtensorMap state[6]; CUtensorMap coef[3]; CUtensorMap store[6]; CUtensorMap hist; };
 
         // producer -> compute hand-off record of one tile
         struct Meta
@@ -208,7 +208,9 @@ namespace pvc
         //   edge     no wall, but the warp touches the grid edge / padding / guard band: position-only overwrites
         //   general  some cell or neighbour is a wall: coefficient planes gx, gy from shared memory, bp from a bit mask
         // All arithmetic is explicit round-to-nearest mul/add/sub in the reference's operation order (no FMA).
-        template <int NW, int R, int MODE>
+        // BPF: the air flag of the general path comes from a third staged coefficient plane (bp = 1.0 / 0.0 per cell) instead of
+        // the per-thread bit mask: a multiply / one compare per cell where the bit tests cost 5 instructions
+        template <int NW, int R, int MODE, bool BPF = false>
         struct Stepper
         {
             const Layout& L;
@@ -217,6 +219,7 @@ namespace pvc
             const uint32_t colOut, colPad, colLeft;      // edge path: column classes of the thread's 4 cells
             const uint32_t bpBits;                       // general path: air flags of the thread's R x 4 cells
             const float4* cGx; const float4* cGy;        // general path: this thread's coefficient float4s, row stride 32
+            const float4* cBp;                           // BPF: likewise for the air-flag plane
 
             __device__ __forceinline__ void pressure(float (&p)[R][4], const float (&vx)[R][4], const float (&vy)[R][4], const float4 vxBelow) const
             {
@@ -244,6 +247,8 @@ namespace pvc
                     }
                     else
                     {
+                        float bpv[4] = { 1.f, 1.f, 1.f, 1.f };
+                        if (MODE == kGeneral && BPF) { const float4 b4 = cBp[j * 32]; bpv[0] = b4.x; bpv[1] = b4.y; bpv[2] = b4.z; bpv[3] = b4.w; }
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
@@ -252,6 +257,7 @@ namespace pvc
                             const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
                             const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
                             if (MODE == kFast) p[j][k] = pn;
+                            else if (BPF) p[j][k] = __fmul_rn(pn, bpv[k]);          // x 1.0 is exact, x 0.0 gives the reference's b * (...) = 0
                             else p[j][k] = ((bpBits >> (j * 4 + k)) & 1u) ? pn : 0.f;
                         }
                     }
@@ -331,13 +337,15 @@ namespace pvc
                         const float4 y4 = cGy[j * 32];
                         const float ga[4] = { x4.x, x4.y, x4.z, x4.w };
                         const float ha[4] = { y4.x, y4.y, y4.z, y4.w };
+                        float bpv[4] = { 1.f, 1.f, 1.f, 1.f };
+                        if (BPF) { const float4 b4 = cBp[j * 32]; bpv[0] = b4.x; bpv[1] = b4.y; bpv[2] = b4.z; bpv[3] = b4.w; }
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
                             const float pu = (j > 0) ? p[j - 1][k] : pa[k];
                             const float pl = (k > 0) ? p[j][k - 1] : pLeft;
                             const float pt = p[j][k];
-                            const bool air = (bpBits >> (j * 4 + k)) & 1u;
+                            const bool air = BPF ? (bpv[k] != 0.f) : (((bpBits >> (j * 4 + k)) & 1u) != 0u);
                             const float airX = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
                             const float airY = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
                             const float wallX = __fmul_rn(ga[k], air ? pt : pu);
@@ -357,6 +365,7 @@ namespace pvc
             size_t histRow;           // floats between rows of the history
             uint32_t ownRows;         // bit j: row j of this thread is owned (stored), see computeTile
             int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
+            bool onlyLast;            // pulse cell on the padding row / column: inject only the solve's last sample
             const float* pulse;       // 4 samples of this generation (shared memory)
             bool track;               // this warp's block is not yet known to be active: accumulate the activity OR
             // TMA-store variants (TS): the tile's stores go through three [VR][120] staging planes in shared memory and ONE
@@ -411,8 +420,8 @@ namespace pvc
                 }
         }
 
-        template <int NW, int R, int MODE, bool TS>
-        __device__ __forceinline__ void stepLoop(const Stepper<NW, R, MODE>& S, TileCtx& X, const int nsteps,
+        template <int NW, int R, int MODE, bool TS, bool BPF = false>
+        __device__ __forceinline__ void stepLoop(const Stepper<NW, R, MODE, BPF>& S, TileCtx& X, const int nsteps,
                                                  float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], float4 vxBelow,
                                                  float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
         {
@@ -472,7 +481,7 @@ namespace pvc
                         }
                     }
                 }
-                if (X.sj >= 0 && !(TS && last)) injectPulse<R>(X, p, X.pulse[TS ? step + 1 : step]);
+                if (X.sj >= 0 && !(TS && last) && (!X.onlyLast || last)) injectPulse<R>(X, p, X.pulse[TS ? step + 1 : step]);
                 if (!last) sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
                 if (TS && X.storer && last) bulkWaitRead<0>();        // plane for vy (staged after the barrier): g2, one step old
                 // also the write-after-read fence of sPBot for the next pass's first pressure sub-step
@@ -502,9 +511,14 @@ namespace pvc
             static constexpr int TR = NW * R;
             static constexpr uint32_t kPlaneBytes = TR * kTileCols * sizeof(float);
             static constexpr uint32_t kMaskBytes = NW * 32 * sizeof(uint32_t);
+            // coefficient planes staged for a wall tile: gx, gy and -- where 227 KB of shared memory allow -- the air-flag plane
+            // bp (otherwise the per-thread bit mask of bpMaskKernel)
+            static constexpr size_t kOther = 3 * (size_t)TR * kTileCols * sizeof(float) + 2 * (size_t)(NW + 1) * 32 * sizeof(float4)
+                                           + ((TS || SO) ? (size_t)3 * (NW - 2) * R * kValidCols * sizeof(float) : 0) + 2 * sizeof(Meta) + 256;
+            static constexpr int NP = (kOther + (size_t)CB * (3 * (size_t)TR * kTileCols * sizeof(float) + NW * 32 * sizeof(uint32_t)) <= 232448) ? 3 : 2;
             static constexpr size_t offStage = 0;
             static constexpr size_t offCoef = offStage + 3 * (size_t)kPlaneBytes;
-            static constexpr size_t offMask = offCoef + (size_t)CB * 2 * kPlaneBytes;
+            static constexpr size_t offMask = offCoef + (size_t)CB * NP * kPlaneBytes;
             static constexpr size_t offVxTop = offMask + (size_t)CB * kMaskBytes;
             static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
             static constexpr size_t offOut = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);      // [3][(NW - 2) * R][120] (TS only)
@@ -531,7 +545,7 @@ namespace pvc
             static_assert(NW <= 31 && R * 4 <= 32, "Meta holds 32 warps; bpMask holds 32 cells per thread");
             extern __shared__ __align__(128) unsigned char smemRaw[];
             float* stage = reinterpret_cast<float*>(smemRaw + SM::offStage);                       // [3][TR][128]
-            float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);                      // [CB][2][TR][32]
+            float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);                      // [CB][NP][TR][32]: gx, gy(, bp)
             uint32_t* sMask = reinterpret_cast<uint32_t*>(smemRaw + SM::offMask);                  // [CB][NW][32]
             float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
             float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
@@ -844,11 +858,12 @@ namespace pvc
                         if (anySlow)
                         {
                             uint64_t* bar = fullCoef + coefBuf;
-                            float4* dst = sCoef + (size_t)coefBuf * 2 * TR * 32;
-                            mbarExpectTx(bar, 2u * SM::kPlaneBytes + SM::kMaskBytes);
+                            float4* dst = sCoef + (size_t)coefBuf * SM::NP * TR * 32;
+                            mbarExpectTx(bar, (SM::NP == 3) ? 3u * SM::kPlaneBytes : 2u * SM::kPlaneBytes + SM::kMaskBytes);
                             tmaLoad2d(dst, &maps.coef[0], tx * kValidCols, ty * L.valid_rows, bar);
                             tmaLoad2d(dst + (size_t)TR * 32, &maps.coef[1], tx * kValidCols, ty * L.valid_rows, bar);
-                            bulkLoad1d(sMask + (size_t)coefBuf * NW * 32, A.bpMask + (size_t)id * NW * 32, SM::kMaskBytes, bar);
+                            if (SM::NP == 3) tmaLoad2d(dst + (size_t)2 * TR * 32, &maps.coef[2], tx * kValidCols, ty * L.valid_rows, bar);
+                            else bulkLoad1d(sMask + (size_t)coefBuf * NW * 32, A.bpMask + (size_t)id * NW * 32, SM::kMaskBytes, bar);
                         }
                         const CUtensorMap* mp = (gen & 1) ? &maps.state[3] : &maps.state[0];
                         mbarExpectTx(full, 3u * SM::kPlaneBytes);
@@ -973,6 +988,16 @@ namespace pvc
                     const int sj = m->srcR - rBase, sk = m->srcC - cBase;
                     const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
                     X.sj = hasSrc ? sj : -1; X.sk = sk;
+                    // A listener on the padding row / column (b == 0): the reference zeroes the injected sample in the next
+                    // pressure sub-step before anything reads it (FDTD.cpp:125-141, :234), so the cell records 0 for ever and
+                    // only the very last sample survives in the final state.  The edge path never recomputes such cells, so
+                    // the injection is dropped instead -- except for that last sample.
+                    X.onlyLast = false;
+                    if (hasSrc && (m->srcR >= L.gx || m->srcC >= L.gy))
+                    {
+                        if (TS || t0 + nsteps < A.T) X.sj = -1;
+                        else X.onlyLast = true;
+                    }
                 }
                 X.pulse = m->pulse;
                 const bool hints = (A.firstActive != nullptr) && (A.hist != nullptr);
@@ -986,12 +1011,12 @@ namespace pvc
 
                 if (mode == kFast)
                 {
-                    const Stepper<NW, R, kFast> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
+                    const Stepper<NW, R, kFast> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr, nullptr };
                     stepLoop<NW, R, kFast, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
                 else if (mode == kEdge)
                 {
-                    const Stepper<NW, R, kEdge> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr };
+                    const Stepper<NW, R, kEdge> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, nullptr, nullptr, nullptr };
                     stepLoop<NW, R, kEdge, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
                 }
                 else
@@ -999,10 +1024,18 @@ namespace pvc
                     // the coefficient buffer of this tile (usually landed long ago: it was requested one tile ahead)
                     bool ok = mbarWaitBounded(fullCoef + coefBuf, coefParity, A.abortFlag);
                     (void)ok;
-                    const float4* cg = sCoef + (size_t)coefBuf * 2 * TR * 32 + (size_t)(wp * R) * 32 + lane;
-                    const uint32_t bpBits = sMask[(size_t)coefBuf * NW * 32 + wp * 32 + lane];
-                    const Stepper<NW, R, kGeneral> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, bpBits, cg, cg + (size_t)TR * 32 };
-                    stepLoop<NW, R, kGeneral, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    const float4* cg = sCoef + (size_t)coefBuf * SM::NP * TR * 32 + (size_t)(wp * R) * 32 + lane;
+                    if (SM::NP == 3)
+                    {
+                        const Stepper<NW, R, kGeneral, true> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, 0u, cg, cg + (size_t)TR * 32, cg + (size_t)2 * TR * 32 };
+                        stepLoop<NW, R, kGeneral, TS, true>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    }
+                    else
+                    {
+                        const uint32_t bpBits = sMask[(size_t)coefBuf * NW * 32 + wp * 32 + lane];
+                        const Stepper<NW, R, kGeneral> S{ L, A.courant, lane, wp, rBase, colOut, colPad, colLeft, bpBits, cg, cg + (size_t)TR * 32, nullptr };
+                        stepLoop<NW, R, kGeneral, TS>(S, X, nsteps, p, vx, vy, vxBelow, sVxTop, sPBot, activity);
+                    }
                 }
 
                 if (threadIdx.x == 32 * 7) trace(PVC_DBG(A), seq - 1, 5);
@@ -1134,13 +1167,13 @@ namespace pvc
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
             { cudaGetLastError(); setError("ws2 step kernel: cuTensorMapEncodeTiled unavailable"); return PVC_ERR_CUDA; }
             const Layout& L = s->L;
-            for (int f = 0; f < 2; ++f)
+            for (int f = 0; f < 3; ++f)
             {
                 const cuuint64_t dims[2] = { (cuuint64_t)L.pitch, (cuuint64_t)L.rows_alloc };
                 const cuuint64_t strides[1] = { (cuuint64_t)L.pitch * sizeof(float) };
                 const cuuint32_t box[2] = { (cuuint32_t)kTileCols, (cuuint32_t)L.tile_rows };
                 const cuuint32_t estr[2] = { 1u, 1u };
-                const CUresult r = ((EncodeFn)fn)(&out[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->coef[1 + f], dims, strides, box, estr,
+                const CUresult r = ((EncodeFn)fn)(&out[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->coef[(1 + f) % 3], dims, strides, box, estr,
                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { setError("ws2 step kernel: coefficient tensor map %d failed (%d)", f, (int)r); return PVC_ERR_CUDA; }

@@ -165,6 +165,9 @@ def test_batched_sources_equal_separate_solves(pv, scenes):
     (121, 150, (60, 120)),      # one column past a tile boundary, listener on the last interior column
     (239, 202, (238, 0)),
     (97, 64, (50, 50)),
+    (130, 90, (130, 40)),       # listener on the padding ROW (b == 0): records zeros, the injected samples never propagate
+    (130, 91, (40, 130)),       # listener on the padding COLUMN
+    (60, 50, (60, 60)),         # ... on the padding corner
 ])
 def test_edge_case_grids_and_listeners(pv, n, T, listener_cell):
     size, _ = common.scaled_config(n)
@@ -184,6 +187,10 @@ def test_edge_case_grids_and_listeners(pv, n, T, listener_cell):
     p, vx, vy = gpu.state()
     assert common.bit_equal(vx, ora.hvx[-1].reshape(n + 1, n + 1)).all()
     assert common.bit_equal(vy, ora.hvy[-1].reshape(n + 1, n + 1)).all()
+    # final pressure state = last record + the last injected sample (FDTD.cpp:234), also when the listener sits on a b == 0 cell
+    want_p = ora.hist[T - 1].copy()
+    want_p[listener_cell[0] * (n + 1) + listener_cell[1]] += ora.pulse[T - 1]
+    assert common.bit_equal(p, want_p.reshape(n + 1, n + 1)).all()
     assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
     gpu.close()
 

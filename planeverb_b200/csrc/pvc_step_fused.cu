@@ -1126,7 +1126,8 @@ namespace pvc
                                          {14, 4, 1, 5}, {15, 4, 1, 5}, {30, 2, 1, 5}, {20, 3, 1, 5}, {14, 4, 1, 5},
                                          {10, 8, 1, 5}, {11, 6, 1, 5}, {12, 6, 1, 5},         // 39..46: pvc_step_ws2.cu
                                          {14, 4, 1, 5}, {15, 4, 1, 5}, {14, 4, 1, 5},           // 47, 48: ws2 + publisher warp; 49: + state out through TMA stores
-                                         {8, 4, 1, 5}, {10, 4, 1, 5} };                         // 50, 51: small tiles for grids with fewer tiles than SMs
+                                         {8, 4, 1, 5}, {10, 4, 1, 5},                           // 50, 51: small tiles for grids with fewer tiles than SMs
+                                         {12, 4, 1, 5}, {12, 5, 1, 5} };                        // 52, 53: 3 compute warps per scheduler (service warps on two of them)
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     int fusedTileRows(int variant)
@@ -1425,7 +1426,7 @@ namespace pvc
             case 36: return launchGen<15, 4, true, true>(s, nsrc, t0, t1, hist, launches);
             case 37: return launchGen<15, 4, false, true>(s, nsrc, t0, t1, hist, launches);
             case 38: return launchGen<11, 6, true, true>(s, nsrc, t0, t1, hist, launches);
-            case 39: case 40: case 41: case 42: case 43: case 44: case 45: case 46: case 47: case 48: case 49: case 50: case 51: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
+            case 39: case 40: case 41: case 42: case 43: case 44: case 45: case 46: case 47: case 48: case 49: case 50: case 51: case 52: case 53: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
             default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
         }
     }
@@ -1451,6 +1452,7 @@ namespace pvc
             case 2004: return maskVariant<20, 4, 1>(s);
             case 1004: return maskVariant<10, 4, 1>(s);
             case 1204: return maskVariant<12, 4, 1>(s);
+            case 1205: return maskVariant<12, 5, 1>(s);
             case 806: return maskVariant<8, 6, 1>(s);
             case 1006: return maskVariant<10, 6, 1>(s);
             case 1206: return maskVariant<12, 6, 1>(s);

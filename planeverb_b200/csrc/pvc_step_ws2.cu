@@ -1371,6 +1371,8 @@ namespace pvc
             case 49: return ws2::launch<14, 4, 1, false, true, true>(s, nsrc, t0, t1, hist, launches);
             case 50: return ws2::launch<8, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 51: return ws2::launch<10, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 52: return ws2::launch<12, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 53: return ws2::launch<12, 5, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -1391,6 +1393,8 @@ namespace pvc
             case 49: return ws2::buildMask<14, 4>(s);
             case 50: return ws2::buildMask<8, 4>(s);
             case 51: return ws2::buildMask<10, 4>(s);
+            case 52: return ws2::buildMask<12, 4>(s);
+            case 53: return ws2::buildMask<12, 5>(s);
             default: return PVC_OK;
         }
     }

@@ -100,15 +100,31 @@ namespace pvc
     }
 
     // The same value as decibels() for a NORMAL, positive, finite e (the caller checks a whole batch with one
-    // predicate), as straight-line code: no special-case branches, the exponent term of logf picked from
-    // {-ln2, 0, +ln2} instead of an int->double conversion and a multiply (k is -1, 0 or 1 for m in [0.5, 2) and
-    // k*ln2 is then exact), and float->double of the reduced mantissa done with integer ops (exact for normal floats).
-    // Of the reference recipe's three 64-bit conversions (a quarter-rate pipe) only the final rounding remains.
+    // predicate), as straight-line code with the logf kernel in a cheaper, EXHAUSTIVELY verified form
+    // (tools/micro/logf_fma_recipe.c runs all 2^24 floats of [0.5, 2), the only inputs log10f hands to logf, against
+    // the host libm: zero mismatches; tests/test_oracle.py::test_device_logf_fma_form_is_exhaustively_exact):
+    //   * a 33-entry table indexed by (bits(m) - 0x3f330000) >> 19 (arithmetic, -7..25) that holds, per logf interval AND
+    //     exponent k in {-1, 0, 1}, { invc * 2^-k, logc + k*ln2 } (buildLogfTable33: the reference's own y0 = logc + k*ln2,
+    //     one rounding, and an exact power-of-two scaling), so neither the reduced mantissa z = m * 2^-k nor k is formed;
+    //   * r = fma(m, invc', -1) and the polynomial in FMA form: 6 double-precision instructions instead of 11.  The fused
+    //     roundings differ from e_logf.c's separate ones only far below the final rounding to float -- on no input at all
+    //     (glibc's own __logf_fma variant, which FMA-capable x86-64 hosts run, contracts the same expressions);
+    //   * float -> double of m by integer ops (exact for normal floats).
     __device__ __forceinline__ bool isNormalPositive(float e)
     {
         return (__float_as_uint(e) - 0x00800000u) < 0x7f000000u;
     }
-    __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab)
+    constexpr int kLogf33 = 33, kLogf33Bias = 7;
+    __device__ __forceinline__ LogfEntry buildLogfTable33(int idx, const LogfEntry* __restrict__ tab16)
+    {
+        const int j = idx - kLogf33Bias, ti = j & 15, tk = j >> 4;                       // tk = -1, 0 or 1
+        const LogfEntry e = tab16[ti];
+        LogfEntry o;
+        o.invc = __dmul_rn(e.invc, tk < 0 ? 2.0 : (tk > 0 ? 0.5 : 1.0));                 // exact
+        o.logc = __dadd_rn(e.logc, __dmul_rn((double)tk, 0x1.62e42fefa39efp-1));         // y0 of e_logf.c
+        return o;
+    }
+    __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab33)
     {
     #ifdef PVC_FAST_LOG10
         return __fmul_rn(__log2f(e), 3.0102999566398120f);
@@ -118,19 +134,14 @@ namespace pvc
         const int i = (int)((unsigned)k >> 31);
         const uint32_t hm = (uint32_t)((hx & 0x007fffff) | ((0x7f - i) << 23));     // m in [1,2) or [0.5,1)
         const float yk = (float)(k + i);
-        const uint32_t tmp = hm - 0x3f330000u;
-        const int ti = (tmp >> 19) & 15;
-        const int tk = (int)tmp >> 23;                                                // -1, 0 or 1
-        const uint32_t iz = hm - (tmp & 0xff800000u);                                 // z in [~0.7, 1.4)
-        const LogfEntry en = tab[ti];
-        const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
-        const double kln2 = (tk == 0) ? 0.0 : (tk > 0 ? 0x1.62e42fefa39efp-1 : -0x1.62e42fefa39efp-1);
-        const double r = __dsub_rn(__dmul_rn(z, en.invc), 1.0);
-        const double y0 = __dadd_rn(en.logc, kln2);
+        const int idx = ((int)(hm - 0x3f330000u) >> 19) + kLogf33Bias;
+        const LogfEntry en = tab33[idx];
+        const double md = __hiloint2double((int)((hm >> 3) + 0x38000000u), (int)(hm << 29));
+        const double r = __fma_rn(md, en.invc, -1.0);
         const double r2 = __dmul_rn(r, r);
-        double y = __dadd_rn(__dmul_rn(0x1.5575b0be00b6ap-2, r), -0x1.ffffef20a4123p-2);
-        y = __dadd_rn(__dmul_rn(-0x1.00ea348b88334p-2, r2), y);
-        y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+        double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+        y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+        y = __fma_rn(y, r2, __dadd_rn(en.logc, r));
         const float lf = (float)y;
         const float zz = __fadd_rn(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(4.3429449201e-01f, lf));
         return __fmul_rn(10.f, __fadd_rn(zz, __fmul_rn(yk, 3.0102920532e-01f)));
@@ -152,7 +163,9 @@ namespace pvc
                          float* __restrict__ delay, float* __restrict__ walkDelay, const int* __restrict__ firstActive)
     {
         __shared__ LogfEntry sTab[16];
+        __shared__ LogfEntry sTab33[kLogf33];
         if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
+        if (threadIdx.x < kLogf33) sTab33[threadIdx.x] = buildLogfTable33(threadIdx.x, kLogfTable);
         __syncthreads();
 
         const int c = blockIdx.x * HC + threadIdx.x;              // block = one history strip of one row (spare threads if the strip is narrower)
@@ -354,7 +367,7 @@ namespace pvc
                 if (normal)
                 {
                     #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab);
+                    for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab33);
                 }
                 else
                 {

@@ -207,3 +207,25 @@ def test_device_log10f_recipe_matches_libm():
     want = np.array([libm.log10f(float(v)) for v in x], np.float32)
     got = log10f(x)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_device_logf_fma_form_is_exhaustively_exact(tmp_path):
+    """The analyzer's hot loop evaluates glibc's logf kernel in FMA form over a 33-entry {invc * 2^-k, logc + k*ln2} table
+    (pvc_analyze.cu::decibelsNormal).  tools/micro/logf_fma_recipe.c restates that form in C and runs ALL 2^24 floats of
+    [0.5, 2) -- the only inputs fdlibm's log10f hands to logf -- against the host libm, together with e_logf.c as written
+    and its FMA-contracted variant: every one of them must agree bit for bit on every input."""
+    import os
+    import re
+    import subprocess
+    csrc = os.path.join(common.ROOT, "tools", "micro", "logf_fma_recipe.c")
+    exe = str(tmp_path / "logf_fma_recipe")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, csrc, "-lm"])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "inputs 16777216  a!=b 0  a!=libm 0  b!=libm 0  device!=libm 0" in p.stdout
+    # the C restatement and the CUDA source use the same constants and the same table indexing
+    cu = open(os.path.join(common.ROOT, "planeverb_b200", "csrc", "pvc_analyze.cu")).read()
+    c = open(csrc).read()
+    for const in re.findall(r"-?0x1\.[0-9a-f]+p[+-]\d+", c):
+        assert const in cu, const
+    assert "0x3f330000u) >> 19) + kLogf33Bias" in cu and "kLogf33Bias = 7" in cu and ">> 19) + 7" in c

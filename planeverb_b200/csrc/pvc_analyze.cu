@@ -355,14 +355,15 @@ namespace pvc
                 // the kBatch Schroeder values first (one dependent add each), then their logarithms, which are
                 // independent of each other: straight-line when all are normal floats (all but a vanishing few batches)
                 float e[kBatch];
-                bool normal = true;
                 #pragma unroll
                 for (int u = 0; u < kBatch; ++u)
                 {
                     edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
                     e[u] = edc;
-                    normal = normal && isNormalPositive(edc);
                 }
+                // the running sum of squares never decreases (a NaN or an infinity sticks): the first and the last value of
+                // the batch bracket the others
+                const bool normal = isNormalPositive(e[0]) && isNormalPositive(e[kBatch - 1]);
                 float y[kBatch];
                 if (normal)
                 {

@@ -215,7 +215,10 @@ namespace pvc
         }
 
         // ---- onset: first sample with |p| > threshold (Analyzer.cpp:146-154); kBatch loads in flight ----
-        constexpr int kBatch = 8;
+    #ifndef PVC_AN_BATCH
+    #define PVC_AN_BATCH 16
+    #endif
+        constexpr int kBatch = PVC_AN_BATCH;          // streaming loads in flight per thread (A/B: make EXTRA=-DPVC_AN_BATCH=8)
         int onset = -1;
         for (int t0 = onsetBegin; t0 < T && onset < 0; t0 += kBatch)
         {

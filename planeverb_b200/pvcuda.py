@@ -158,6 +158,14 @@ def derive_emitter_cell(resolution, size_x, size_y, x, z):
     return None if code else (int(rc[0]), int(rc[1]))
 
 
+def memory_requirement(gx, gy, T, max_sources, variant=0, step_kernel=0):
+    """Device bytes a solver of this size allocates (pvc_memory_requirement: host arithmetic, needs no GPU); 0 = invalid config."""
+    cfg = PvcConfig(gx=int(gx), gy=int(gy), T=int(T), fs=1443, resolution=275, dx=0.3565818, courant=0.6666667, flux_samples=7, dry_samples=14,
+                    wet_samples=115, tail_samples=14, max_sources=int(max_sources), device=0, step_kernel=int(step_kernel),
+                    reserved=int(variant))
+    return int(lib().pvc_memory_requirement(C.byref(cfg)))
+
+
 def device_count():
     return int(lib().pvc_device_count())
 

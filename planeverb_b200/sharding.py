@@ -23,6 +23,38 @@ def shard(items, world, rank):
     return list(items[lo:hi])
 
 
+def plan_batches(n_items, world, rank, max_batch):
+    """This rank's shard of n_items split into consecutive batches of at most max_batch items: [(lo, hi), ...] in global
+    indices.  A 2048^2 source keeps 71 GB of pressure history for 4000 steps, so a GPU solves its shard of BASELINE
+    configs[3] a few sources at a time (tools/gpu_config4.py); batches are as even as possible (5 items, max 2 -> 2, 2, 1)."""
+    if max_batch < 1:
+        raise ValueError(f"max_batch {max_batch}")
+    lo, hi = shard_bounds(n_items, world, rank)
+    n = hi - lo
+    if n == 0:
+        return []
+    k = -(-n // max_batch)                      # number of batches
+    base, extra = divmod(n, k)
+    out, at = [], lo
+    for b in range(k):
+        size = base + (1 if b < extra else 0)
+        out.append((at, at + size))
+        at += size
+    return out
+
+
+def max_batch_for_memory(bytes_for, budget_bytes, cap):
+    """Largest batch size S in 1..cap with bytes_for(S) <= budget_bytes (bytes_for = the solver's device-memory requirement
+    for S batched sources, pvcuda.memory_requirement); 0 if not even one source fits."""
+    best = 0
+    for s in range(1, max(cap, 0) + 1):
+        if bytes_for(s) <= budget_bytes:
+            best = s
+        else:
+            break
+    return best
+
+
 def gather_outputs(local, dist=None, device=None, n_total=None):
     """All-gather per-source outputs.  local: float32 array [n_local_sources, n_emitters, 8].
     Returns the list of every rank's array, in rank order (shards may differ in length).

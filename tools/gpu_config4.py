@@ -20,7 +20,8 @@ def main():
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--T", type=int, default=4000)
     ap.add_argument("--sources", type=int, default=8)
-    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=0, help="sources per solve; 0 = as many as fit 95 %% of the device memory")
+    ap.add_argument("--mem-gb", type=float, default=178.0, help="device memory the batch size is derived from")
     ap.add_argument("--scene", default="HugeRoom")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -33,14 +34,18 @@ def main():
     size, scale = common.scaled_config(a.n)
     boxes = common.boxes_of(scenes, a.scene, scale)
     everyone = common.listeners_for(a.sources, scale)
-    mine = sharding.shard(everyone, world, rank)
-    B = max(1, min(a.batch, len(mine)))
+    lo, hi = sharding.shard_bounds(a.sources, world, rank)
+    fit = sharding.max_batch_for_memory(lambda S: pvcuda.memory_requirement(a.n, a.n, a.T, S), 0.95 * a.mem_gb * 1e9, max(hi - lo, 1))
+    if fit < 1:
+        raise SystemExit(f"one {a.n}x{a.n} source of {a.T} steps does not fit {a.mem_gb} GB")
+    plan = sharding.plan_batches(a.sources, world, rank, min(a.batch, fit) if a.batch > 0 else fit)
+    B = max([h - l for l, h in plan] or [1])
     emitters = [(x * scale, 0.0, z * scale) for (x, z) in common.EMITTERS]
     G = pvcuda.Scene(size, size, 275, T=a.T, max_sources=B, device=local if world > 1 else 0, efree=0.0447895788)
     assert G.gx == a.n and G.gy == a.n
     for b in boxes: G.add_aabb(*b)
     G.flush_geometry()
-    batches = [mine[i:i + B] for i in range(0, len(mine), B)]
+    batches = [everyone[l:h] for l, h in plan]
     bufs = [pvcuda.pinned_array((len(b), len(emitters), 8)) for b in batches]
 
     def sync():

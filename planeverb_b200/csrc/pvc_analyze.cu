@@ -124,16 +124,26 @@ namespace pvc
         o.logc = __dadd_rn(e.logc, __dmul_rn((double)tk, 0x1.62e42fefa39efp-1));         // y0 of e_logf.c
         return o;
     }
-    __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab33)
+    // Per-exponent part of fdlibm's log10f for a normal float with exponent field E = 1..254: k = E - 127, i = (k < 0),
+    // K = k + i, and the two products that depend on K alone, y*log10_2lo and y*log10_2hi with y = (float)K; z holds K << 23,
+    // so that the mantissa re-biased to [0.5, 2) is bits(e) - z.  One 16-byte shared-memory load (neighbouring cells have
+    // neighbouring energies: mostly a broadcast) replaces 10 integer / conversion / multiply instructions per sample.
+    constexpr int kExpEntries = 256;
+    __device__ __forceinline__ float4 buildExponentEntry(int E)
+    {
+        const int k = E - 127;
+        const int i = (int)((unsigned)k >> 31);
+        const float yk = (float)(k + i);
+        return make_float4(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(yk, 3.0102920532e-01f), __int_as_float((k + i) << 23), 0.f);
+    }
+    __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab33, const float4* __restrict__ tabExp)
     {
     #ifdef PVC_FAST_LOG10
         return __fmul_rn(__log2f(e), 3.0102999566398120f);
     #else
         const int hx = __float_as_int(e);
-        const int k = (hx >> 23) - 127;
-        const int i = (int)((unsigned)k >> 31);
-        const uint32_t hm = (uint32_t)((hx & 0x007fffff) | ((0x7f - i) << 23));     // m in [1,2) or [0.5,1)
-        const float yk = (float)(k + i);
+        const float4 ex = tabExp[(unsigned)hx >> 23];
+        const uint32_t hm = (uint32_t)(hx - __float_as_int(ex.z));                  // m in [1,2) (e >= 1) or [0.5,1)
         const int idx = ((int)(hm - 0x3f330000u) >> 19) + kLogf33Bias;
         const LogfEntry en = tab33[idx];
         const double md = __hiloint2double((int)((hm >> 3) + 0x38000000u), (int)(hm << 29));
@@ -143,8 +153,8 @@ namespace pvc
         y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
         y = __fma_rn(y, r2, __dadd_rn(en.logc, r));
         const float lf = (float)y;
-        const float zz = __fadd_rn(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(4.3429449201e-01f, lf));
-        return __fmul_rn(10.f, __fadd_rn(zz, __fmul_rn(yk, 3.0102920532e-01f)));
+        const float zz = __fadd_rn(ex.x, __fmul_rn(4.3429449201e-01f, lf));
+        return __fmul_rn(10.f, __fadd_rn(zz, ex.y));
     #endif
     }
 
@@ -166,6 +176,8 @@ namespace pvc
         __shared__ LogfEntry sTab33[kLogf33];
         if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
         if (threadIdx.x < kLogf33) sTab33[threadIdx.x] = buildLogfTable33(threadIdx.x, kLogfTable);
+        __shared__ float4 sTabExp[kExpEntries];
+        for (int E = threadIdx.x; E < kExpEntries; E += blockDim.x) sTabExp[E] = buildExponentEntry(E);
         __syncthreads();
 
         const int c = blockIdx.x * HC + threadIdx.x;              // block = one history strip of one row (spare threads if the strip is narrower)
@@ -371,7 +383,7 @@ namespace pvc
                 if (normal)
                 {
                     #pragma unroll
-                    for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab33);
+                    for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab33, sTabExp);
                 }
                 else
                 {

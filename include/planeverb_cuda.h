@@ -164,6 +164,11 @@ PVC_API const float* pvc_results_dev(pvc_solver* s, int source);
 /* debug/profiling aid: runs a few 4-step launches and returns, per CTA of the last one, 8 %globaltimer stamps
  * (start, tile loaded, after each of the 4 steps, stores issued); returns the number of CTAs or a negative... >= 0 ok */
 PVC_API int  pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out, int maxBlocks);
+/* host-side mirror of the generational step kernel's work-item order (pvc_internal.h::ws2DecodeItem, the same inline function
+ * the kernel calls): item w of 0 .. num_gen * tiles_per_source * nsrc - 1 -> out3 = { source, generation, position in the tile
+ * order }.  Host arithmetic, needs no GPU; tests/test_abi.py checks that the order is a bijection in which every dependency of
+ * an item (same source, previous generation) precedes it -- the kernel's deadlock-freedom argument.  PVC_ERR_INVALID if out of range. */
+PVC_API int  pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_per_source, int* out3);
 /* page-locked host buffers for the result grids (plain malloc'd memory works too, just slower to copy) */
 PVC_API void* pvc_host_alloc(size_t bytes);
 PVC_API void  pvc_host_free(void* p);

@@ -704,6 +704,16 @@ int pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out, int max
     return rc ? rc : blocks;
 }
 
+int pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_per_source, int* out3)
+{
+    if (!out3 || gen_chunk < 1 || src_group < 1 || src_group > nsrc || num_gen < 1 || nsrc < 1 || tiles_per_source < 1 ||
+        w < 0 || (long long)w >= (long long)num_gen * tiles_per_source * nsrc) { setError("pvc_debug_ws2_item: bad argument"); return PVC_ERR_INVALID; }
+    const pvc::Ws2Order ord = { gen_chunk, src_group, num_gen, nsrc, tiles_per_source, tiles_per_source * nsrc };
+    const pvc::Ws2Item it = pvc::ws2DecodeItem(w, ord);
+    out3[0] = it.s; out3[1] = it.gen; out3[2] = it.o;
+    return PVC_OK;
+}
+
 void* pvc_host_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -144,6 +144,40 @@ struct pvc_solver
 
 namespace pvc
 {
+    // ---- work-item order of the generational step kernel (pvc_step_ws2.cu) --------------------------------------------
+    // One launch covers numGen generations of every (source, tile).  Work item w of 0 .. numGen * tps * nsrc - 1 is:
+    // chunks of genChunk generations; inside a chunk one source group (srcGroup sources whose ping-pong state fits the L2)
+    // after the other; inside a group generation-major, then position in the tile order, then source.  Every dependency of
+    // an item -- same source, the tile and its up-to-8 neighbours, previous generation -- precedes it in this order, which
+    // is what makes the kernel's "pull the next item, wait for its dependencies" loop deadlock-free with co-resident CTAs.
+    // Shared by the kernel and the host (pvc_debug_ws2_item -> tests/test_abi.py checks the invariant on the CPU).
+    struct Ws2Order { int genChunk, srcGroup, numGen, nsrc, tps, numTiles; };      // numTiles = tps * nsrc
+    struct Ws2Item { int s, gen, o; };                  // source, generation relative to the launch, position in the tile order
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    inline Ws2Item ws2DecodeItem(int w, const Ws2Order& P)
+    {
+        const int chunkItems = P.genChunk * P.numTiles;
+        const int c = w / chunkItems;
+        int rem = w - c * chunkItems;
+        const int left = P.numGen - c * P.genChunk;
+        const int gc = P.genChunk < left ? P.genChunk : left;
+        const int groupItems = gc * P.tps * P.srcGroup;
+        const int q = rem / groupItems;
+        rem -= q * groupItems;
+        const int rest = P.nsrc - q * P.srcGroup;
+        const int sq = P.srcGroup < rest ? P.srcGroup : rest;
+        const int g = rem / (sq * P.tps);
+        rem -= g * (sq * P.tps);
+        const int o = rem / sq;
+        Ws2Item it;
+        it.s = q * P.srcGroup + (rem - o * sq);
+        it.gen = c * P.genChunk + g;
+        it.o = o;
+        return it;
+    }
+
     // step kernels (pvc_step.cu / pvc_step_fused.cu)
     int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);

@@ -730,23 +730,12 @@ namespace pvc
                     w = __shfl_sync(0xffffffffu, w, 0);
                     nx.valid = w < total;
                     if (!nx.valid) return;
-                    // item order: chunks of genChunk generations; inside a chunk one source group after the other (a group's
-                    // ping-pong state stays L2-resident for the whole chunk); inside a group generation-major, then tile
-                    // order, then source.  Every dependency of an item (same source, neighbour tiles, previous generation)
-                    // precedes it in this order.
-                    const int chunkItems = A.genChunk * A.numTiles;
-                    const int c = w / chunkItems;
-                    int rem = w - c * chunkItems;
-                    const int gc = min(A.genChunk, A.numGen - c * A.genChunk);
-                    const int groupItems = gc * tps * A.srcGroup;
-                    const int q = rem / groupItems;
-                    rem -= q * groupItems;
-                    const int sq = min(A.srcGroup, A.nsrc - q * A.srcGroup);
-                    const int g = rem / (sq * tps);
-                    rem -= g * (sq * tps);
-                    const int o = rem / sq;
-                    nx.s = q * A.srcGroup + (rem - o * sq);
-                    nx.gen = A.gen0 + c * A.genChunk + g;
+                    // item order (pvc_internal.h::ws2DecodeItem): every dependency of an item precedes it
+                    const Ws2Order ord = { A.genChunk, A.srcGroup, A.numGen, A.nsrc, tps, A.numTiles };
+                    const Ws2Item wi = ws2DecodeItem(w, ord);
+                    const int o = wi.o;
+                    nx.s = wi.s;
+                    nx.gen = A.gen0 + wi.gen;
                     nx.id = A.tileOrder ? A.tileOrder[o] : o;          // null: row-major order
                     nx.ty = nx.id / L.tiles_x; nx.tx = nx.id - nx.ty * L.tiles_x;
                     // the tile's hand-off record, gathered lane-parallel (loads overlap the dependency probe below)

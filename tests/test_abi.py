@@ -105,3 +105,40 @@ def test_struct_layouts_match_header():
     assert C.sizeof(pvcuda.PvcConfig) == 15 * 4
     assert C.sizeof(pvcuda.PvcRect) == 24
     assert C.sizeof(pvcuda.PvcListener) == 24
+
+
+@pytest.mark.parametrize("gen_chunk,src_group,num_gen,nsrc,tps", [
+    (16, 2, 40, 4, 6),        # the bench configuration's shape (two groups of two sources), a partial last chunk
+    (16, 3, 16, 3, 5),        # one group, exactly one chunk
+    (4, 2, 9, 5, 4),          # uneven last group (2 + 2 + 1) and a partial last chunk
+    (1, 1, 5, 3, 7),          # degenerate: generation-major over single-source groups
+    (16, 1, 3, 1, 11),        # single source, fewer generations than a chunk
+])
+def test_ws2_work_item_order_is_a_dependency_respecting_bijection(gen_chunk, src_group, num_gen, nsrc, tps):
+    """The generational step kernel pulls work items from one counter and waits for an item's dependencies: the tile and
+    its neighbours, same source, previous generation.  That loop cannot deadlock if (a) every (source, generation, tile) is
+    exactly one item and (b) every item of generation g-1 of a source precedes every item of generation g of that source.
+    pvc_debug_ws2_item evaluates the very inline function the kernel calls (pvc_internal.h::ws2DecodeItem) on the host."""
+    import ctypes as C
+    L = pvcuda.lib()
+    out = (C.c_int * 3)()
+    total = num_gen * nsrc * tps
+    seen = {}
+    last_of = {}            # (source, generation) -> largest item index
+    first_of = {}           # (source, generation) -> smallest item index
+    for w in range(total):
+        assert L.pvc_debug_ws2_item(w, gen_chunk, src_group, num_gen, nsrc, tps, out) == 0
+        s, g, o = out[0], out[1], out[2]
+        assert 0 <= s < nsrc and 0 <= g < num_gen and 0 <= o < tps
+        assert (s, g, o) not in seen
+        seen[(s, g, o)] = w
+        last_of[(s, g)] = w
+        first_of.setdefault((s, g), w)
+    assert len(seen) == total
+    for s in range(nsrc):
+        for g in range(1, num_gen):
+            assert last_of[(s, g - 1)] < first_of[(s, g)]
+    # sources of one group interleave inside a generation (their state shares the L2), groups do not inside a chunk
+    for w in (-1, total):
+        assert L.pvc_debug_ws2_item(w, gen_chunk, src_group, num_gen, nsrc, tps, out) == pvcuda.PVC_ERR_INVALID
+    assert L.pvc_debug_ws2_item(0, gen_chunk, nsrc + 1, num_gen, nsrc, tps, out) == pvcuda.PVC_ERR_INVALID

@@ -169,6 +169,10 @@ PVC_API int  pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out
  * order }.  Host arithmetic, needs no GPU; tests/test_abi.py checks that the order is a bijection in which every dependency of
  * an item (same source, previous generation) precedes it -- the kernel's deadlock-freedom argument.  PVC_ERR_INVALID if out of range. */
 PVC_API int  pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_per_source, int* out3);
+/* Listener-direction algorithm of the analyzer (Analyzer::EncodeListenerDirection, Analyzer.cpp:340-431): 0 (default) = pointer
+ * jumping over a link array, 1 = the reference's walk, one thread per start cell.  Bit-identical results; the second exists as the
+ * cross-check of the first (tests/test_gpu_parity.py). */
+PVC_API int  pvc_set_walk_mode(pvc_solver* s, int sequential);
 /* page-locked host buffers for the result grids (plain malloc'd memory works too, just slower to copy) */
 PVC_API void* pvc_host_alloc(size_t bytes);
 PVC_API void  pvc_host_free(void* p);

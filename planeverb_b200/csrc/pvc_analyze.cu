@@ -16,7 +16,6 @@
 //     sums of Analyzer.cpp:303-319 -- this anti-causal pass is why a pressure history exists at all.
 // A block is the cells of one history strip (128 columns): its 4 warps walk one contiguous 512-byte-per-sample stream.
 #include <float.h>
-#include <cstdlib>
 #include "pvc_internal.h"
 
 namespace pvc
@@ -665,8 +664,7 @@ namespace pvc
             encodeResponseKernel<kValidCols><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
                                                                             s->hintsValid ? s->firstActive : nullptr);
         else { setError("analyzer: unsupported history strip width %d", L.hist_chunk); return PVC_ERR_INVALID; }
-        const char* walkEnv = getenv("PVC_WALK");           // read per call: the tests switch it
-        if (walkEnv && walkEnv[0] == 's')
+        if (s->walkSequential)                              // pvc_set_walk_mode: the reference's walk, the cross-check of the tests
         {
             listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
             *launches += 2;

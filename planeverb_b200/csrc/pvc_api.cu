@@ -37,7 +37,9 @@ namespace pvc
         L.warp_rows = fusedWarpRows(c.reserved);
         L.valid_rows = L.tile_rows - 2 * kTileK;
         L.tiles_x = (L.cols + kValidCols - 1) / kValidCols;
-        L.tiles_y = (L.rows + L.valid_rows - 1) / L.valid_rows;
+        // resident tiles only have to OWN the gx interior rows: the padding row gx is always current in the halo of the tile above it
+        // (it depends on row gx - 1 of the same step only) and is recorded from there (pvc_step_res.cu)
+        L.tiles_y = (variantKind(c.reserved) == 6) ? (L.gx + L.valid_rows - 1) / L.valid_rows : (L.rows + L.valid_rows - 1) / L.valid_rows;
         L.pitch = roundUp(L.tiles_x * kValidCols + 2 * kGuardCols, 32);
         L.rows_alloc = L.tiles_y * L.valid_rows + 2 * kGuardRows;
         if (L.rows_alloc < L.rows + kGuardRows + 1) L.rows_alloc = L.rows + kGuardRows + 1;
@@ -50,23 +52,51 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto: the second warp-specialised generational kernel (pvc_step_ws2.cu, variant 47: 14 compute warps x
-    // 4 rows + a producer warp that prefetches every per-tile input with TMA / into a shared-memory record + a publisher
-    // warp that releases finished tiles, source-group item order that keeps a group's state L2-resident) -- fastest at
-    // every batch/grid size measured on B200 (profiles/).  It needs cuTensorMapEncodeTiled from the driver; without it fall back to the plain 8 x 6 kernel.
+    // variant 0 = auto.
+    //   * resident kernel (pvc_step_res.cu, variants 60..64) whenever every tile of at least one source fits the GPU at once:
+    //     state in registers for the whole solve, only halo strips through the L2.  Among the tilings that fit, the one with the
+    //     lowest estimated solve time: passes x launches x (exchange latency + per-warp step time x warps sharing an SM).
+    //   * else the warp-specialised generational kernel (pvc_step_ws2.cu): variant 47 (14 compute warps x 4 rows + producer +
+    //     publisher warp, source groups that keep a group's state L2-resident), or variant 50 (32-row tiles) when the default
+    //     tiling yields fewer than ~1.4 work items per SM and generation (measured cross-over, profiles/r01_variants.txt).
+    //   * without cuTensorMapEncodeTiled in the driver the generational kernels cannot run: the plain 8 x 6 kernel (18).
+    struct ResidentChoice { int variant; double cost; };
+    static ResidentChoice bestResident(const pvc_config& c, int sms)
+    {
+        ResidentChoice best = { 0, 0.0 };
+        for (int v = 60; v <= 64; ++v)
+        {
+            if (!variantAvailable(v)) continue;
+            const int nw = variantWarps(v), perSm = variantMinBlocks(v);
+            const int vr = nw * 4 - 2 * kTileK;
+            const long tiles = (long)((c.gx + vr - 1) / vr) * ((c.gy + 1 + kValidCols - 1) / kValidCols);
+            const long cap = (long)sms * perSm;
+            if (tiles > cap) continue;
+            const long perLaunch = cap / tiles;
+            const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
+            const long ctas = tiles * (c.max_sources < perLaunch ? c.max_sources : perLaunch);
+            const long ctasPerSm = (ctas + sms - 1) / sms;                       // CTAs that actually share an SM
+            // microseconds per pass: hand-over latency (hidden behind the other CTA when two share an SM) + issue time of the
+            // warps on the SM (0.22 us per compute warp and pass when the SM is full, floor 1.2 us for a lone small CTA)
+            const double compute = 0.22 * nw * (double)ctasPerSm;
+            const double pass = (ctasPerSm > 1 ? 0.4 : 1.2) + (compute > 1.2 ? compute : 1.2);
+            const double cost = pass * (double)launches;
+            if (best.variant == 0 || cost < best.cost) { best.variant = v; best.cost = cost; }
+        }
+        return best;
+    }
     static int resolveVariant(const pvc_config& c)
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
+        int sms = 148;
+        { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, c.device) == cudaSuccess && v > 0) sms = v; else cudaGetLastError(); }
+        const ResidentChoice rc = bestResident(c, sms);
+        if (rc.variant) return rc.variant;
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
         if (!tma) return 18;
-        // Few work items per generation (single-source plugin use, small grids): the default 56-row tiles leave SMs idle
-        // and every generation waits on the publish -> acquire -> TMA chain of its neighbours; 32-row tiles (variant 50)
-        // double the items.  Measured cross-over on B200: ~1.4 items of the default tiling per SM (profiles/r01_variants.txt).
-        int sms = 148;
-        { int dev = 0, v = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, c.device) == cudaSuccess && v > 0) sms = v; }
         const long items = (long)((c.gx + 1 + 47) / 48) * ((c.gy + 1 + kValidCols - 1) / kValidCols) * c.max_sources;
         return (items * 10 <= (long)sms * 14) ? 50 : 47;
     }
@@ -252,7 +282,7 @@ size_t pvc_memory_requirement(const pvc_config* cfg)
     pvc_config r = *cfg; r.reserved = resolveVariant(*cfg);
     const Layout L = makeLayout(r);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + 4 * L.plane + S * L.hist_source + (size_t)cfg->T +
+    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 : 4) * L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 11 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
@@ -270,6 +300,12 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
     s->cfg.reserved = resolveVariant(*cfg);
+    if (cfg->step_kernel == 0 && !variantAvailable(s->cfg.reserved))
+    {
+        setError("pvc_create: step-kernel variant %d is not compiled into this build (make EXTRA=-DPVC_ALL_VARIANTS)", s->cfg.reserved);
+        delete s;
+        return PVC_ERR_INVALID;
+    }
     s->device = cfg->device;
     s->L = makeLayout(s->cfg);
     { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device); s->numSMs = sms > 0 ? sms : 148; }
@@ -303,6 +339,11 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
     PVC_TRY(cudaMalloc(&s->doneGen, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));
+    if (variantKind(s->cfg.reserved) == 6)
+    {
+        for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->lin[f], sizeof(float) * L.plane));
+        PVC_TRY(cudaMalloc(&s->resFlags, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));
+    }
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
@@ -317,7 +358,10 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     for (int i = 0; i < 4; ++i) PVC_TRY(cudaEventCreateWithFlags(&s->srcCopied[i], cudaEventDisableTiming));
     #undef PVC_TRY
     s->efree = 1.f;
-    s->useGraphs = getenv("PVC_NO_GRAPHS") ? 0 : 1;
+    s->useGraphs = variantKind(s->cfg.reserved) == 0 ? 1 : 0;      // only the one-launch-per-4-steps kernels have enough launches to replay
+#ifdef PVC_TUNING
+    if (getenv("PVC_NO_GRAPHS")) s->useGraphs = 0;
+#endif
     buildTensorMaps(s);
     int rc = launchClearGeometry(s);
     if (rc) { pvc_destroy(s); return rc; }
@@ -332,7 +376,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) cudaFree(s->coef[f]); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) { cudaFree(s->coef[f]); cudaFree(s->lin[f]); } cudaFree(s->resFlags); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
     if (s->evAnalyzed) cudaEventDestroy(s->evAnalyzed);
     if (s->evCopied) cudaEventDestroy(s->evCopied);
@@ -371,6 +415,11 @@ int pvc_clear_geometry(pvc_solver* s)
 int pvc_apply_geometry(pvc_solver* s, const pvc_rect* rects, int n)
 {
     if (!s || (n > 0 && !rects) || n < 0) { setError("pvc_apply_geometry: bad argument"); return PVC_ERR_INVALID; }
+    // a wall's admittance Y = (1-R)/(1+R) lies in [0, 1] for every reflection coefficient R in [0, 1]; a negative one (R > 1, an
+    // amplifying wall) has no physical meaning and the coefficient planes of pvc_step_res.cu keep a flag in its sign
+    for (int i = 0; i < n; ++i)
+        if (rects[i].add && !(rects[i].admittance >= 0.f && rects[i].admittance <= 1.f))
+        { setError("pvc_apply_geometry: edit %d has admittance %g outside [0, 1] (absorption must lie in [0, 1])", i, (double)rects[i].admittance); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     return launchApplyRects(s, rects, n);
 }
@@ -412,8 +461,9 @@ int pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, floa
     PVC_CUDA(cudaMalloc(&wFree, sizeof(float) * L.plane));
     s->w = wFree;
     int rc = launchClearGeometry(s);
-    SourceParams sp{ lr, lc, lr, lc, 0.f, 0.f };
+    SourceParams sp{ lr, lc, lr, lc, 0.f, 0.f, 0 };
     if (!rc && cudaMemcpyAsync(s->src, &sp, sizeof(sp), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) rc = PVC_ERR_CUDA;
+    if (!rc) rc = markDeadSources(s, 1);
     if (!rc) rc = zeroState(s, 1);
     int launches = 0;
     if (!rc) rc = runSteps(s, 1, n, &launches);
@@ -455,10 +505,11 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
     for (int i = 0; i < n; ++i)
     {
         const pvc_listener& l = listeners[i];
-        sp[i] = SourceParams{ l.cell_r, l.cell_c, l.efree_r, l.efree_c, l.x, l.z };
+        sp[i] = SourceParams{ l.cell_r, l.cell_c, l.efree_r, l.efree_c, l.x, l.z, 0 };
     }
     PVC_CUDA(cudaMemcpyAsync(s->src, sp, sizeof(SourceParams) * n, cudaMemcpyHostToDevice, s->stream));
     PVC_CUDA(cudaEventRecord(s->srcCopied[slot], s->stream));
+    { const int rcDead = markDeadSources(s, n); if (rcDead) return rcDead; }
     int launches = 0;
     PVC_CUDA(cudaEventRecord(s->ev[0], s->stream));
     int rc = zeroState(s, n);
@@ -711,6 +762,13 @@ int pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsr
     const pvc::Ws2Order ord = { gen_chunk, src_group, num_gen, nsrc, tiles_per_source, tiles_per_source * nsrc };
     const pvc::Ws2Item it = pvc::ws2DecodeItem(w, ord);
     out3[0] = it.s; out3[1] = it.gen; out3[2] = it.o;
+    return PVC_OK;
+}
+
+int pvc_set_walk_mode(pvc_solver* s, int sequential)
+{
+    if (!s) { setError("pvc_set_walk_mode: null solver"); return PVC_ERR_INVALID; }
+    s->walkSequential = sequential ? 1 : 0;
     return PVC_OK;
 }
 

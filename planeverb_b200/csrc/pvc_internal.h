@@ -74,6 +74,10 @@ namespace pvc
         int cell_r, cell_c;
         int efree_r, efree_c;
         float x, z;
+        int dead;             // the pulse cell is not an interior air cell (wall, padding row / column): filled on the device by
+                              // markDeadSourcesKernel after the geometry of the frame has been applied.  The reference zeroes a
+                              // sample injected there in the next pressure sub-step before anything reads it (FDTD.cpp:125-141,
+                              // :234); the resident kernel's multiply-free wall rule relies on p == 0 in such cells and skips it
     };
 }
 
@@ -100,6 +104,9 @@ struct pvc_solver
     float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
     float* w;                // wall plane (air flag / admittance), the geometry's source of truth
     float* coef[3];          // general-path coefficient planes bp, gx, gy derived from w (pvc_step_fused.cu)
+    float* lin[3];           // linear-form coefficient planes cP, sX, sY derived from w (pvc_step_res.cu); null until a resident variant needs them
+    int* resFlags;           // resident kernel: passes completed per (source, tile)
+    int resSourcesPerLaunch; // resident kernel: sources solved concurrently by one launch (co-residency limit), 0 = not computed yet
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
     uint32_t* bpMask;        // per (tile, warp, lane): air flags of the thread's cells (pvc_step_ws2.cu)
     int slowMaskDirty;
@@ -139,6 +146,7 @@ struct pvc_solver
     int lastStepLaunches;
     unsigned long long* timeline;   // debug only
     int useGraphs;
+    int walkSequential;      // pvc_set_walk_mode: 1 = listener direction by the reference's sequential walk (cross-check)
     pvc::GraphSlot graphs[pvc::kMaxGraphBatch + 1];   // captured step-launch sequences, by batch size
 };
 
@@ -184,6 +192,14 @@ namespace pvc
     int rebuildSlowMask(pvc_solver* s);
     int launchWs2Steps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches);
     int rebuildWs2Descriptors(pvc_solver* s, int variant);
+    int launchResidentSteps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches);
+    int rebuildResidentDescriptors(pvc_solver* s, int variant);
+    int residentCapacity(int variant, int device);     // CTAs of a resident variant that can be co-resident on the device (0: unknown / does not fit)
+    int markDeadSources(pvc_solver* s, int n);
+    bool variantAvailable(int variant);
+    int variantKind(int variant);
+    int variantMinBlocks(int variant);
+    int variantWarps(int variant);
     int buildTensorMaps(pvc_solver* s);
     int fusedTileRows(int variant);
     int fusedWarpRows(int variant);

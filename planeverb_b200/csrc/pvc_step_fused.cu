@@ -442,6 +442,7 @@ namespace pvc
         computeTile<NW, R, CS>(L, A, tx, ty, s, p, vx, vy, sVxTop, sPBot, sCoefDyn, -1, runOf(A));
     }
 
+#ifdef PVC_ALL_VARIANTS      // superseded experiments (profiles/r01_variants.txt): make EXTRA=-DPVC_ALL_VARIANTS
     // ---- persistent variant: TMA bulk-copy prefetch of the next tile through shared memory ----------------
     // One CTA per SM walks tiles b, b+G, b+2G, ...  While it steps tile i in registers, the TMA engine
     // (cp.async.bulk global->shared, mbarrier complete_tx) lands the 3*TR 512-byte rows of tile i+1 in a
@@ -1037,6 +1038,8 @@ namespace pvc
     }
 
     // Per-cell coefficients of the general path, rebuilt after every geometry edit from the wall plane w.
+#endif // PVC_ALL_VARIANTS
+
     // With bp = 1 for an interior air cell (reference b = 1) and 0 otherwise, the reference's three update
     // rules (FDTD.cpp:125-223 incl. the grid-edge overrides) collapse to data:
     //   p  <- bp ? p - C*div : 0
@@ -1115,20 +1118,52 @@ namespace pvc
         if (lane == 0) mask[((size_t)ty * L.tiles_x + tx) * 32 + wp] = anyWall ? 2u : (anyEdge ? 1u : 0u);
     }
 
-    // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, persistent TMA-prefetch
-    struct Variant { int nw, r, minBlocks, persistent; };
-    static const Variant kVariants[] = { {8, 6, 2, 0}, {8, 8, 2, 0}, {16, 4, 2, 0}, {16, 8, 1, 0}, {8, 4, 4, 0}, {8, 8, 1, 0},
-                                         {16, 4, 1, 0}, {12, 8, 1, 0}, {8, 8, 1, 1}, {14, 8, 1, 1},
-                                         {24, 4, 1, 0}, {16, 6, 1, 0}, {20, 4, 1, 0}, {24, 4, 1, 1}, {16, 6, 1, 1}, {12, 8, 1, 1},
-                                         {10, 4, 2, 0}, {12, 4, 2, 0}, {8, 6, 2, 0}, {10, 6, 2, 0}, {8, 6, 2, 0}, {20, 4, 1, 0},
-                                         {16, 4, 1, 2}, {12, 6, 1, 2}, {20, 4, 1, 2}, {16, 4, 1, 2}, {12, 8, 1, 2},
-                                         {16, 4, 1, 2}, {12, 4, 1, 2}, {10, 4, 1, 2}, {16, 4, 1, 3}, {16, 4, 1, 3}, {12, 6, 1, 3}, {16, 4, 1, 4}, {16, 4, 1, 4}, {12, 6, 1, 4}, {15, 4, 1, 4}, {15, 4, 1, 4}, {11, 6, 1, 4},
-                                         {14, 4, 1, 5}, {15, 4, 1, 5}, {30, 2, 1, 5}, {20, 3, 1, 5}, {14, 4, 1, 5},
-                                         {10, 8, 1, 5}, {11, 6, 1, 5}, {12, 6, 1, 5},         // 39..46: pvc_step_ws2.cu
-                                         {14, 4, 1, 5}, {15, 4, 1, 5}, {14, 4, 1, 5},           // 47, 48: ws2 + publisher warp; 49: + state out through TMA stores
-                                         {8, 4, 1, 5}, {10, 4, 1, 5},                           // 50, 51: small tiles for grids with fewer tiles than SMs
-                                         {12, 4, 1, 5}, {12, 5, 1, 5} };                        // 52, 53: 3 compute warps per scheduler (service warps on two of them)
+    // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, kind
+    //   kind 0 one launch per 4 steps (fusedStepKernel)      1 persistent        2 TMA persistent   3 generational
+    //        4 first warp-specialised generational           5 ws2 (pvc_step_ws2.cu)                6 resident (pvc_step_res.cu)
+    // The default build carries what the product selects -- 47 / 50 (ws2), 60..64 (resident), 18 (fallback without the TMA
+    // driver entry point) -- plus step_kernel = 1 (two-launch baseline, pvc_step.cu).  Everything else documents the
+    // search (profiles/r01_variants.txt) and is compiled only with make EXTRA=-DPVC_ALL_VARIANTS.
+    struct Variant { int nw, r, minBlocks, persistent, builtin; };
+    static const Variant kVariants[] = { {8, 6, 2, 0, 1}, {8, 8, 2, 0, 0}, {16, 4, 2, 0, 0}, {16, 8, 1, 0, 0}, {8, 4, 4, 0, 0}, {8, 8, 1, 0, 0},
+                                         {16, 4, 1, 0, 0}, {12, 8, 1, 0, 0}, {8, 8, 1, 1, 0}, {14, 8, 1, 1, 0},
+                                         {24, 4, 1, 0, 0}, {16, 6, 1, 0, 0}, {20, 4, 1, 0, 0}, {24, 4, 1, 1, 0}, {16, 6, 1, 1, 0}, {12, 8, 1, 1, 0},
+                                         {10, 4, 2, 0, 0}, {12, 4, 2, 0, 0}, {8, 6, 2, 0, 1}, {10, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {20, 4, 1, 0, 0},
+                                         {16, 4, 1, 2, 0}, {12, 6, 1, 2, 0}, {20, 4, 1, 2, 0}, {16, 4, 1, 2, 0}, {12, 8, 1, 2, 0},
+                                         {16, 4, 1, 2, 0}, {12, 4, 1, 2, 0}, {10, 4, 1, 2, 0}, {16, 4, 1, 3, 0}, {16, 4, 1, 3, 0}, {12, 6, 1, 3, 0}, {16, 4, 1, 4, 0}, {16, 4, 1, 4, 0}, {12, 6, 1, 4, 0}, {15, 4, 1, 4, 0}, {15, 4, 1, 4, 0}, {11, 6, 1, 4, 0},
+                                         {14, 4, 1, 5, 0}, {15, 4, 1, 5, 0}, {30, 2, 1, 5, 0}, {20, 3, 1, 5, 0}, {14, 4, 1, 5, 0},
+                                         {10, 8, 1, 5, 0}, {11, 6, 1, 5, 0}, {12, 6, 1, 5, 0},         // 39..46: pvc_step_ws2.cu experiments
+                                         {14, 4, 1, 5, 1}, {15, 4, 1, 5, 0}, {14, 4, 1, 5, 0},           // 47 (default for large batches), 48, 49
+                                         {8, 4, 1, 5, 1}, {10, 4, 1, 5, 0},                              // 50 (default when few work items), 51
+                                         {12, 4, 1, 5, 0}, {12, 5, 1, 5, 0},                             // 52, 53
+                                         {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0},   // 54..59 unused
+                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1} };   // 60..64: resident
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+    bool variantAvailable(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants || (variant >= 54 && variant <= 59)) return false;
+#ifdef PVC_ALL_VARIANTS
+        return true;
+#else
+        return kVariants[variant].builtin != 0;
+#endif
+    }
+    int variantKind(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants) variant = 0;
+        return kVariants[variant].persistent;
+    }
+    int variantMinBlocks(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants) variant = 0;
+        return kVariants[variant].minBlocks;
+    }
+    int variantWarps(int variant)
+    {
+        if (variant < 0 || variant >= kNumVariants) variant = 0;
+        return kVariants[variant].nw;
+    }
 
     int fusedTileRows(int variant)
     {
@@ -1149,7 +1184,9 @@ namespace pvc
         A.t0 = t; A.nsteps = (t1 - t < kTileK) ? (t1 - t) : kTileK;
         A.courant = s->cfg.courant;
         A.timeline = s->timeline;
-        if (s->timeline) { static const char* dbg = getenv("PVC_DEBUG_NSTEPS"); if (dbg) A.nsteps = atoi(dbg); }   // debug: memory-floor probe
+#ifdef PVC_TUNING
+        if (s->timeline) { static const char* dbg = getenv("PVC_DEBUG_NSTEPS"); if (dbg) A.nsteps = atoi(dbg); }   // debug: memory-floor probe (results invalid)
+#endif
         return A;
     }
 
@@ -1190,6 +1227,7 @@ namespace pvc
         return PVC_OK;
     }
 
+#ifdef PVC_ALL_VARIANTS
     template <int NW, int R>
     static int launchPersistent(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
@@ -1305,6 +1343,8 @@ namespace pvc
         return PVC_OK;
     }
 
+#endif // PVC_ALL_VARIANTS
+
     // 3-D tensor maps {pitch, rows_alloc, sources} of the six state planes, box 128 x tileRows x 1 (driver entry point
     // fetched through the runtime, no libcuda link)
     int buildTensorMaps(pvc_solver* s)
@@ -1342,37 +1382,34 @@ namespace pvc
         slowMaskKernel<NW, R, MINB><<<dim3(L.tiles_x, L.tiles_y), NW * 32, 0, s->stream>>>(L, s->w, s->slowMask);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("slow mask launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
-        // tile order, most expensive first (general-path warps cost ~3x, edge-path ~1.3x a fast warp)
-        const int tiles = L.tiles_x * L.tiles_y;
-        {
-            // row-major order (see below) needs no read-back: a frame loop that edits geometry every frame then never
-            // waits for the device here.  The identity order is uploaded once.
-            static const char* orderEnv0 = getenv("PVC_TILE_ORDER");
-            int v0 = s->cfg.reserved; if (v0 < 0 || v0 >= kNumVariants) v0 = 0;
-            bool natural0 = kVariants[v0].persistent >= 4;
-            if (orderEnv0) natural0 = orderEnv0[0] == 'n';
-            if (natural0 && s->tileOrderNatural == 1) { s->slowMaskDirty = 0; return PVC_OK; }
-        }
-        std::vector<uint32_t> modes((size_t)tiles * 32);
-        if (cudaMemcpyAsync(modes.data(), s->slowMask, sizeof(uint32_t) * modes.size(), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
-            cudaStreamSynchronize(s->stream) != cudaSuccess)
-        { setError("slow mask readback: %s", cudaGetErrorString(cudaGetLastError())); return PVC_ERR_CUDA; }
-        std::vector<std::pair<int, int>> cost((size_t)tiles);
-        for (int t = 0; t < tiles; ++t)
-        {
-            int c = 0;
-            for (int wIdx = 0; wIdx < NW; ++wIdx) { const uint32_t m = modes[(size_t)t * 32 + wIdx]; c += (m == 2u) ? 30 : (m == 1u ? 13 : 10); }
-            cost[(size_t)t] = std::make_pair(-c, t);
-        }
-        // The generational kernels keep the row-major tile order: every dependency of an item is then about one
+        // The generational / resident kernels keep the row-major tile order: every dependency of an item is then about one
         // generation old, whereas "expensive tiles first" makes the wall tiles at the head of generation g wait for
         // neighbours at the tail of generation g-1 (measured: 7 % slower).  The one-launch-per-4-steps kernels sort by
-        // cost so the expensive tiles do not form the launch's tail.  PVC_TILE_ORDER=natural|cost overrides.
-        static const char* orderEnv = getenv("PVC_TILE_ORDER");
-        int vCur = s->cfg.reserved; if (vCur < 0 || vCur >= kNumVariants) vCur = 0;
-        bool natural = kVariants[vCur].persistent >= 4;
-        if (orderEnv) natural = orderEnv[0] == 'n';
-        if (!natural) std::sort(cost.begin(), cost.end());
+        // cost (general-path warps ~3x, edge-path ~1.3x a fast warp) so the expensive tiles do not form the launch's tail.
+        const int tiles = L.tiles_x * L.tiles_y;
+        bool natural = variantKind(s->cfg.reserved) >= 4;
+#ifdef PVC_TUNING
+        { static const char* orderEnv = getenv("PVC_TILE_ORDER"); if (orderEnv) natural = orderEnv[0] == 'n'; }
+#endif
+        // row-major order needs no read-back: a frame loop that edits geometry every frame then never waits for the
+        // device here.  The identity order is uploaded once.
+        if (natural && s->tileOrderNatural == 1) { s->slowMaskDirty = 0; return PVC_OK; }
+        std::vector<std::pair<int, int>> cost((size_t)tiles);
+        if (natural) { for (int t = 0; t < tiles; ++t) cost[(size_t)t] = std::make_pair(0, t); }
+        else
+        {
+            std::vector<uint32_t> modes((size_t)tiles * 32);
+            if (cudaMemcpyAsync(modes.data(), s->slowMask, sizeof(uint32_t) * modes.size(), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess)
+            { setError("slow mask readback: %s", cudaGetErrorString(cudaGetLastError())); return PVC_ERR_CUDA; }
+            for (int t = 0; t < tiles; ++t)
+            {
+                int c = 0;
+                for (int wIdx = 0; wIdx < NW; ++wIdx) { const uint32_t m = modes[(size_t)t * 32 + wIdx]; c += (m == 2u) ? 30 : (m == 1u ? 13 : 10); }
+                cost[(size_t)t] = std::make_pair(-c, t);
+            }
+            std::sort(cost.begin(), cost.end());
+        }
         s->tileOrderNatural = natural ? 1 : 0;
         std::vector<int> order((size_t)tiles);
         for (int t = 0; t < tiles; ++t) order[(size_t)t] = cost[(size_t)t].second;
@@ -1385,9 +1422,14 @@ namespace pvc
 
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
     {
-        int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
+        const int v = s->cfg.reserved;
+        if (!variantAvailable(v)) { setError("step-kernel variant %d is not compiled into this build (make EXTRA=-DPVC_ALL_VARIANTS)", v); return PVC_ERR_INVALID; }
+        if (variantKind(v) == 5) return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
+        if (variantKind(v) == 6) return launchResidentSteps(s, v, nsrc, t0, t1, hist, launches);
         switch (v)
         {
+            case 0: case 18: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
+#ifdef PVC_ALL_VARIANTS
             case 1: return launchVariant<8, 8, 2>(s, nsrc, t0, t1, hist, launches);
             case 2: return launchVariant<16, 4, 2>(s, nsrc, t0, t1, hist, launches);
             case 3: return launchVariant<16, 8, 1>(s, nsrc, t0, t1, hist, launches);
@@ -1405,7 +1447,6 @@ namespace pvc
             case 15: return launchPersistent<12, 8>(s, nsrc, t0, t1, hist, launches);
             case 16: return launchVariant<10, 4, 2>(s, nsrc, t0, t1, hist, launches);
             case 17: return launchVariant<12, 4, 2>(s, nsrc, t0, t1, hist, launches);
-            case 18: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
             case 19: return launchVariant<10, 6, 2>(s, nsrc, t0, t1, hist, launches);
             case 20: return launchVariant<8, 6, 2, true>(s, nsrc, t0, t1, hist, launches);
             case 21: return launchVariant<20, 4, 1, true>(s, nsrc, t0, t1, hist, launches);
@@ -1426,39 +1467,44 @@ namespace pvc
             case 36: return launchGen<15, 4, true, true>(s, nsrc, t0, t1, hist, launches);
             case 37: return launchGen<15, 4, false, true>(s, nsrc, t0, t1, hist, launches);
             case 38: return launchGen<11, 6, true, true>(s, nsrc, t0, t1, hist, launches);
-            case 39: case 40: case 41: case 42: case 43: case 44: case 45: case 46: case 47: case 48: case 49: case 50: case 51: case 52: case 53: return launchWs2Steps(s, v, nsrc, t0, t1, hist, launches);
-            default: return launchVariant<8, 6, 2>(s, nsrc, t0, t1, hist, launches);
+#endif
+            default: setError("step-kernel variant %d: no launcher", v); return PVC_ERR_INVALID;
         }
     }
 
     int rebuildSlowMask(pvc_solver* s)
     {
+        const int v = s->cfg.reserved;
+        if (!variantAvailable(v)) { setError("step-kernel variant %d is not compiled into this build (make EXTRA=-DPVC_ALL_VARIANTS)", v); return PVC_ERR_INVALID; }
         buildCoefficientsKernel<<<(unsigned)((s->L.plane + 255) / 256), 256, 0, s->stream>>>(s->L, s->w, s->coef[0], s->coef[1], s->coef[2]);
-        int v = s->cfg.reserved; if (v < 0 || v >= kNumVariants) v = 0;
-        if (kVariants[v].persistent == 5) { const int rc = rebuildWs2Descriptors(s, v); if (rc) return rc; }
+        if (variantKind(v) == 5) { const int rc = rebuildWs2Descriptors(s, v); if (rc) return rc; }
+        if (variantKind(v) == 6) { const int rc = rebuildResidentDescriptors(s, v); if (rc) return rc; }
         switch (kVariants[v].nw * 100 + kVariants[v].r)
         {
+            case 806: return maskVariant<8, 6, 1>(s);
+            case 804: return maskVariant<8, 4, 1>(s);
+            case 1004: return maskVariant<10, 4, 1>(s);
+            case 1204: return maskVariant<12, 4, 1>(s);
             case 1404: return maskVariant<14, 4, 1>(s);
+            case 1604: return maskVariant<16, 4, 1>(s);
+            case 2004: return maskVariant<20, 4, 1>(s);
+#ifdef PVC_ALL_VARIANTS
             case 1008: return maskVariant<10, 8, 1>(s);
             case 3002: return maskVariant<30, 2, 1>(s);
             case 2003: return maskVariant<20, 3, 1>(s);
             case 808: return maskVariant<8, 8, 1>(s);
-            case 1604: return maskVariant<16, 4, 1>(s);
             case 1608: return maskVariant<16, 8, 1>(s);
-            case 804: return maskVariant<8, 4, 1>(s);
             case 1408: return maskVariant<14, 8, 1>(s);
             case 2404: return maskVariant<24, 4, 1>(s);
             case 1606: return maskVariant<16, 6, 1>(s);
-            case 2004: return maskVariant<20, 4, 1>(s);
-            case 1004: return maskVariant<10, 4, 1>(s);
-            case 1204: return maskVariant<12, 4, 1>(s);
             case 1205: return maskVariant<12, 5, 1>(s);
-            case 806: return maskVariant<8, 6, 1>(s);
             case 1006: return maskVariant<10, 6, 1>(s);
             case 1206: return maskVariant<12, 6, 1>(s);
             case 1504: return maskVariant<15, 4, 1>(s);
             case 1106: return maskVariant<11, 6, 1>(s);
-            default: return maskVariant<12, 8, 1>(s);
+            case 1208: return maskVariant<12, 8, 1>(s);
+#endif
+            default: setError("step-kernel variant %d: no mask kernel for %d x %d tiles", v, kVariants[v].nw, kVariants[v].r); return PVC_ERR_INVALID;
         }
     }
 }

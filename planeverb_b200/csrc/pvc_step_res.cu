@@ -1,0 +1,569 @@
+// pvc_step_res.cu -- "resident" step kernel: the whole solve of a source in ONE launch with the state in registers.
+//
+// Same numerics as every other step kernel here: Grid::GenerateResponseCPU's time step
+// (ProjectPlaneverb/src/FDTD/FDTD.cpp:122-235) in the reference's operation order, explicit round-to-nearest fp32
+// mul / add / sub, K = 4 steps per pass over tiles of (NW*R) x 128 cells incl. a 4-cell halo, a warp owning R rows x 128
+// columns and a lane one float4 of each row.  What differs from the generational kernel (pvc_step_ws2.cu):
+//
+//   * A tile belongs to ONE CTA for the whole solve and its p / vx / vy never leave the registers.  Between passes a
+//     CTA writes only the 4-cell-wide strips its neighbours need (first / last four owned rows, lanes 1 and 30 of the
+//     others) into the ping-pong state planes and reads its own halo ring back from them: ~32 KB per tile and pass
+//     through the L2 instead of 155 KB (full tile in through TMA, owned cells out), no TMA stage to drain, no store
+//     burst, no producer / publisher warps.  Hand-over: one counter per tile, `st.release.gpu` after a CTA barrier,
+//     `ld.acquire.gpu` polls of the up-to-8 neighbours by every warp.  All CTAs are co-resident (cooperative launch);
+//     a batch of sources that does not fit is solved a few sources per launch, one launch after the other.
+//   * Walls, the absorbing grid edge, the padding row / column and the guard band are DATA in a form that costs what
+//     the interior-air path costs.  With p == 0 in every cell that is not interior air (an invariant of the scheme:
+//     such a cell's pressure coefficient is 0 and nothing is ever injected there), the four cases of the reference's
+//     velocity rule and its edge overrides collapse to
+//         vx' = k * vx - c * (p - p_up)        k in {0, 1}, c in {Courant, Y_wall, 1, 0}
+//         p'  = p - cP * div                    cP in {Courant, 0}
+//     -- (air, air): k = 1, c = Courant; air under a wall: p_up == 0, c = Y_up -> -(Y_up * p); wall under air: p == 0,
+//     c = Y_self -> Y_self * p_up; row 0: c = 1 -> -p; padding row: c = 1 -> p_up; everything else 0.  k * vx is exact
+//     and -(c * d) is an exactly negated product, so fma(k, vx, -(c * d)) rounds once, exactly like the reference's
+//     separate multiply and subtract: three instructions per velocity component, as in the air path.  Three coefficient
+//     planes (cP, and k folded into the sign of c: -Courant marks k = 1) are staged once per solve in shared memory.
+//     Admittances must be >= 0 (absorption in [0, 1]); pvc_apply_geometry rejects anything else.
+//
+// Selected automatically when every tile of at least one source fits the GPU at once (grids up to ~1024 x 1024): the
+// reference's own contract (70^2 .. 191^2 cells, one listener) runs as one to four CTAs with no hand-over at all or
+// one per pass instead of a publish -> acquire -> TMA chain per generation.
+//
+// Roofline: HBM by the 28 B / cell-update accounting of SURVEY.md 8d; physically the kernel
+// moves the 4-byte history record per cell-step and the strips, and is bound by instruction issue.
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "pvc_internal.h"
+
+namespace pvc
+{
+    namespace res
+    {
+        __device__ __forceinline__ int loadAcquire(const int* p)
+        {
+            int v;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            return v;
+        }
+        __device__ __forceinline__ void storeRelease(int* p, int v)
+        {
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        }
+        __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+        // neighbour-only synchronisation of the step loop (see pvc_step_ws2.cu::phaseSync): a warp meets the warp above and
+        // the warp below on the named barrier of their common edge (id = upper warp + 1), even warps the lower edge first
+        template <int NW, bool PAIR>
+        __device__ __forceinline__ void phaseSync(int wp)
+        {
+            if (PAIR)
+            {
+                if (wp & 1) { pairBarrier(wp); if (wp + 1 < NW) pairBarrier(wp + 1); }
+                else { if (wp + 1 < NW) pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
+            }
+            else __syncthreads();            // taller tiles (16 named barriers per CTA) and two-CTA-per-SM variants (barriers are an SM resource)
+        }
+        // 1.0f where x < 0 (one FSET): the k of the linear-form velocity rule, folded into the sign of its coefficient
+        __device__ __forceinline__ float signFlag(float x)
+        {
+            float r;
+            asm("set.lt.f32.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+            return r;
+        }
+
+        struct Args
+        {
+            float* p0; float* vx0; float* vy0;     // ping-pong buffer 0 (pass g reads buffer g & 1, writes the other)
+            float* p1; float* vx1; float* vy1;
+            float* hist;
+            const uint32_t* mode;                  // [tile][32] path mode per warp (slowMaskKernel): 0 = interior air, else coefficient path
+            const float* cP; const float* sX; const float* sY;
+            int* firstActive;                      // [source][tile][32]
+            const SourceParams* src;
+            const float* pulse;
+            int* flags;                            // [source][tile] passes completed
+            int* abortFlag;
+            int tilesPerSource, s0, nsrc;          // this launch solves sources s0 .. s0 + nsrc - 1
+            int numGen, T;
+            float courant;
+        };
+
+        // ---- one time step of a warp's R x 128 block; GEN = coefficient path (walls / edges / guard band as data) ----
+        template <int R, bool GEN>
+        __device__ __forceinline__ void pressureStep(float (&p)[R][4], const float (&vx)[R][4], const float (&vy)[R][4], const float4 vxBelow,
+                                                     const float C, const float4* __restrict__ cP)
+        {
+            const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
+                float ck[4] = { C, C, C, C };
+                if (GEN) { const float4 c4 = cP[j * 32]; ck[0] = c4.x; ck[1] = c4.y; ck[2] = c4.z; ck[3] = c4.w; }
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
+                    const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
+                    const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
+                    p[j][k] = __fsub_rn(p[j][k], __fmul_rn(ck[k], div));
+                }
+            }
+        }
+        template <int R, bool GEN>
+        __device__ __forceinline__ void velocityStep(const float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], const float4 pAbove,
+                                                     const float C, const float4* __restrict__ sX, const float4* __restrict__ sY)
+        {
+            const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
+                if (!GEN)
+                {
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                        vx[j][k] = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pu)));
+                        vy[j][k] = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(p[j][k], pl)));
+                    }
+                }
+                else
+                {
+                    const float4 x4 = sX[j * 32], y4 = sY[j * 32];
+                    const float gx[4] = { x4.x, x4.y, x4.z, x4.w };
+                    const float gy[4] = { y4.x, y4.y, y4.z, y4.w };
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const float pu = (j > 0) ? p[j - 1][k] : pa[k];
+                        const float pl = (k > 0) ? p[j][k - 1] : pLeft;
+                        // fma(k, v, -(|s| * d)): k * v is exact (k is 0 or 1), so this is the reference's v - c*d (k = 1) or -(c*d)
+                        const float tx = __fmul_rn(fabsf(gx[k]), __fsub_rn(p[j][k], pu));
+                        const float ty = __fmul_rn(fabsf(gy[k]), __fsub_rn(p[j][k], pl));
+                        vx[j][k] = __fmaf_rn(signFlag(gx[k]), vx[j][k], -tx);
+                        vy[j][k] = __fmaf_rn(signFlag(gy[k]), vy[j][k], -ty);
+                    }
+                }
+            }
+        }
+
+        template <int NW, int R>
+        struct Smem
+        {
+            static constexpr int TR = NW * R;
+            static constexpr size_t offVxTop = 0;
+            static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
+            static constexpr size_t offCoef = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);        // [3][TR][32] float4: cP, sX, sY
+            static constexpr size_t total = offCoef + (size_t)3 * TR * 32 * sizeof(float4);
+        };
+
+        // everything of a thread that is fixed for the solve
+        struct Ctx
+        {
+            int lane, wp;
+            float C;
+            float* hist;              // sample 0 of the thread's 4 cells in its row 0 (advanced by the step loop)
+            size_t histRow;
+            uint32_t ownRows;         // bit j: row j of the thread is recorded / stored (owned, inside the alloc grid, lanes 1..30)
+            int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
+            const float* pulse;
+            const float4* cP; const float4* sX; const float4* sY;       // this thread's coefficient float4s (row stride 32), shared memory
+        };
+
+        // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised
+        template <int NW, int R, bool PAIR, bool GEN, bool TRACK>
+        __device__ __forceinline__ void stepLoop(Ctx& X, const int t0, const int nsteps, float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
+                                                 float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
+        {
+            const int lane = X.lane, wp = X.wp;
+            #pragma unroll 1
+            for (int step = 0; step < nsteps; ++step)
+            {
+                // ---- pressure sub-step (FDTD.cpp:125-141)
+                pressureStep<R, GEN>(p, vx, vy, sVxTop[wp + 1][lane], X.C, X.cP);
+                sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+                phaseSync<NW, PAIR>(wp);
+                // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
+                velocityStep<R, GEN>(p, vx, vy, sPBot[wp][lane], X.C, X.sX, X.sY);
+                // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if ((X.ownRows >> j) & 1u)
+                        __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                X.hist += kHistChunkDefault;
+                if (TRACK)
+                {
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                    {
+                        activity |= __float_as_uint(p[j][0]) | __float_as_uint(p[j][1]);
+                        activity |= __float_as_uint(p[j][2]) | __float_as_uint(p[j][3]);
+                    }
+                }
+                if (X.sj >= 0)
+                {
+                    // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
+                    const float add = __ldg(X.pulse + t0 + step);
+                    const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
+                    const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if (j == X.sj)
+                        {
+                            p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
+                            p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
+                        }
+                }
+                if (step + 1 < nsteps)
+                {
+                    sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                    phaseSync<NW, PAIR>(wp);            // also the write-after-read fence of sPBot
+                }
+            }
+        }
+
+        template <int NW, int R, int MINB>
+        __global__ void __launch_bounds__(NW * 32, MINB)
+        residentKernel(const Layout L, const Args A)
+        {
+            using SM = Smem<NW, R>;
+            constexpr int TR = SM::TR;
+            constexpr bool PAIR = (MINB == 1) && (NW <= 16);
+            extern __shared__ __align__(128) unsigned char smemRaw[];
+            float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
+            float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
+            float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);
+
+            const int lane = threadIdx.x & 31;
+            const int wp = threadIdx.x >> 5;
+            const int tps = A.tilesPerSource;
+            const int sLocal = blockIdx.x / tps;
+            const int tile = blockIdx.x - sLocal * tps;
+            const int s = A.s0 + sLocal;
+            const int ty = tile / L.tiles_x, tx = tile - ty * L.tiles_x;
+            const int rBase = ty * L.valid_rows - kTileK + wp * R;
+            const int cBase = tx * kValidCols - kGuardCols + lane * 4;
+            const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
+            const size_t src0 = (size_t)s * L.plane + cell0;
+
+            if (wp == 0)
+            {
+                sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const bool general = A.mode[(size_t)tile * 32 + wp] != 0u;
+            if (general)
+            {
+                // this thread's coefficient float4s, read back only by itself: no synchronisation needed
+                #pragma unroll
+                for (int f = 0; f < 3; ++f)
+                {
+                    const float* plane = (f == 0 ? A.cP : (f == 1 ? A.sX : A.sY)) + cell0;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        sCoef[((size_t)f * TR + wp * R + j) * 32 + lane] = __ldg(reinterpret_cast<const float4*>(plane + (size_t)j * L.pitch));
+                }
+            }
+            __syncthreads();
+
+            // ---- row / lane classes of this thread, fixed for the solve
+            uint32_t haloRows = 0u, ownRows = 0u, stripRows = 0u;
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+            {
+                const int tr = wp * R + j, r = rBase + j;
+                const bool halo = tr < kTileK || tr >= TR - kTileK;
+                // the padding row r == gx may be the first halo row of the last tile row (tiles cover gx rows): it depends only on the
+                // owned row gx - 1 of the same step, so it is always current there and is recorded / stored with the owned rows
+                const bool owned = (!halo && r < L.rows) || (halo && tr >= TR - kTileK && r == L.gx);
+                if (halo) haloRows |= 1u << j;
+                if (owned) ownRows |= 1u << j;
+                if (owned && (tr < 2 * kTileK || tr >= TR - 2 * kTileK)) stripRows |= 1u << j;
+            }
+            const bool haloLane = lane == 0 || lane == 31;
+            const bool stripLane = lane == 1 || lane == 30;
+            if (haloLane || cBase >= L.cols) ownRows = 0u;
+            const uint32_t loadRows = haloLane ? ((1u << R) - 1u) : haloRows;          // rows reloaded from the state planes before every pass
+            const uint32_t storeRows = ownRows & (stripLane ? ((1u << R) - 1u) : stripRows);   // rows a neighbour reads: written after every pass
+
+            // neighbours: lane i < 9 (i != 4) watches tile (tx + i%3 - 1, ty + i/3 - 1)
+            const int* watch = nullptr;
+            {
+                const int nx = tx + lane % 3 - 1, ny = ty + lane / 3 - 1;
+                if (lane < 9 && lane != 4 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y)
+                    watch = A.flags + (size_t)s * tps + (size_t)ny * L.tiles_x + nx;
+            }
+            int* const myFlag = A.flags + (size_t)s * tps + tile;
+
+            Ctx X;
+            X.lane = lane; X.wp = wp; X.C = A.courant;
+            X.hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
+                   + ((ptrdiff_t)(cBase >> 7) * L.T) * kHistChunkDefault + (cBase & 127);
+            X.histRow = L.hist_row;
+            X.ownRows = ownRows;
+            const SourceParams sp = A.src[s];
+            {
+                const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
+                const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
+                X.sj = (hasSrc && !sp.dead) ? sj : -1; X.sk = sk;
+            }
+            X.pulse = A.pulse;
+            X.cP = sCoef + (size_t)(wp * R) * 32 + lane;
+            X.sX = X.cP + (size_t)TR * 32;
+            X.sY = X.cP + (size_t)2 * TR * 32;
+
+            float p[R][4], vx[R][4], vy[R][4];
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) { p[j][k] = 0.f; vx[j][k] = 0.f; vy[j][k] = 0.f; }
+
+            int firstGen = kNeverActive;          // first pass in which this warp's block recorded anything but zeros
+            #pragma unroll 1
+            for (int g = 0; g < A.numGen; ++g)
+            {
+                const int t0 = g * kTileK;
+                const int nsteps = min(kTileK, A.T - t0);
+                if (g > 0)
+                {
+                    // ---- warp 0 waits until every neighbour has finished pass g - 1 (its lanes watch one neighbour each); the CTA
+                    //      barrier hands the acquire on to the other warps, which then reload the halo ring from buffer g & 1
+                    int ok = 1;
+                    if (wp == 0)
+                    {
+                        unsigned spins = 0;
+                        while (true)
+                        {
+                            const bool ready = !watch || loadAcquire(watch) >= g;
+                            if (__all_sync(0xffffffffu, ready)) break;
+                            __nanosleep(20);
+                            ++spins;
+                            bool giveUp = false;
+                            if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)A.abortFlag;
+                            if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(A.abortFlag, 1); ok = 0; break; }
+                        }
+                    }
+                    if (!__syncthreads_and(ok)) break;            // uniform: a dependency wait timed out (pvc_synchronize reports it)
+                    if (loadRows)
+                    {
+                        const float* gp = ((g & 1) ? A.p1 : A.p0) + src0;
+                        const float* gx = ((g & 1) ? A.vx1 : A.vx0) + src0;
+                        const float* gy = ((g & 1) ? A.vy1 : A.vy0) + src0;
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            if ((loadRows >> j) & 1u)
+                            {
+                                const float4 a = __ldcg(reinterpret_cast<const float4*>(gp + (size_t)j * L.pitch));
+                                const float4 b = __ldcg(reinterpret_cast<const float4*>(gx + (size_t)j * L.pitch));
+                                const float4 c = __ldcg(reinterpret_cast<const float4*>(gy + (size_t)j * L.pitch));
+                                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+                            }
+                    }
+                }
+                sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                phaseSync<NW, PAIR>(wp);
+
+                uint32_t activity = 0u;
+                if (firstGen == kNeverActive)
+                {
+                    if (general) stepLoop<NW, R, PAIR, true, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    else stepLoop<NW, R, PAIR, false, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    const bool hot = ((activity & 0x7fffffffu) != 0u) && !haloLane;
+                    if (__any_sync(0xffffffffu, hot)) firstGen = g;
+                }
+                else
+                {
+                    if (general) stepLoop<NW, R, PAIR, true, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    else stepLoop<NW, R, PAIR, false, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                }
+
+                // ---- hand the strips (last pass: every owned cell -- the final state) to buffer (g + 1) & 1
+                const bool lastPass = g + 1 == A.numGen;
+                const uint32_t outRows = lastPass ? ownRows : storeRows;
+                if (outRows)
+                {
+                    if (lastPass && sp.dead && A.T == t0 + nsteps)
+                    {
+                        // the reference injects the last pulse sample even into a wall / padding cell, where nothing ever reads it
+                        // again (FDTD.cpp:234): it only shows in the final state
+                        const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
+                        if (sj >= 0 && sj < R && sk >= 0 && sk < 4)
+                        {
+                            const float add = __ldg(A.pulse + A.T - 1);
+                            #pragma unroll
+                            for (int j = 0; j < R; ++j)
+                                #pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (j == sj && k == sk) p[j][k] = __fadd_rn(p[j][k], add);
+                        }
+                    }
+                    float* gp = ((g & 1) ? A.p0 : A.p1) + src0;
+                    float* gx = ((g & 1) ? A.vx0 : A.vx1) + src0;
+                    float* gy = ((g & 1) ? A.vy0 : A.vy1) + src0;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        if ((outRows >> j) & 1u)
+                        {
+                            __stcg(reinterpret_cast<float4*>(gp + (size_t)j * L.pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+                            __stcg(reinterpret_cast<float4*>(gx + (size_t)j * L.pitch), make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]));
+                            __stcg(reinterpret_cast<float4*>(gy + (size_t)j * L.pitch), make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]));
+                        }
+                }
+                // every warp has stored its strips and finished reading the exchange rows: publish pass g.  (A CTA barrier, not
+                // per-warp arrivals on the counter: neighbour-only synchronisation lets the first warp of a 20-warp tile run up
+                // to two passes ahead of the last one, which a count could not tell from two warps of the same pass.)
+                __syncthreads();
+                if (threadIdx.x == 0) storeRelease(myFlag, g + 1);
+            }
+            if (lane == 0 && firstGen != kNeverActive && A.firstActive)
+                A.firstActive[((size_t)s * tps + tile) * 32 + wp] = firstGen;
+        }
+
+        // ---- linear-form coefficient planes from the wall plane (see the header) ------------------------------------
+        __global__ void buildLinearKernel(const Layout L, const float courant, const float* __restrict__ w,
+                                          float* __restrict__ cP, float* __restrict__ sX, float* __restrict__ sY)
+        {
+            const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= L.plane) return;
+            const int r = (int)(i / L.pitch) - kGuardRows, c = (int)(i % L.pitch) - kGuardCols;
+            const bool inRows = (r >= 0) && (r < L.gx), inCols = (c >= 0) && (c < L.gy);
+            const float wSelf = w[i];
+            const bool air = inRows && inCols && __float_as_uint(wSelf) == kAirBits;
+            float x = 0.f, y = 0.f;
+            if (inCols && r >= 0 && r <= L.gx)
+            {
+                if (r == 0 || r == L.gx) x = 1.f;                        // vx = -p (FDTD.cpp:208) / vx = p_up (FDTD.cpp:209)
+                else
+                {
+                    const float wUp = w[i - L.pitch];
+                    const bool airUp = __float_as_uint(wUp) == kAirBits;
+                    x = air ? (airUp ? -courant : wUp) : (airUp ? wSelf : 0.f);
+                }
+            }
+            if (inRows && c >= 0 && c <= L.gy)
+            {
+                if (c == 0 || c == L.gy) y = 1.f;                        // vy = -p (FDTD.cpp:220) / vy = p_left (FDTD.cpp:221)
+                else
+                {
+                    const float wLeft = w[i - 1];
+                    const bool airLeft = __float_as_uint(wLeft) == kAirBits;
+                    y = air ? (airLeft ? -courant : wLeft) : (airLeft ? wSelf : 0.f);
+                }
+            }
+            cP[i] = air ? courant : 0.f;
+            sX[i] = x;
+            sY[i] = y;
+        }
+
+        __global__ void markDeadSourcesKernel(const Layout L, const float* __restrict__ w, SourceParams* __restrict__ src, int n)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= n) return;
+            const int r = src[i].cell_r, c = src[i].cell_c;
+            const bool interior = r >= 0 && c >= 0 && r < L.gx && c < L.gy;
+            src[i].dead = (interior && __float_as_uint(w[cellIndex(L, r, c)]) == kAirBits) ? 0 : 1;
+        }
+
+        template <int NW, int R, int MINB>
+        static int capacity(int device)
+        {
+            static int cached[64] = {};
+            int& c = cached[device & 63];
+            if (c) return c;
+            const size_t smem = Smem<NW, R>::total;
+            if (cudaFuncSetAttribute(residentKernel<NW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+            int perSm = 0, sms = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, residentKernel<NW, R, MINB>, NW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+            c = perSm * sms;
+            return c;
+        }
+
+        template <int NW, int R, int MINB>
+        static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
+        {
+            const Layout& L = s->L;
+            if (t0 != 0 || s->cur != 0) { setError("resident step kernel: must start at step 0"); return PVC_ERR_INVALID; }
+            if (!hist || !s->lin[0] || !s->resFlags) { setError("resident step kernel: history / coefficient planes missing"); return PVC_ERR_INVALID; }
+            if (L.hist_chunk != kHistChunkDefault || L.tile_rows != NW * R) { setError("resident step kernel: layout does not match the variant"); return PVC_ERR_INVALID; }
+            const int tps = L.tiles_x * L.tiles_y;
+            const int cap = capacity<NW, R, MINB>(s->device);
+            if (cap < tps) { setError("resident step kernel: %d tiles per source exceed the %d co-resident CTAs of this device", tps, cap); return PVC_ERR_INVALID; }
+            const int perLaunch = cap / tps;
+            const int gens = (t1 + kTileK - 1) / kTileK;
+            cudaMemsetAsync(s->resFlags, 0, sizeof(int) * (size_t)tps * nsrc, s->stream);
+            cudaMemsetAsync(s->tileCounters, 0, sizeof(int), s->stream);            // slot 0 of the pool is the abort flag
+            Args A;
+            A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
+            A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
+            A.hist = hist; A.mode = s->slowMask; A.cP = s->lin[0]; A.sX = s->lin[1]; A.sY = s->lin[2];
+            A.firstActive = s->firstActive; A.src = s->src; A.pulse = s->pulse;
+            A.flags = s->resFlags; A.abortFlag = s->tileCounters;
+            A.tilesPerSource = tps; A.numGen = gens; A.T = t1; A.courant = s->cfg.courant;
+            Layout Lc = L;
+            for (int s0 = 0; s0 < nsrc; s0 += perLaunch)
+            {
+                A.s0 = s0; A.nsrc = (nsrc - s0 < perLaunch) ? (nsrc - s0) : perLaunch;
+                void* params[2] = { &Lc, &A };
+                // cooperative launch: fails instead of deadlocking if the CTAs could not all be resident
+                const cudaError_t e = cudaLaunchCooperativeKernel((const void*)residentKernel<NW, R, MINB>, dim3((unsigned)(tps * A.nsrc)), dim3(NW * 32), params,
+                                                                  Smem<NW, R>::total, s->stream);
+                if (e != cudaSuccess) { setError("resident step kernel launch (%d CTAs): %s", tps * A.nsrc, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+                *launches += 1;
+            }
+            s->cur = gens & 1;
+            s->checkAbort = 1;
+            return PVC_OK;
+        }
+    }
+
+    int launchResidentSteps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches)
+    {
+        switch (variant)
+        {
+            case 60: return res::launch<8, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 61: return res::launch<10, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 62: return res::launch<12, 4, 2>(s, nsrc, t0, t1, hist, launches);
+            case 63: return res::launch<16, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 64: return res::launch<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            default: setError("resident step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
+        }
+    }
+
+    int residentCapacity(int variant, int device)
+    {
+        switch (variant)
+        {
+            case 60: return res::capacity<8, 4, 2>(device);
+            case 61: return res::capacity<10, 4, 2>(device);
+            case 62: return res::capacity<12, 4, 2>(device);
+            case 63: return res::capacity<16, 4, 1>(device);
+            case 64: return res::capacity<20, 4, 1>(device);
+            default: return 0;
+        }
+    }
+
+    int rebuildResidentDescriptors(pvc_solver* s, int variant)
+    {
+        (void)variant;
+        if (!s->lin[0]) { setError("resident step kernel: coefficient planes not allocated"); return PVC_ERR_INVALID; }
+        res::buildLinearKernel<<<(unsigned)((s->L.plane + 255) / 256), 256, 0, s->stream>>>(s->L, s->cfg.courant, s->w, s->lin[0], s->lin[1], s->lin[2]);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("linear coefficient launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    int markDeadSources(pvc_solver* s, int n)
+    {
+        res::markDeadSourcesKernel<<<(n + 63) / 64, 64, 0, s->stream>>>(s->L, s->w, s->src, n);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("dead-source launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+}

@@ -1239,7 +1239,9 @@ namespace pvc
             A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
             A.hist = hist;
+#ifdef PVC_TUNING
             { static const char* dbg = getenv("PVC_DEBUG_NOHIST"); if (dbg) A.hist = nullptr; }      // debug: memory-floor probe (results invalid)
+#endif
             if (TS || SO) { rc = buildStoreMaps(s, TS ? A.hist : nullptr, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
             A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder; A.firstActive = s->firstActive;
             A.src = s->src; A.pulse = s->pulse;
@@ -1249,18 +1251,26 @@ namespace pvc
             {
                 // sources per group: as many as keep both ping-pong copies of the group's state (2 x 12 B per cell) inside
                 // ~85 MB of the 126 MB L2, groups balanced; the history stream is written evict-first and does not compete
-                static const char* eg = getenv("PVC_GROUP_SRC"); static const char* ec = getenv("PVC_GROUP_GENS");
                 const double perSource = 24.0 * (double)L.plane;
                 int maxSg = (int)(85.0e6 / perSource); if (maxSg < 1) maxSg = 1;
                 const int groups = (nsrc + maxSg - 1) / maxSg;
                 A.srcGroup = (nsrc + groups - 1) / groups;
                 A.genChunk = 16;
-                { static const char* ef = getenv("PVC_EARLY_FETCH"); A.earlyFetch = ef ? atoi(ef) : 2; }
-                { static const char* sp = getenv("PVC_SLOW_POLL"); A.slowPathPoll = sp ? atoi(sp) : 1; }
-                { static const char* lr = getenv("PVC_LATE_RELEASE"); A.lateRelease = lr ? atoi(lr) : 0; }
-                { static const char* fm = getenv("PVC_FENCE_MODE"); A.fenceMode = fm ? atoi(fm) : 0; }
+                // protocol knobs, fixed in the release build (the measured optimum, profiles/r01_variants.txt); a tuning build
+                // (make EXTRA=-DPVC_TUNING) reads them from the environment
+                A.earlyFetch = 2; A.slowPathPoll = 1; A.lateRelease = 0; A.fenceMode = 0; A.tsDebug = 0;
                 A.debug = nullptr;
-                { static const char* td = getenv("PVC_TS_DEBUG"); A.tsDebug = td ? atoi(td) : 0; }
+#ifdef PVC_TUNING
+                static const char* eg = getenv("PVC_GROUP_SRC"); static const char* ec = getenv("PVC_GROUP_GENS");
+                { static const char* ef = getenv("PVC_EARLY_FETCH"); if (ef) A.earlyFetch = atoi(ef); }
+                { static const char* sp = getenv("PVC_SLOW_POLL"); if (sp) A.slowPathPoll = atoi(sp); }
+                { static const char* lr = getenv("PVC_LATE_RELEASE"); if (lr) A.lateRelease = atoi(lr); }
+                { static const char* fm = getenv("PVC_FENCE_MODE"); if (fm) A.fenceMode = atoi(fm); }
+                { static const char* td = getenv("PVC_TS_DEBUG"); if (td) A.tsDebug = atoi(td); }
+                if (eg && atoi(eg) > 0) A.srcGroup = atoi(eg);
+                if (ec && atoi(ec) > 0) A.genChunk = atoi(ec);
+#endif
+#ifdef PVC_WS2_TRACE
                 {
                     static const char* dbg = getenv("PVC_DEBUG_COUNTERS");
                     static unsigned long long* counters = nullptr;
@@ -1292,16 +1302,6 @@ namespace pvc
                                         sum[7] += (double)a[6] - (double)prev[6];     // tile period
                                         ++cnt;
                                     }
-                                for (int c = 5; c < 7; ++c)
-                                {
-                                    const unsigned long long base = h[4 + ((size_t)c * kTraceTiles + 10) * kTraceSlots + 4];
-                                    for (int k = 10; k < 16; ++k)
-                                    {
-                                        const unsigned long long* a = h + 4 + ((size_t)c * kTraceTiles + k) * kTraceSlots;
-                                        fprintf(stderr, "[ws2 raw] cta %d tile %d: P gotempty %6lld issue %6lld fetched %6lld published %6lld | C wait %6lld ready %6lld loopend %6lld stored %6lld\n", c, k,
-                                                (long long)(a[7] - base), (long long)(a[0] - base), (long long)(a[1] - base), (long long)(a[2] - base), (long long)(a[3] - base), (long long)(a[4] - base), (long long)(a[5] - base), (long long)(a[6] - base));
-                                    }
-                                }
                                 if (cnt) fprintf(stderr, "[ws2 trace] n=%ld  issue->ready %.0f  wait-on-full %.0f  drain+steps %.0f  stores %.0f | prevReady->issue %.0f  fetchNext %.0f  publishPrev %.0f | period %.0f ns\n",
                                                  cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt, sum[6] / cnt, sum[7] / cnt);
                             }
@@ -1312,8 +1312,7 @@ namespace pvc
                         A.debug = counters;
                     }
                 }
-                if (eg && atoi(eg) > 0) A.srcGroup = atoi(eg);
-                if (ec && atoi(ec) > 0) A.genChunk = atoi(ec);
+#endif
                 if (A.srcGroup > nsrc) A.srcGroup = nsrc;
             }
             int k = 1;
@@ -1347,6 +1346,9 @@ namespace pvc
     {
         switch (variant)
         {
+            case 47: return ws2::launch<14, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+            case 50: return ws2::launch<8, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
+#ifdef PVC_ALL_VARIANTS
             case 39: return ws2::launch<14, 4, 2>(s, nsrc, t0, t1, hist, launches);
             case 40: return ws2::launch<15, 4, 1>(s, nsrc, t0, t1, hist, launches);
             case 41: return ws2::launch<30, 2, 1>(s, nsrc, t0, t1, hist, launches);
@@ -1355,20 +1357,22 @@ namespace pvc
             case 44: return ws2::launch<10, 8, 1>(s, nsrc, t0, t1, hist, launches);
             case 45: return ws2::launch<11, 6, 1>(s, nsrc, t0, t1, hist, launches);
             case 46: return ws2::launch<12, 6, 1>(s, nsrc, t0, t1, hist, launches);
-            case 47: return ws2::launch<14, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 48: return ws2::launch<15, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 49: return ws2::launch<14, 4, 1, false, true, true>(s, nsrc, t0, t1, hist, launches);
-            case 50: return ws2::launch<8, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 51: return ws2::launch<10, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 52: return ws2::launch<12, 4, 1, false, true>(s, nsrc, t0, t1, hist, launches);
             case 53: return ws2::launch<12, 5, 1, false, true>(s, nsrc, t0, t1, hist, launches);
-            default: setError("ws2 step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
+#endif
+            default: setError("ws2 step kernel: variant %d is not compiled into this build", variant); return PVC_ERR_INVALID;
         }
     }
     int rebuildWs2Descriptors(pvc_solver* s, int variant)
     {
         switch (variant)
         {
+            case 47: return ws2::buildMask<14, 4>(s);
+            case 50: return ws2::buildMask<8, 4>(s);
+#ifdef PVC_ALL_VARIANTS
             case 39: return ws2::buildMask<14, 4>(s);
             case 40: return ws2::buildMask<15, 4>(s);
             case 41: return ws2::buildMask<30, 2>(s);
@@ -1377,13 +1381,12 @@ namespace pvc
             case 44: return ws2::buildMask<10, 8>(s);
             case 45: return ws2::buildMask<11, 6>(s);
             case 46: return ws2::buildMask<12, 6>(s);
-            case 47: return ws2::buildMask<14, 4>(s);
             case 48: return ws2::buildMask<15, 4>(s);
             case 49: return ws2::buildMask<14, 4>(s);
-            case 50: return ws2::buildMask<8, 4>(s);
             case 51: return ws2::buildMask<10, 4>(s);
             case 52: return ws2::buildMask<12, 4>(s);
             case 53: return ws2::buildMask<12, 5>(s);
+#endif
             default: return PVC_OK;
         }
     }

@@ -91,7 +91,7 @@ def test_golden_vectors(pv, name):
     gpu.close()
 
 
-@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 7), (0, 8), (0, 9), (0, 10), (0, 11), (0, 12), (0, 13), (0, 14), (0, 15), (0, 16), (0, 18), (0, 20), (0, 22), (0, 23), (0, 24), (0, 25), (0, 26), (0, 27), (0, 28), (0, 29), (0, 30), (0, 31), (0, 32), (0, 33), (0, 34), (0, 35), (0, 36), (0, 37), (0, 38), (0, 39), (0, 40), (0, 41), (0, 42), (0, 43), (0, 44), (0, 45), (0, 47), (0, 48), (0, 49), (0, 50), (0, 51), (0, 52), (0, 53)])
+@pytest.mark.parametrize("step_kernel,variant", [(1, 0), (0, 0), (0, 18), (0, 47), (0, 50), (0, 60), (0, 61), (0, 62), (0, 63), (0, 64)])
 def test_every_step_kernel_variant_matches_oracle(pv, scenes, step_kernel, variant):
     gpu, ora, Ls = run_pair(pv, scenes, "FloorPlanScene", n=250, T=301, step_kernel=step_kernel, variant=variant)
     res, dly = gpu.solve(Ls)
@@ -473,65 +473,62 @@ def test_error_paths(pv):
     assert "invalid" in str(e.value)
 
 
-def _dsp_gains(rt60, wet):
-    """PlaneverbDSP's RT60 -> three reverb-bus gains (PlaneverbDSP/src/PvDSPContext.cpp:165-229), float32."""
-    f = np.float32
-    T1, T2, T3, TS = f(0.5), f(1.0), f(3.0), f(0.1)
-    term = lambda t: np.power(f(10.0), f(-3.0) * TS / t).astype(np.float32)
-    t2 = term(rt60)
-    a_mid = wet * (term(T2) - t2) / (term(T2) - term(T1))
-    c_mid = wet * (term(T3) - t2) / (term(T3) - term(T2))
-    A = np.where(rt60 > T2, 0, np.where(rt60 < T1, 1, a_mid))
-    B = np.where(rt60 < T1, 0, np.where(rt60 > T2, c_mid, wet - a_mid))
-    Cc = np.where(rt60 > T3, 1, np.where(rt60 < T2, 0, wet - c_mid))
-    return np.stack([A, B, Cc]).astype(np.float32)
-
-
-def test_outputs_are_acceptable_to_the_dsp_consumer(pv, scenes):
-    """PlaneverbDSP only renders a source when lowpass is in [20, 20000] Hz, obstructionGain > 0 and
-    direction != 0 (PvDSPContext.cpp:258-262), then maps rt60/wetGain onto three reverb buses. On an open scene every
-    cell with an onset must pass those gates, and the bus gains computed from the device outputs must equal the ones
-    computed from the reference's golden outputs."""
-    meta, z = common.load_golden("singlewall_95_res375")
-    gpu = pv.Scene(meta["size"], meta["size"], meta["resolution"], T=meta["T_override"])
-    for b in common.golden_boxes(z):
-        gpu.add_aabb(*b)
-    res, dly = gpu.solve([meta["listener"]])
-    valid = (dly[0] < 3e38) & ~common.reference_clamped(meta, z["delay"], gpu.D)
-    r = res[0][valid]
-    assert valid.sum() > 8000
-    assert ((r[:, 3] >= 20.0) & (r[:, 3] <= 20000.0)).all()
-    assert (r[:, 0] > 0).all()
-    lr, lc = int(np.float32(meta["listener"][0]) / gpu.dx), int(np.float32(meta["listener"][2]) / gpu.dx)
-    nonzero_dir = (r[:, 4] != 0) | (r[:, 5] != 0)
-    assert (~nonzero_dir).sum() <= 1                    # only a cell whose walk ends exactly on the listener position
-    finite = np.isfinite(r[:, 2]) & (r[:, 2] > 0)
-    g_dev = _dsp_gains(r[finite, 2], r[finite, 1])
-    g_ref = _dsp_gains(z["results"][valid][finite, 2], z["results"][valid][finite, 1])
-    assert np.array_equal(g_dev.view(np.uint32), g_ref.view(np.uint32))
-    gpu.close()
+def test_outputs_through_the_reference_dsp_consumer(pv, scenes):
+    """the consumer of the hot path's outputs is PlaneverbDSP.  The UNMODIFIED reference consumer
+    (PlaneverbDSP/src/PvDSPContext.cpp, built into oracle/_ref/libpvdspref.so by oracle/dspdriver/Makefile) renders a test
+    signal with the device's PlaneverbOutput of every sampled cell and with the reference's own golden output of the same
+    cell: its validity gates (lowpass in [20, 20000] Hz, obstructionGain > 0, direction != 0, :258-262) must decide alike, and
+    the dry bus and the three reverb buses (FindGainA/B/C, :165-229; Butterworth low-pass, Lowpass.cpp) must come out
+    bit-identical wherever the low-pass cutoffs are (the cutoff may differ by 1 ulp: powf), else within 1e-5."""
+    from oracle import pvdspref
+    assert pvdspref.available(), "oracle/_ref/libpvdspref.so missing: run __graft_entry__.build() where /root/reference exists"
+    audio = pvdspref.test_signal(256)
+    for name in ("singlewall_95_res375", "floorplan_70"):
+        meta, z = common.load_golden(name)
+        gpu = pv.Scene(meta["size"], meta["size"], meta["resolution"], T=meta["T_override"])
+        for b in common.golden_boxes(z):
+            gpu.add_aabb(*b)
+        res, dly = gpu.solve([meta["listener"]])
+        valid = (dly[0] < 3e38) & ~common.reference_clamped(meta, z["delay"], gpu.D)
+        cells = np.nonzero(valid)[0]
+        cells = cells[:: max(1, cells.size // 400)]
+        lx, lz = meta["listener"][0], meta["listener"][2]
+        accepted = exact = 0
+        for cell in cells:
+            r, c = divmod(int(cell), gpu.gy)
+            pos = ((r + 0.5) * float(gpu.dx), (c + 0.5) * float(gpu.dx))
+            out = gpu.lookup((pos[0], 0.0, pos[1]))                       # Analyzer::GetResponseResult through the C ABI
+            assert out is not None and common.bit_equal(out, res[0][cell]).all()
+            dev = pvdspref.render(out, pos, (lx, lz), audio)
+            ref = pvdspref.render(z["results"][cell], pos, (lx, lz), audio)
+            assert (np.abs(dev).sum() > 0) == (np.abs(ref).sum() > 0), f"{name} cell {cell}: the DSP gates disagree"
+            if np.abs(ref).sum() > 0:
+                accepted += 1
+                if out[3] == z["results"][cell][3]:
+                    assert np.array_equal(dev.view(np.uint32), ref.view(np.uint32)), f"{name} cell {cell}: DSP buses differ"
+                    exact += 1
+                else:
+                    assert np.allclose(dev, ref, rtol=1e-5, atol=1e-7), f"{name} cell {cell}: DSP buses differ beyond the 1-ulp cutoff"
+        assert accepted > 0.9 * cells.size and exact > 0.9 * accepted, (name, cells.size, accepted, exact)
+        gpu.close()
 
 
 @pytest.mark.parametrize("scene,n,T", [("HugeRoom", 400, 900), ("FloorPlanScene", 300, 700), (None, 257, 600)])
 def test_pointer_jumping_direction_equals_the_sequential_walk(pv, scenes, scene, n, T):
     """Analyzer::EncodeListenerDirection (Analyzer.cpp:340-431): the default device path resolves every walk by
-    pointer jumping over a link array; PVC_WALK=sequential runs the reference's walk one thread per cell.  Both must
+    pointer jumping over a link array; pvc_set_walk_mode(1) runs the reference's walk one thread per cell.  Both must
     give the same direction for every cell (and the oracle agrees, see the other parity tests)."""
-    import os
     size, scale = common.scaled_config(n)
     listeners = common.listeners_for(2, scale)
     outs = []
-    for mode in ("jump", "sequential"):
-        os.environ["PVC_WALK"] = mode
-        try:
-            gpu = pv.Scene(size, size, 275, T=T, max_sources=2)
-            for b in (common.boxes_of(scenes, scene, scale) if scene else []):
-                gpu.add_aabb(*b)
-            res, dly = gpu.solve(listeners)
-            outs.append((np.array(res, copy=True), np.array(dly, copy=True)))
-            gpu.close()
-        finally:
-            os.environ.pop("PVC_WALK", None)
+    for sequential in (False, True):
+        gpu = pv.Scene(size, size, 275, T=T, max_sources=2)
+        gpu.set_walk_mode(sequential)
+        for b in (common.boxes_of(scenes, scene, scale) if scene else []):
+            gpu.add_aabb(*b)
+        res, dly = gpu.solve(listeners)
+        outs.append((np.array(res, copy=True), np.array(dly, copy=True)))
+        gpu.close()
     (ra, da), (rb, db) = outs
     assert np.array_equal(da, db)
     assert common.bit_equal(ra, rb).all()

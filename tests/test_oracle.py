@@ -229,3 +229,29 @@ def test_device_logf_fma_form_is_exhaustively_exact(tmp_path):
     for const in re.findall(r"-?0x1\.[0-9a-f]+p[+-]\d+", c):
         assert const in cu, const
     assert "0x3f330000u) >> 19) + kLogf33Bias" in cu and "kLogf33Bias = 7" in cu and ">> 19) + 7" in c
+
+
+def test_reference_dsp_consumer_accepts_the_golden_outputs():
+    """the unmodified PlaneverbDSP (oracle/_ref/libpvdspref.so) renders the reference's golden outputs: cells
+    with an onset pass its validity gates (PvDSPContext.cpp:258-262) and drive the dry bus and, by RT60 (:165-229), the
+    matching reverb buses; an all-zero PlaneverbOutput (a cell without an onset) is rejected and leaves silence."""
+    from oracle import pvdspref
+    if not pvdspref.available():
+        pytest.skip("oracle/_ref/libpvdspref.so not built (needs /root/reference)")
+    meta, z = common.load_golden("singlewall_95_res375")
+    audio = pvdspref.test_signal(256)
+    valid = np.nonzero(z["delay"] < 3e38)[0]
+    lx, lz = meta["listener"][0], meta["listener"][2]
+    n_ok = 0
+    for cell in valid[::97]:
+        out = z["results"][cell]
+        bufs = pvdspref.render(out, (3.0, 4.0), (lx, lz), audio)
+        gates = (20.0 <= out[3] <= 20000.0) and out[0] > 0 and (out[4] != 0 or out[5] != 0)
+        assert (np.abs(bufs[0]).sum() > 0) == gates
+        if gates:
+            n_ok += 1
+            rt60 = out[2]
+            assert (np.abs(bufs[1]).sum() > 0) == (rt60 <= 1.0)          # bus A: 0.5 s reverb, silent above T_ER_2
+            assert (np.abs(bufs[3]).sum() > 0) == (rt60 >= 1.0)          # bus C: 3 s reverb, silent below T_ER_2
+    assert n_ok > 50
+    assert np.abs(pvdspref.render(np.zeros(8, np.float32), (3.0, 4.0), (lx, lz), audio)).sum() == 0

@@ -44,9 +44,15 @@ PVU_EXPORT void PVU_CC PlaneverbUpdateGeometry(int id, float posX, float posY, f
 PVU_EXPORT void PVU_CC PlaneverbRemoveGeometry(int id);
 PVU_EXPORT void PVU_CC PlaneverbSetListenerPosition(float x, float y, float z);
 
-/* extension (not in the reference): number of completed background solve+analyse frames since Init,
- * so a host can wait for the first frame instead of polling GetOutput; and the last error text */
+/* extensions (not in the reference):
+ *   PlaneverbFramesCompleted  completed background solve+analyse frames since Init, so a host can wait for the first frame
+ *                             instead of polling GetOutput;
+ *   PlaneverbWorkerState      0 no context, 1 the acoustics thread is running, 2 stopped by Exit, -1 stopped by a device
+ *                             failure (GetOutput then keeps serving the last good frame);
+ *   PlaneverbLastError        process-wide text of the last failure, including the acoustics thread's (empty if none); the
+ *                             pointer stays valid until the calling thread asks again. */
 PVU_EXPORT unsigned long long PVU_CC PlaneverbFramesCompleted(void);
+PVU_EXPORT int PVU_CC PlaneverbWorkerState(void);
 PVU_EXPORT const char* PVU_CC PlaneverbLastError(void);
 
 #ifdef __cplusplus

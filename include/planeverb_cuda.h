@@ -173,6 +173,8 @@ PVC_API int  pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen
  * jumping over a link array, 1 = the reference's walk, one thread per start cell.  Bit-identical results; the second exists as the
  * cross-check of the first (tests/test_gpu_parity.py). */
 PVC_API int  pvc_set_walk_mode(pvc_solver* s, int sequential);
+/* the step-kernel variant this solver runs (pvc_config::reserved after "0 = auto" has been resolved; see pvc_api.cu::resolveVariant) */
+PVC_API int  pvc_step_variant(pvc_solver* s);
 /* page-locked host buffers for the result grids (plain malloc'd memory works too, just slower to copy) */
 PVC_API void* pvc_host_alloc(size_t bytes);
 PVC_API void  pvc_host_free(void* p);

@@ -10,7 +10,7 @@
  *   Analyzer                         /root/reference/ProjectPlaneverb/src/DSP/Analyzer.cpp:48-431
  * written from the semantics tables in SURVEY.md App. A/B, not from the reference text.
  *
- * PARITY PIN: tests/test_oracle_vs_reference.py checks every function here bit-for-bit (fields,
+ * PARITY PIN: tests/test_oracle.py checks every function here bit-for-bit (fields,
  * delays, all eight outputs) against the UNMODIFIED reference compiled in place into
  * oracle/_ref/libpvref.so (oracle/refdriver/Makefile) and against the committed golden vectors in
  * tests/golden/ that were captured from that build (tools/make_golden.py).  The reference itself
@@ -178,10 +178,10 @@ typedef struct
  *   acc    : optional causal accumulators over ALL alloc cells (arrays of N), windows in samples
  *            Sd (flux), D (dry), W (wet) as in Analyzer.cpp:170-173,237
  */
-void pvo_simulate(int gx, int gy, const int16_t* b, const float* R, float courant,
+static void simulate_impl(int gx, int gy, const int16_t* b, const float* R, float courant,
                   int li, const float* pulse, int T,
                   float* p, float* vx, float* vy,
-                  float* hist, float* hvx, float* hvy,
+                  float* hist, size_t histI0, size_t histCount, float* hvx, float* hvy,
                   int* onset, float* edry, float* fx, float* fy, float* wet,
                   int Sd, int D, int W)
 {
@@ -226,7 +226,7 @@ void pvo_simulate(int gx, int gy, const int16_t* b, const float* R, float couran
             vy[r * S + gy] = p[r * S + gy - 1];
         }
         /* 5. record sample t (FDTD.cpp:226-231) */
-        if (hist) memcpy(hist + (size_t)t * N, p, sizeof(float) * N);
+        if (hist) memcpy(hist + (size_t)t * histCount, p + histI0, sizeof(float) * histCount);
         if (hvx)  memcpy(hvx + (size_t)t * N, vx, sizeof(float) * N);
         if (hvy)  memcpy(hvy + (size_t)t * N, vy, sizeof(float) * N);
         if (onset)
@@ -246,6 +246,31 @@ void pvo_simulate(int gx, int gy, const int16_t* b, const float* R, float couran
         /* 6. inject after the record (FDTD.cpp:234) */
         p[li] += pulse[t];
     }
+}
+
+void pvo_simulate(int gx, int gy, const int16_t* b, const float* R, float courant,
+                  int li, const float* pulse, int T,
+                  float* p, float* vx, float* vy,
+                  float* hist, float* hvx, float* hvy,
+                  int* onset, float* edry, float* fx, float* fy, float* wet,
+                  int Sd, int D, int W)
+{
+    simulate_impl(gx, gy, b, R, courant, li, pulse, T, p, vx, vy, hist, 0, (size_t)(gx + 1) * (gy + 1), hvx, hvy,
+                  onset, edry, fx, fy, wet, Sd, D, W);
+}
+
+/* Same simulation, keeping the pressure history of alloc cells [histI0, histI0 + histCount) only (hist[t*histCount + i - histI0]):
+ * sizes whose full T*N history does not fit the host (2048 x 2048 x 4000 steps = 67 GB).  The causal accumulators cover every
+ * cell as before; pvo_encode_band then computes the anti-causal RT60 for the cells of the band. */
+void pvo_simulate_band(int gx, int gy, const int16_t* b, const float* R, float courant,
+                       int li, const float* pulse, int T,
+                       float* p, float* vx, float* vy,
+                       float* hist, long long histI0, long long histCount,
+                       int* onset, float* edry, float* fx, float* fy, float* wet,
+                       int Sd, int D, int W)
+{
+    simulate_impl(gx, gy, b, R, courant, li, pulse, T, p, vx, vy, hist, (size_t)histI0, (size_t)histCount, NULL, NULL,
+                  onset, edry, fx, fy, wet, Sd, D, W);
 }
 
 /* FreeGrid.cpp:71-110: sum p^2 of the first n samples at the probe cell, times r = (int)(1/dx)*dx.
@@ -297,12 +322,12 @@ float pvo_efree_per_r(float efree, float dx, int lX, int lY, int eX, int eY)
  * cells with an onset are written (no-onset cells keep what the caller put there, Analyzer.cpp:161-165).
  * delay: gx*gy floats. clamped: optional gx*gy bytes, 1 where onset+D >= T (reference reads out of bounds).
  */
-void pvo_encode(int gx, int gy, int T, int fs, float dx, float efree, float lx, float lz,
-                const float* hist, const int* onset, const float* edry, const float* fx,
+static void encode_impl(int gx, int gy, int T, int fs, float dx, float efree, float lx, float lz,
+                const float* histBand, size_t histI0, size_t histCount, const int* onset, const float* edry, const float* fx,
                 const float* fy, const float* wet, float* results, float* delay, uint8_t* clamped)
 {
     const int S = gy + 1;
-    const size_t N = (size_t)(gx + 1) * S;
+    const size_t N = histCount;
     const int D = (int)(PVO_DRY_GAIN_S * (float)fs);
     const int listenerX = (int)(lx * (1.f / dx));      /* Analyzer.cpp:201-202 */
     const int listenerY = (int)(lz * (1.f / dx));
@@ -339,7 +364,9 @@ void pvo_encode(int gx, int gy, int T, int fs, float dx, float efree, float lx, 
         /* wet gain (Analyzer.cpp:247) */
         out[1] = sqrtf(wet[i] / efree);
 
-        /* RT60 (Analyzer.cpp:282-326) */
+        /* RT60 (Analyzer.cpp:282-326); outside the recorded band: NaN = "not computed" */
+        if ((size_t)i < histI0 || (size_t)i >= histI0 + histCount) { out[2] = NAN; continue; }
+        const float* hist = histBand + ((size_t)i - histI0) - (size_t)i;      /* hist[k*N + i] below addresses the band */
         int start = directEnd + 1;
         int end = T - (int)(PVO_SCHROEDER_S * fs);
         int regressN = end - start;
@@ -363,6 +390,22 @@ void pvo_encode(int gx, int gy, int T, int fs, float dx, float efree, float lx, 
         float slopeDBperSec = slopeDBperSample * fs;
         out[2] = -60.f / slopeDBperSec;
     }
+}
+
+void pvo_encode(int gx, int gy, int T, int fs, float dx, float efree, float lx, float lz,
+                const float* hist, const int* onset, const float* edry, const float* fx,
+                const float* fy, const float* wet, float* results, float* delay, uint8_t* clamped)
+{
+    encode_impl(gx, gy, T, fs, dx, efree, lx, lz, hist, 0, (size_t)(gx + 1) * (gy + 1), onset, edry, fx, fy, wet, results, delay, clamped);
+}
+
+/* pvo_encode over a banded history (pvo_simulate_band): every output but RT60 for every cell, RT60 for the cells of the band,
+ * NaN elsewhere */
+void pvo_encode_band(int gx, int gy, int T, int fs, float dx, float efree, float lx, float lz,
+                     const float* hist, long long histI0, long long histCount, const int* onset, const float* edry, const float* fx,
+                     const float* fy, const float* wet, float* results, float* delay, uint8_t* clamped)
+{
+    encode_impl(gx, gy, T, fs, dx, efree, lx, lz, hist, (size_t)histI0, (size_t)histCount, onset, edry, fx, fy, wet, results, delay, clamped);
 }
 
 /* Analyzer.cpp:340-431 for every interior cell (needs all occlusion/delay values first) */

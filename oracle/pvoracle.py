@@ -36,6 +36,8 @@ def lib():
         L.pvo_remove_aabb.argtypes = [_i, _i, _f, _vp, _vp] + [_f] * 4
         L.pvo_listener_cell.argtypes = [_f, _f, _f, _vp, _vp]
         L.pvo_simulate.argtypes = [_i, _i, _vp, _vp, _f, _i, _vp, _i] + [_vp] * 11 + [_i] * 3
+        L.pvo_simulate_band.argtypes = [_i, _i, _vp, _vp, _f, _i, _vp, _i] + [_vp] * 4 + [C.c_longlong] * 2 + [_vp] * 5 + [_i] * 3
+        L.pvo_encode_band.argtypes = [_i, _i, _i, _i, _f, _f, _f, _f, _vp, C.c_longlong, C.c_longlong] + [_vp] * 8
         L.pvo_efree.argtypes = [_i, _i, _i]
         L.pvo_efree.restype = _f
         L.pvo_efree_per_r.argtypes = [_f, _f, _i, _i, _i, _i]
@@ -116,7 +118,28 @@ class OracleSim:
         lib().pvo_listener_cell(self.dx, float(listener[0]), float(listener[2]), C.byref(lr), C.byref(lc))
         return lr.value, lc.value
 
+    def generate_band(self, listener, row0, rows):
+        """generate() keeping the pressure history of alloc rows [row0, row0 + rows) only (self.hist: (T, rows * (gy + 1))): for
+        grids whose full history does not fit the host.  analyze() then yields RT60 for the interior cells of those rows and
+        NaN elsewhere; every other output is complete."""
+        N, T = self.N, self.T
+        self.p = np.zeros(N, np.float32)
+        self.vx = np.zeros(N, np.float32)
+        self.vy = np.zeros(N, np.float32)
+        self.band = (int(row0) * self.S, int(rows) * self.S)
+        self.hist = np.zeros((T, self.band[1]), np.float32)
+        self.hvx = self.hvy = None
+        self.onset = np.zeros(N, np.int32)
+        self.edry, self.fx, self.fy, self.wet = (np.zeros(N, np.float32) for _ in range(4))
+        lr, lc = self.listener_cell(listener)
+        lib().pvo_simulate_band(self.gx, self.gy, _p(self.b), _p(self.R), self.courant, lr * self.S + lc,
+                                _p(self.pulse), T, _p(self.p), _p(self.vx), _p(self.vy),
+                                _p(self.hist), self.band[0], self.band[1],
+                                _p(self.onset), _p(self.edry), _p(self.fx), _p(self.fy), _p(self.wet),
+                                self.Sd, self.D, self.W)
+
     def generate(self, listener, keep_velocity=False):
+        self.band = None
         N, T = self.N, self.T
         self.p = np.zeros(N, np.float32)
         self.vx = np.zeros(N, np.float32)
@@ -135,9 +158,14 @@ class OracleSim:
 
     def analyze(self, listener):
         lx, lz = float(listener[0]), float(listener[2])
-        lib().pvo_encode(self.gx, self.gy, self.T, self.fs, self.dx, self.efree, lx, lz,
-                         _p(self.hist), _p(self.onset), _p(self.edry), _p(self.fx), _p(self.fy), _p(self.wet),
-                         _p(self.results), _p(self.delay), _p(self.clamped))
+        if getattr(self, "band", None):
+            lib().pvo_encode_band(self.gx, self.gy, self.T, self.fs, self.dx, self.efree, lx, lz,
+                                  _p(self.hist), self.band[0], self.band[1], _p(self.onset), _p(self.edry), _p(self.fx), _p(self.fy),
+                                  _p(self.wet), _p(self.results), _p(self.delay), _p(self.clamped))
+        else:
+            lib().pvo_encode(self.gx, self.gy, self.T, self.fs, self.dx, self.efree, lx, lz,
+                             _p(self.hist), _p(self.onset), _p(self.edry), _p(self.fx), _p(self.fy), _p(self.wet),
+                             _p(self.results), _p(self.delay), _p(self.clamped))
         lib().pvo_directions(self.gx, self.gy, self.T, self.fs, self.resolution, self.dx, lx, lz,
                              _p(self.results), _p(self.delay))
 

@@ -10,7 +10,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libpvref.so")
+# PVREF_LIB selects another build of the same unmodified sources (oracle/_ref/libpvref_fast.so: the shipped Release flags,
+# timing only -- bench.py's second CPU row); the oracle proper is the strict build
+LIB_PATH = os.environ.get("PVREF_LIB") or os.path.join(_HERE, "_ref", "libpvref.so")
 
 
 def available():

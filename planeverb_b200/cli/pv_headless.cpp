@@ -76,9 +76,25 @@ int main(int argc, char** argv)
     std::vector<Planeverb::EmissionID> eids;
     for (const auto& e : emitters) eids.push_back(Planeverb::Emit(e));
 
+    // wait for n more frames; gives up when the acoustics thread has stopped (device failure) or makes no progress for 20 s
+    // (e.g. a listener outside the grid: its frames are skipped)
     auto waitFrames = [](unsigned long long n) {
         const unsigned long long start = PlaneverbFramesCompleted();
-        while (PlaneverbFramesCompleted() < start + n) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        unsigned long long seen = start;
+        auto lastProgress = std::chrono::steady_clock::now();
+        while (PlaneverbFramesCompleted() < start + n)
+        {
+            const unsigned long long now = PlaneverbFramesCompleted();
+            if (now != seen) { seen = now; lastProgress = std::chrono::steady_clock::now(); }
+            const bool stalled = std::chrono::steady_clock::now() - lastProgress > std::chrono::seconds(20);
+            if (PlaneverbWorkerState() != 1 || stalled)
+            {
+                std::fprintf(stderr, "pv_headless: no frames (%s): %s\n", stalled ? "no progress for 20 s" : "acoustics thread stopped", PlaneverbLastError());
+                Planeverb::Exit();
+                std::exit(2);
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        }
     };
     const auto t0 = std::chrono::steady_clock::now();
     waitFrames((unsigned long long)frames + 1);          // geometry queued now reaches the grid before the next solve

@@ -14,8 +14,18 @@
 //     the loop runs one frame deep, a frame's grid is copied out while the next frame is solved), so GetOutput on
 //     the game/audio thread never reads a half-written frame (the reference races by design);
 //   * the listener position and running flag are atomics / mutex-protected;
+//   * every API call works on a shared_ptr snapshot of the context taken under the context mutex, so Exit() on the game
+//     thread cannot free the result grids under a GetOutput() running on the audio thread (AudioCore.cpp:95 pattern): the
+//     last holder frees them;
+//   * a listener outside the grid (or NaN) skips the frame -- GetOutput keeps serving the last good one -- instead of
+//     indexing outside the grid as the reference does (FDTD.cpp:97-99); a DEVICE failure stops the worker, and both are
+//     reported through the process-wide PlaneverbLastError() / PlaneverbWorkerState();
+//   * PlaneverbConfig::gridWorldOffset != 0 is rejected with pv_InvalidConfig (the reference's header marks it
+//     "!!! Not supported !!!", PvTypes.h:58, and applies it inconsistently, Grid.cpp:139-142 vs 252-255);
 //   * errors thrown inside the C ABI are caught there (the reference lets enums escape extern "C").
 #include <atomic>
+#include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +56,8 @@ namespace Planeverb
             std::atomic<unsigned long long> frames{ 0 };
             std::mutex solverMutex;               // serialises device access (worker vs GetImpulseResponse)
             std::atomic<int> solverWaiters{ 0 };  // API threads waiting for the device: the worker yields to them
+            std::atomic<unsigned long long> skipped{ 0 };   // frames skipped because the listener was outside the grid
+            std::atomic<bool> listenerWarned{ false };
 
             // listener (written by the game thread, read by the worker)
             std::mutex listenerMutex;
@@ -71,11 +83,33 @@ namespace Planeverb
             // GetImpulseResponse scratch
             std::vector<Cell> irCells;
             std::vector<float> irFloats;
+
+            std::atomic<int> workerState{ 0 };    // 0 not started, 1 running, 2 stopped by Exit, -1 stopped by a device failure
+
+            void shutdown()                       // stop and join the worker (idempotent; called by Exit / Init, never by the worker)
+            {
+                running.store(false, std::memory_order_release);
+                if (worker.joinable()) worker.join();
+            }
+            ~Context()
+            {   // runs in whichever thread drops the last reference: the worker has been joined by then (Exit / Init)
+                shutdown();
+                if (scene) pvx_destroy(scene);
+                for (float* g : grid) pvc_host_free(g);
+            }
         };
 
         std::mutex g_contextMutex;
-        std::unique_ptr<Context> g_context;
-        thread_local std::string g_lastError;
+        std::shared_ptr<Context> g_context;
+
+        // process-wide error text: the worker thread's failures must reach whoever asks (PlaneverbLastError)
+        std::mutex g_errorMutex;
+        std::string g_lastError;
+        void setLastError(const std::string& text)
+        {
+            std::lock_guard<std::mutex> lock(g_errorMutex);
+            g_lastError = text;
+        }
 
         void workerLoop(Context* ctx)
         {
@@ -89,6 +123,25 @@ namespace Planeverb
                     l = ctx->listener;
                 }
                 const float xyz[3] = { l.x, l.y, l.z };
+                {
+                    // FDTD.cpp:97-99 turns the listener position into a cell without any check; outside the grid (or NaN) the
+                    // reference indexes out of bounds.  Here such a frame is skipped and the last good results stay published.
+                    bool inside = std::isfinite(l.x) && std::isfinite(l.z);
+                    if (inside)
+                    {
+                        const float fx = l.x / ctx->params.dx, fz = l.z / ctx->params.dx;
+                        inside = fx >= 0.f && fz >= 0.f && fx < (float)(ctx->params.gx + 1) && fz < (float)(ctx->params.gy + 1);
+                    }
+                    if (!inside)
+                    {
+                        if (!ctx->listenerWarned.exchange(true))
+                            setLastError("listener position outside the grid: frames are skipped until it returns (last good results stay published)");
+                        ctx->skipped.fetch_add(1, std::memory_order_release);
+                        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                        continue;
+                    }
+                    ctx->listenerWarned.store(false);
+                }
                 int rc;
                 while (ctx->solverWaiters.load(std::memory_order_acquire) > 0) std::this_thread::yield();
                 {
@@ -99,7 +152,9 @@ namespace Planeverb
                     rc = pvx_solve_pipelined(ctx->scene, xyz, 1, ctx->grid[next], nullptr);
                 }
                 if (rc != PVC_OK)
-                {   // device failure: stop publishing; GetOutput keeps serving the last good frame
+                {   // device failure: stop publishing (GetOutput keeps serving the last good frame) and say so
+                    setLastError(std::string("acoustics worker stopped: ") + pvc_last_error());
+                    ctx->workerState.store(-1, std::memory_order_release);
                     ctx->running.store(false, std::memory_order_release);
                     break;
                 }
@@ -125,34 +180,43 @@ namespace Planeverb
                 }
             }
             if (filling >= 0)
-            {   // drain the copy in flight (Exit joins this thread before it frees the buffers)
+            {   // drain the copy in flight (Exit joins this thread before the buffers can be freed)
                 std::lock_guard<std::mutex> lock(ctx->solverMutex);
-                pvx_fetch_wait(ctx->scene);
+                if (pvx_fetch_wait(ctx->scene) != PVC_OK && ctx->workerState.load() != -1)
+                {
+                    setLastError(std::string("acoustics worker: last frame failed: ") + pvc_last_error());
+                    ctx->workerState.store(-1, std::memory_order_release);
+                }
             }
+            int expected = 1;
+            ctx->workerState.compare_exchange_strong(expected, 2);
         }
 
-        Context* current() { return g_context.get(); }
+        // every API call works on a snapshot: Exit() may reset g_context while another thread is inside GetOutput()
+        std::shared_ptr<Context> current()
+        {
+            std::lock_guard<std::mutex> guard(g_contextMutex);
+            return g_context;
+        }
     } // namespace
 
     void Init(const PlaneverbConfig* config)
     {
-        std::lock_guard<std::mutex> guard(g_contextMutex);
-        if (g_context)
-        {
-            g_context->running.store(false);
-            if (g_context->worker.joinable()) g_context->worker.join();
-            pvx_destroy(g_context->scene);
-            for (float* g : g_context->grid) pvc_host_free(g);
-            g_context.reset();
-        }
+        Exit();                                        // PvContext.cpp:27-30
         // PvContext.cpp:101-107
         if (config == nullptr || config->gridResolution < pv_LowResolution ||
             config->gridSizeInMeters.x == 0 || config->gridSizeInMeters.y == 0 ||
             config->tempFileDirectory == nullptr)
         {
+            setLastError("Init: invalid PlaneverbConfig (PvContext.cpp:101-107)");
             throw pv_InvalidConfig;
         }
-        std::unique_ptr<Context> ctx(new Context());
+        if (config->gridWorldOffset.x != 0.f || config->gridWorldOffset.y != 0.f)
+        {
+            setLastError("Init: gridWorldOffset is not supported (PvTypes.h:58)");
+            throw pv_InvalidConfig;
+        }
+        std::shared_ptr<Context> ctx = std::make_shared<Context>();
         std::memcpy(&ctx->config, config, sizeof(PlaneverbConfig));
         ctx->params = pvhost::derive(config->gridResolution, config->gridSizeInMeters.x, config->gridSizeInMeters.y);
         int device = 0;
@@ -161,7 +225,7 @@ namespace Planeverb
                                   0, -1.f, 1, device, 0, 0, &ctx->scene);
         if (rc != PVC_OK)
         {
-            g_lastError = pvc_last_error();
+            setLastError(std::string("Init: ") + pvc_last_error());
             throw (rc == PVC_ERR_MEMORY) ? pv_NotEnoughMemory : pv_InvalidConfig;
         }
         const size_t cells = (size_t)ctx->params.gx * ctx->params.gy;
@@ -170,26 +234,27 @@ namespace Planeverb
             ctx->grid[i] = static_cast<float*>(pvc_host_alloc(sizeof(float) * cells * 8));
             if (!ctx->grid[i])
             {
-                g_lastError = pvc_last_error();
-                for (int k = 0; k < i; ++k) pvc_host_free(ctx->grid[k]);
-                pvx_destroy(ctx->scene);
-                throw pv_NotEnoughMemory;
+                setLastError(std::string("Init: ") + pvc_last_error());
+                throw pv_NotEnoughMemory;             // ~Context frees what was allocated
             }
             std::memset(ctx->grid[i], 0, sizeof(float) * cells * 8);      // Context's memset (PvContext.cpp:132)
         }
+        setLastError("");
+        ctx->workerState.store(1, std::memory_order_release);
         ctx->worker = std::thread(workerLoop, ctx.get());
+        std::lock_guard<std::mutex> guard(g_contextMutex);
         g_context = std::move(ctx);
     }
 
     void Exit()
     {
-        std::lock_guard<std::mutex> guard(g_contextMutex);
-        if (!g_context) return;
-        g_context->running.store(false, std::memory_order_release);
-        if (g_context->worker.joinable()) g_context->worker.join();
-        pvx_destroy(g_context->scene);
-        for (float* g : g_context->grid) pvc_host_free(g);
-        g_context.reset();
+        std::shared_ptr<Context> ctx;
+        {
+            std::lock_guard<std::mutex> guard(g_contextMutex);
+            ctx.swap(g_context);
+        }
+        if (!ctx) return;
+        ctx->shutdown();        // join the worker here; the buffers go when the last snapshot (a GetOutput in flight) is dropped
     }
 
     void ChangeSettings(const PlaneverbConfig* newConfig)
@@ -200,7 +265,7 @@ namespace Planeverb
 
     void SetListenerPosition(const vec3& listenerPosition)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return;
         std::lock_guard<std::mutex> lock(ctx->listenerMutex);
         ctx->listener = listenerPosition;
@@ -208,7 +273,7 @@ namespace Planeverb
 
     EmissionID Emit(const vec3& emitterPosition)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return PV_INVALID_EMISSION_ID;
         std::lock_guard<std::mutex> lock(ctx->emitterMutex);
         if (!ctx->freeEmitters.empty())
@@ -224,7 +289,7 @@ namespace Planeverb
 
     void UpdateEmission(EmissionID id, const vec3& position)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return;
         std::lock_guard<std::mutex> lock(ctx->emitterMutex);
         if (id < ctx->emitters.size()) ctx->emitters[id] = position;
@@ -232,7 +297,7 @@ namespace Planeverb
 
     void EndEmission(EmissionID id)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return;
         std::lock_guard<std::mutex> lock(ctx->emitterMutex);
         if (id < ctx->emitters.size()) ctx->freeEmitters.push_back(id);
@@ -242,7 +307,7 @@ namespace Planeverb
     {
         PlaneverbOutput out{};
         out.occlusion = PV_INVALID_DRY_GAIN;             // FDTD.cpp:23-47: every failure path
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return out;
         vec3 pos;
         {
@@ -251,9 +316,7 @@ namespace Planeverb
             pos = ctx->emitters[emitter];
         }
         int r, c;
-        if (!pvhost::emitterCell(ctx->params, pos.x, pos.z, r, c,
-                                 ctx->config.gridWorldOffset.x, ctx->config.gridWorldOffset.y))
-            return out;
+        if (!pvhost::emitterCell(ctx->params, pos.x, pos.z, r, c)) return out;
         float v[8];
         {
             std::lock_guard<std::mutex> lock(ctx->publishMutex);
@@ -282,17 +345,17 @@ namespace Planeverb
 
     PlaneObjectID AddGeometry(const AABB* transform)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx || !transform) return PV_INVALID_PLANE_OBJECT_ID;
         std::lock_guard<std::mutex> lock(ctx->geometryMutex);
-        const PlaneObjectID id = addObject(ctx, *transform);
+        const PlaneObjectID id = addObject(ctx.get(), *transform);
         pvx_add_aabb(ctx->scene, transform->position.x, transform->position.y, transform->width, transform->height, transform->absorption);
         return id;
     }
 
     void UpdateGeometry(PlaneObjectID id, const AABB* newTransform)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx || !newTransform) return;
         std::lock_guard<std::mutex> lock(ctx->geometryMutex);
         if (id >= ctx->objects.size()) return;
@@ -305,7 +368,7 @@ namespace Planeverb
 
     void RemoveGeometry(PlaneObjectID id)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return;
         std::lock_guard<std::mutex> lock(ctx->geometryMutex);
         if (id >= ctx->objects.size()) return;
@@ -317,7 +380,7 @@ namespace Planeverb
 
     std::pair<const Cell*, unsigned> GetImpulseResponse(const vec3& position)
     {
-        Context* ctx = current();
+        const std::shared_ptr<Context> ctx = current();
         if (!ctx) return std::make_pair((const Cell*)nullptr, 0u);
         const unsigned T = (unsigned)ctx->params.T;
         ctx->solverWaiters.fetch_add(1, std::memory_order_acq_rel);
@@ -359,9 +422,9 @@ void PVU_CC PlaneverbInit(float gridSizeX, float gridSizeY, int gridResolution, 
     config.maxThreadUsage = (unsigned)maxThreadUsage;
     config.threadExecutionType = (Planeverb::PlaneverbExecutionType)threadExecutionType;
     try { Planeverb::Init(&config); }
-    catch (Planeverb::PlaneverbErrorCode code)
+    catch (Planeverb::PlaneverbErrorCode)
     {
-        Planeverb::g_lastError = (code == Planeverb::pv_NotEnoughMemory ? "pv_NotEnoughMemory: " : "pv_InvalidConfig: ") + std::string(pvc_last_error());
+        // Init has recorded the reason (PlaneverbLastError); the reference lets the enum escape extern "C" (PlaneverbUnity.cpp:39)
     }
 }
 
@@ -416,10 +479,22 @@ void PVU_CC PlaneverbSetListenerPosition(float x, float y, float z)
 
 unsigned long long PVU_CC PlaneverbFramesCompleted(void)
 {
-    Planeverb::Context* ctx = Planeverb::current();
+    const std::shared_ptr<Planeverb::Context> ctx = Planeverb::current();
     return ctx ? ctx->frames.load(std::memory_order_acquire) : 0ull;
 }
 
-const char* PVU_CC PlaneverbLastError(void) { return Planeverb::g_lastError.c_str(); }
+int PVU_CC PlaneverbWorkerState(void)
+{
+    const std::shared_ptr<Planeverb::Context> ctx = Planeverb::current();
+    return ctx ? ctx->workerState.load(std::memory_order_acquire) : 0;
+}
+
+const char* PVU_CC PlaneverbLastError(void)
+{
+    thread_local std::string copy;                 // the caller's own copy: the worker may overwrite the shared text at any time
+    std::lock_guard<std::mutex> lock(Planeverb::g_errorMutex);
+    copy = Planeverb::g_lastError;
+    return copy.c_str();
+}
 
 } // extern "C"

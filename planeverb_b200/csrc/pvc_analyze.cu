@@ -432,7 +432,7 @@ namespace pvc
     // no "no improvement" exit, and the start itself is tested for loudness only).  So:
     //   1. walkNextKernel    next[u] = the cell the walk ends on if it ends at/after u without another move (DONE bit),
     //                        else the cell it moves to;
-    //   2. walkJumpKernel    next[u] <- next[next[u]] in place, ceil(log2 T) + 1 jumps in total (delays are integral
+    //   2. walkJumpKernel    next[u] <- next[next[next[next[u]]]] in place, ceil(log4 T) + 1 passes (delays are integral
     //                        sample indices that strictly decrease along a walk, so no path is longer than T);
     //   3. walkResolveKernel the first hop from every start cell, the end cell from next[], the unit vector (:413-430).
     // Same exits, same tie-breaking, same fp32 expressions as the sequential walk (which remains the cross-check in
@@ -542,7 +542,7 @@ namespace pvc
             if (v >= 0)
             {
                 int n = next[v];
-                while (n >= 0) n = next[n];            // already resolved by the jump rounds; a safety net, not a loop
+                while (n >= 0) n = next[n];            // the jump rounds have resolved every link (see launchAnalyzer); this follows whatever a pathological case left
                 target = n & 0x7fffffff;
             }
         }
@@ -673,16 +673,16 @@ namespace pvc
         {
             const size_t cells = (size_t)L.gx * L.gy;
             walkNextKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
-            int jumpsLeft = 1;
-            while ((1 << jumpsLeft) < A.T) ++jumpsLeft;          // ceil(log2 T)
-            jumpsLeft += 1;
-            int rounds = 0;
-            while (jumpsLeft > 0)
-            {
-                const int j = jumpsLeft < 3 ? jumpsLeft : 3;     // a few jumps per pass: fewer passes over the link array
-                walkJumpKernel<<<dim3((unsigned)((cells + 255) / 256), nsrc), 256, 0, s->stream>>>(cells, j, s->walkNext);
-                jumpsLeft -= j; ++rounds;
-            }
+            // A pass follows up to kHops further links from every cell, so it multiplies the length every link spans by at
+            // least kHops + 1 (in place: a link read here may already be longer); delays are integral sample indices that
+            // strictly decrease along a walk, so no walk is longer than T hops: ceil(log_(kHops+1) T) passes resolve them all,
+            // one more for good measure.  walkResolveKernel still follows whatever is left.
+            constexpr int kHops = 3;
+            int rounds = 1;
+            for (long span = kHops + 1; span < (long)A.T; span *= kHops + 1) ++rounds;
+            rounds += 1;
+            for (int k = 0; k < rounds; ++k)
+                walkJumpKernel<<<dim3((unsigned)((cells + 255) / 256), nsrc), 256, 0, s->stream>>>(cells, kHops, s->walkNext);
             walkResolveKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
             *launches += 3 + rounds;
         }

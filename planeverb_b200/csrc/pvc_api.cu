@@ -577,7 +577,12 @@ int pvc_fetch_results_async(pvc_solver* s, int n, float* results, float* delay)
 {
     if (!s || n < 1 || n > s->cfg.max_sources) { setError("pvc_fetch_results_async: bad argument"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
-    if (s->copyPending) PVC_CUDA(cudaEventSynchronize(s->evCopied));       // one copy in flight at a time
+    if (s->copyPending)
+    {   // one copy in flight at a time; a run whose step kernel gave up on a dependency wait must not pass for a good frame
+        PVC_CUDA(cudaEventSynchronize(s->evCopied));
+        s->copyPending = 0;
+        if (*s->hostAbort) { *s->hostAbort = 0; setError("step kernel: a tile dependency wait timed out in the previous frame (its results are invalid)"); return PVC_ERR_CUDA; }
+    }
     const size_t cells = (size_t)s->cfg.gx * s->cfg.gy;
     *s->hostAbort = 0;
     if (s->checkAbort)
@@ -771,6 +776,8 @@ int pvc_set_walk_mode(pvc_solver* s, int sequential)
     s->walkSequential = sequential ? 1 : 0;
     return PVC_OK;
 }
+
+int pvc_step_variant(pvc_solver* s) { return s ? s->cfg.reserved : -1; }
 
 void* pvc_host_alloc(size_t bytes)
 {

@@ -27,7 +27,7 @@ PVC_SYMBOLS = [
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_gather_results_async", "pvc_gather_wait", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
     "pvc_last_timing", "pvc_last_launch_counts", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
-    "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_set_walk_mode",
+    "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_set_walk_mode", "pvc_step_variant",
 ]
 PVX_SYMBOLS = [
     "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
@@ -121,6 +121,7 @@ def lib():
         L.pvc_mark_elapsed.argtypes = [_vp, _vp]
         L.pvc_clear_geometry.argtypes = [_vp]
         L.pvc_set_walk_mode.argtypes = [_vp, _i]
+        L.pvc_step_variant.argtypes = [_vp]
         _lib = L
     return _lib
 
@@ -356,6 +357,10 @@ class Scene:
     def set_walk_mode(self, sequential):
         """listener direction by the reference's sequential walk (True) or pointer jumping (False, default)"""
         _check(lib().pvc_set_walk_mode(self._solver, int(bool(sequential))), "pvc_set_walk_mode")
+
+    def step_variant(self):
+        """the step-kernel variant this scene's solver runs (auto-selection resolved)"""
+        return int(lib().pvc_step_variant(self._solver))
 
     def clear_geometry(self):
         _check(lib().pvc_clear_geometry(self._solver), "pvc_clear_geometry")

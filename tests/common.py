@@ -16,21 +16,12 @@ EMITTERS = [(5, 6), (6, 5), (3.5, 3.5), (12.5, 12.5), (20, 20)]
 RTOL = 1e-4                                  # BASELINE.json north_star tolerance
 
 
-def load_scenes():
-    return json.load(open(SCENES_JSON))
-
-
-def boxes_of(scenes, name, scale=1.0):
-    """AABBs of a .pv scene, optionally scaled from the 25 m authoring world."""
-    out = []
-    for b in scenes[name]["boxes"]:
-        out.append((np.float32(b["pos"][0] * scale), np.float32(b["pos"][1] * scale),
-                    np.float32(b["width"] * scale), np.float32(b["height"] * scale), np.float32(b["absorption"])))
-    return [tuple(float(v) for v in t) for t in out]
+from planeverb_b200.scenes import load_scenes, boxes_of          # noqa: E402,F401  (the product's own scene helpers)
 
 
 def scaled_config(n, resolution=275):
-    """(size_m, scale) so that the reference truncates to exactly n x n cells and the 25 m scenes fill it."""
+    """(size_m, scale) so that the reference truncates to exactly n x n cells and the 25 m scenes fill it: the ORACLE's
+    derivation (tests/test_abi.py checks that the product's planeverb_b200.scenes.scaled_config agrees)."""
     from oracle import pvoracle
     size = pvoracle.size_for_cells(resolution, n)
     dx, _, _ = pvoracle.grid_params(resolution)

@@ -142,3 +142,13 @@ def test_ws2_work_item_order_is_a_dependency_respecting_bijection(gen_chunk, src
     for w in (-1, total):
         assert L.pvc_debug_ws2_item(w, gen_chunk, src_group, num_gen, nsrc, tps, out) == pvcuda.PVC_ERR_INVALID
     assert L.pvc_debug_ws2_item(0, gen_chunk, nsrc + 1, num_gen, nsrc, tps, out) == pvcuda.PVC_ERR_INVALID
+
+
+def test_product_scene_scaling_matches_the_oracle():
+    """bench.py sizes its scenes with the product's own helper (planeverb_b200.scenes, through pvx_derive); it must agree with
+    the oracle's derivation to the bit for every BASELINE grid size."""
+    from planeverb_b200 import scenes as pscenes
+    for n in (70, 128, 250, 512, 1024, 2048):
+        a = pscenes.scaled_config(n)
+        b = common.scaled_config(n)
+        assert np.float32(a[0]) == np.float32(b[0]) and a[1] == b[1], (n, a, b)

@@ -93,6 +93,8 @@ typedef struct pvc_listener
 } pvc_listener;
 
 PVC_API int  pvc_device_count(void);
+/* free / total bytes of device memory (cudaMemGetInfo) */
+PVC_API int  pvc_device_memory(int device, size_t* free_bytes, size_t* total_bytes);
 PVC_API const char* pvc_last_error(void);
 
 PVC_API int  pvc_create(const pvc_config* cfg, pvc_solver** out);

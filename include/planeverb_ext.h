@@ -69,6 +69,31 @@ PVC_API int  pvx_impulse_response(pvx_scene* sc, int source, float x, float y, f
 
 PVC_API pvc_solver* pvx_solver(pvx_scene* sc);
 
+/* ---- multi-GPU form: listener positions are independent simulations, so a list of them is sharded contiguously
+ * over the devices -- one host thread and one stream per device, no data-path collective -- and the per-emitter outputs of every
+ * source are gathered into ONE host table.  The reference has no counterpart (one Context, one listener, PvContext.cpp:63-94);
+ * this is BASELINE.json's "independent source positions shard embarrassingly across the 8 GPUs" behind the same C ABI. ---- */
+typedef struct pvx_multi pvx_multi;
+/* devices[n_devices]: CUDA ordinals (an ordinal may repeat: several scenes on one GPU).  maxSources: the longest listener list a
+ * solve may carry; each device gets the contiguous shard pvx_shard_bounds(maxSources, n_devices, k) and solves it maxBatch sources
+ * at a time (0 = as many as fit 90 % of the device's free memory).  Other arguments as pvx_create. */
+PVC_API int  pvx_create_multi(const int* devices, int n_devices, float sizeX, float sizeY, int resolution, int responseLength,
+                              float efree, int maxSources, int maxBatch, int maxEmitters, pvx_multi** out);
+PVC_API void pvx_destroy_multi(pvx_multi* m);
+PVC_API int  pvx_multi_devices(pvx_multi* m);
+PVC_API pvx_scene* pvx_multi_scene(pvx_multi* m, int k);
+PVC_API int  pvx_multi_batch(pvx_multi* m, int k);
+/* geometry edits go to every device's queue (each flushes before its next solve) */
+PVC_API int  pvx_multi_add_aabb(pvx_multi* m, float posX, float posY, float width, float height, float absorption);
+PVC_API int  pvx_multi_remove_aabb(pvx_multi* m, float posX, float posY, float width, float height, float absorption);
+/* GenerateResponse + AnalyzeResponses for n listeners (xyz triples) on all devices at once, then Analyzer::GetResponseResult for
+ * n_emitters world positions per listener: out[(listener * n_emitters + emitter) * 8 + field], eight -1 for an emitter outside
+ * the grid.  Synchronous; the first failing device's status is returned (pvx_multi_last_error names it). */
+PVC_API int  pvx_multi_solve(pvx_multi* m, const float* listenersXYZ, int n, const float* emittersXYZ, int n_emitters, float* out);
+PVC_API const char* pvx_multi_last_error(pvx_multi* m);
+/* the sharding rule, host arithmetic: contiguous balanced shard [lo, hi) of n_items for part `part` of `parts` */
+PVC_API int  pvx_shard_bounds(int n_items, int parts, int part, int* lo, int* hi);
+
 /* ---- host-only helpers (no device needed): the index/scalar derivations the scene solver feeds the
  * CUDA layer, exported so they can be checked against the reference on a machine without a GPU ---- */
 /* cfg is filled for (resolution, size, responseLength override); floats[2] = dt, FreeGrid probe radius;

@@ -64,7 +64,7 @@ namespace pvc
     static ResidentChoice bestResident(const pvc_config& c, int sms)
     {
         ResidentChoice best = { 0, 0.0 };
-        for (int v = 60; v <= 64; ++v)
+        for (int v = 60; v <= 65; ++v)
         {
             if (!variantAvailable(v)) continue;
             const int nw = variantWarps(v), perSm = variantMinBlocks(v);
@@ -276,13 +276,22 @@ int pvc_device_count(void)
 
 const char* pvc_last_error(void) { return g_error; }
 
+int pvc_device_memory(int device, size_t* free_bytes, size_t* total_bytes)
+{
+    if (!free_bytes || !total_bytes) { setError("pvc_device_memory: null argument"); return PVC_ERR_INVALID; }
+    if (device < 0 || device >= pvc_device_count()) { setError("pvc_device_memory: device %d", device); return PVC_ERR_NO_DEVICE; }
+    PVC_CUDA(cudaSetDevice(device));
+    PVC_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
+    return PVC_OK;
+}
+
 size_t pvc_memory_requirement(const pvc_config* cfg)
 {
     if (!validConfig(cfg)) return 0;
     pvc_config r = *cfg; r.reserved = resolveVariant(*cfg);
     const Layout L = makeLayout(r);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 : 4) * L.plane + S * L.hist_source + (size_t)cfg->T +
+    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 + 32 * S : 4) * L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 11 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
@@ -342,7 +351,8 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     if (variantKind(s->cfg.reserved) == 6)
     {
         for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->lin[f], sizeof(float) * L.plane));
-        PVC_TRY(cudaMalloc(&s->resFlags, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));
+        PVC_TRY(cudaMalloc(&s->resXchg, sizeof(float) * 4 * 8 * S * L.plane));
+        PVC_TRY(cudaMemsetAsync(s->resXchg, 0, sizeof(float) * 4 * 8 * S * L.plane, s->stream));
     }
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
@@ -376,7 +386,7 @@ void pvc_destroy(pvc_solver* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    cudaFree(s->w); for (int f = 0; f < 3; ++f) { cudaFree(s->coef[f]); cudaFree(s->lin[f]); } cudaFree(s->resFlags); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
+    cudaFree(s->w); for (int f = 0; f < 3; ++f) { cudaFree(s->coef[f]); cudaFree(s->lin[f]); } cudaFree(s->resXchg); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
     if (s->evAnalyzed) cudaEventDestroy(s->evAnalyzed);
     if (s->evCopied) cudaEventDestroy(s->evCopied);

@@ -105,7 +105,8 @@ struct pvc_solver
     float* w;                // wall plane (air flag / admittance), the geometry's source of truth
     float* coef[3];          // general-path coefficient planes bp, gx, gy derived from w (pvc_step_fused.cu)
     float* lin[3];           // linear-form coefficient planes cP, sX, sY derived from w (pvc_step_res.cu); null until a resident variant needs them
-    int* resFlags;           // resident kernel: passes completed per (source, tile)
+    void* resXchg;           // resident kernel: mailbox planes [8 slots][max_sources][rows_alloc][pitch] of 16-byte {p, vx, vy, tag} words
+    int resEpoch;            // resident kernel: tag epoch of the last solve (15 bits)
     int resSourcesPerLaunch; // resident kernel: sources solved concurrently by one launch (co-residency limit), 0 = not computed yet
     uint32_t* slowMask;      // per (tile, warp): lanes that must take the general (wall/edge) path
     uint32_t* bpMask;        // per (tile, warp, lane): air flags of the thread's cells (pvc_step_ws2.cu)

@@ -7,11 +7,18 @@
 //
 //   * A tile belongs to ONE CTA for the whole solve and its p / vx / vy never leave the registers.  Between passes a
 //     CTA writes only the 4-cell-wide strips its neighbours need (first / last four owned rows, lanes 1 and 30 of the
-//     others) into the ping-pong state planes and reads its own halo ring back from them: ~32 KB per tile and pass
-//     through the L2 instead of 155 KB (full tile in through TMA, owned cells out), no TMA stage to drain, no store
-//     burst, no producer / publisher warps.  Hand-over: one counter per tile, `st.release.gpu` after a CTA barrier,
-//     `ld.acquire.gpu` polls of the up-to-8 neighbours by every warp.  All CTAs are co-resident (cooperative launch);
-//     a batch of sources that does not fit is solved a few sources per launch, one launch after the other.
+//     others) into a mailbox plane and reads its own halo ring back from it: ~50 KB per tile and pass through the L2
+//     instead of 155 KB (full tile in through TMA, owned cells out), no TMA stage to drain, no store burst, no producer /
+//     publisher warps.  Hand-over WITHOUT fences, flags or CTA barriers: a strip cell travels as ONE 16-byte word
+//     {p, vx, vy, tag} (tag = solve epoch << 16 | pass), written and read with single 128-bit strong accesses, so a
+//     reader that sees the tag it expects has the data that came with it (the low-latency protocol of collective
+//     libraries; it relies on an aligned 16-byte access being performed as one L2 transaction, which
+//     tools/micro/vec16_atomicity.cu stresses on the device and every parity test would expose).  The halo loads ARE the
+//     poll.  Measured against the first version of this kernel (one counter per tile, CTA barrier + st.release, acquire
+//     polls, then reloads): the hand-over chain cost 4.2 us of an 8.3 us pass (profiles/r02_resident_trace.txt).
+//     Eight mailbox slots (pass & 7) keep a writer from overwriting cells a lagging warp of a neighbour still has to read.
+//     All CTAs are co-resident (cooperative launch); a batch of sources that does not fit is solved a few sources per
+//     launch, one launch after the other.
 //   * Walls, the absorbing grid edge, the padding row / column and the guard band are DATA in a form that costs what
 //     the interior-air path costs.  With p == 0 in every cell that is not interior air (an invariant of the scheme:
 //     such a cell's pressure coefficient is 0 and nothing is ever injected there), the four cases of the reference's
@@ -35,22 +42,25 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "pvc_internal.h"
 
 namespace pvc
 {
     namespace res
     {
-        __device__ __forceinline__ int loadAcquire(const int* p)
+        // one mailbox word: 16 bytes, one strong 128-bit access each way (see the header)
+        __device__ __forceinline__ void storeWord(float4* q, float a, float b, float c, int tag)
         {
-            int v;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(a), "f"(b), "f"(c), "f"(__int_as_float(tag)) : "memory");
+        }
+        __device__ __forceinline__ float4 loadWord(const float4* q)
+        {
+            float4 v;
+            asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
             return v;
         }
-        __device__ __forceinline__ void storeRelease(int* p, int v)
-        {
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-        }
+        constexpr int kSlots = 8;
         __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
         // neighbour-only synchronisation of the step loop (see pvc_step_ws2.cu::phaseSync): a warp meets the warp above and
         // the warp below on the named barrier of their common edge (id = upper warp + 1), even warps the lower edge first
@@ -82,12 +92,35 @@ namespace pvc
             int* firstActive;                      // [source][tile][32]
             const SourceParams* src;
             const float* pulse;
-            int* flags;                            // [source][tile] passes completed
+            float4* xchg;                          // mailbox [kSlots][max_sources][rows_alloc][pitch] of {p, vx, vy, tag}
+            size_t xchgSlot;                       // float4s between slots: max_sources * plane
+            int tagBase;                           // solve epoch << 16
             int* abortFlag;
             int tilesPerSource, s0, nsrc;          // this launch solves sources s0 .. s0 + nsrc - 1
             int numGen, T;
             float courant;
+#ifdef PVC_TUNING
+            int dbg;                               // tuning builds only (results invalid): bit 0 no history stores, bit 1 no neighbour wait / halo reload
+            unsigned long long* trace;             // per CTA x traced pass x 8 %globaltimer stamps (null: off)
+#endif
         };
+#ifdef PVC_TUNING
+        constexpr int kTracePass0 = 40, kTracePasses = 32, kTraceSlots = 8;
+        __device__ __forceinline__ void stamp(const Args& A, int g, int slot)
+        {
+            if (A.trace && threadIdx.x == 0 && g >= kTracePass0 && g < kTracePass0 + kTracePasses)
+            {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.trace[((size_t)blockIdx.x * kTracePasses + (g - kTracePass0)) * kTraceSlots + slot] = t;
+            }
+        }
+        #define PVC_STAMP(A, g, slot) stamp(A, g, slot)
+        #define PVC_DBG(A, bit) (((A).dbg >> (bit)) & 1)
+#else
+        #define PVC_STAMP(A, g, slot) do {} while (0)
+        #define PVC_DBG(A, bit) 0
+#endif
 
         // ---- one time step of a warp's R x 128 block; GEN = coefficient path (walls / edges / guard band as data) ----
         template <int R, bool GEN>
@@ -271,40 +304,36 @@ namespace pvc
             __syncthreads();
 
             // ---- row / lane classes of this thread, fixed for the solve
-            uint32_t haloRows = 0u, ownRows = 0u, stripRows = 0u;
+            const bool up = ty > 0, down = ty + 1 < L.tiles_y, left = tx > 0, right = tx + 1 < L.tiles_x;
+            const bool haloLane = lane == 0 || lane == 31;
+            uint32_t ownRows = 0u, loadRows = 0u, sendRows = 0u;
             #pragma unroll
             for (int j = 0; j < R; ++j)
             {
                 const int tr = wp * R + j, r = rBase + j;
-                const bool halo = tr < kTileK || tr >= TR - kTileK;
+                const bool top = tr < kTileK, bottom = tr >= TR - kTileK;
                 // the padding row r == gx may be the first halo row of the last tile row (tiles cover gx rows): it depends only on the
                 // owned row gx - 1 of the same step, so it is always current there and is recorded / stored with the owned rows
-                const bool owned = (!halo && r < L.rows) || (halo && tr >= TR - kTileK && r == L.gx);
-                if (halo) haloRows |= 1u << j;
+                const bool owned = (!top && !bottom && r < L.rows) || (bottom && r == L.gx);
                 if (owned) ownRows |= 1u << j;
-                if (owned && (tr < 2 * kTileK || tr >= TR - 2 * kTileK)) stripRows |= 1u << j;
+                // a halo cell is reloaded iff the tile that owns it exists; everything else outside the tile is guard band (zero for ever)
+                const bool rowOk = top ? up : (bottom ? down : true);
+                const bool colOk = (lane == 0) ? left : (lane == 31 ? right : true);
+                if ((top || bottom || haloLane) && rowOk && colOk) loadRows |= 1u << j;
+                // an owned cell is mailed iff it lies within 4 cells of an edge behind which a tile exists (corners go with the rows)
+                const bool inTile = !top && !bottom && !haloLane;
+                const bool nearRow = (tr < 2 * kTileK && up) || (tr >= TR - 2 * kTileK && down);
+                const bool nearCol = (lane == 1 && left) || (lane == 30 && right);
+                if (inTile && (nearRow || nearCol)) sendRows |= 1u << j;
             }
-            const bool haloLane = lane == 0 || lane == 31;
-            const bool stripLane = lane == 1 || lane == 30;
             if (haloLane || cBase >= L.cols) ownRows = 0u;
-            const uint32_t loadRows = haloLane ? ((1u << R) - 1u) : haloRows;          // rows reloaded from the state planes before every pass
-            const uint32_t storeRows = ownRows & (stripLane ? ((1u << R) - 1u) : stripRows);   // rows a neighbour reads: written after every pass
-
-            // neighbours: lane i < 9 (i != 4) watches tile (tx + i%3 - 1, ty + i/3 - 1)
-            const int* watch = nullptr;
-            {
-                const int nx = tx + lane % 3 - 1, ny = ty + lane / 3 - 1;
-                if (lane < 9 && lane != 4 && nx >= 0 && ny >= 0 && nx < L.tiles_x && ny < L.tiles_y)
-                    watch = A.flags + (size_t)s * tps + (size_t)ny * L.tiles_x + nx;
-            }
-            int* const myFlag = A.flags + (size_t)s * tps + tile;
 
             Ctx X;
             X.lane = lane; X.wp = wp; X.C = A.courant;
             X.hist = A.hist + (size_t)s * L.hist_source + (ptrdiff_t)rBase * (ptrdiff_t)L.hist_row
                    + ((ptrdiff_t)(cBase >> 7) * L.T) * kHistChunkDefault + (cBase & 127);
             X.histRow = L.hist_row;
-            X.ownRows = ownRows;
+            X.ownRows = PVC_DBG(A, 0) ? 0u : ownRows;
             const SourceParams sp = A.src[s];
             {
                 const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
@@ -328,46 +357,39 @@ namespace pvc
             {
                 const int t0 = g * kTileK;
                 const int nsteps = min(kTileK, A.T - t0);
-                if (g > 0)
+                PVC_STAMP(A, g, 0);
+                if (g > 0 && loadRows && !PVC_DBG(A, 1))
                 {
-                    // ---- warp 0 waits until every neighbour has finished pass g - 1 (its lanes watch one neighbour each); the CTA
-                    //      barrier hands the acquire on to the other warps, which then reload the halo ring from buffer g & 1
-                    int ok = 1;
-                    if (wp == 0)
+                    // ---- reload the halo ring from the mailbox: the words the neighbours wrote at the end of pass g - 1 carry tag g
+                    const float4* q0 = A.xchg + (size_t)(g & (kSlots - 1)) * A.xchgSlot + src0;
+                    const int tag = A.tagBase + g;
+                    unsigned spins = 0;
+                    while (true)
                     {
-                        unsigned spins = 0;
-                        while (true)
-                        {
-                            const bool ready = !watch || loadAcquire(watch) >= g;
-                            if (__all_sync(0xffffffffu, ready)) break;
-                            __nanosleep(20);
-                            ++spins;
-                            bool giveUp = false;
-                            if ((spins & 0xffu) == 0u) giveUp = spins > (1u << 22) || *(volatile int*)A.abortFlag;
-                            if (__any_sync(0xffffffffu, giveUp)) { if (lane == 0) atomicExch(A.abortFlag, 1); ok = 0; break; }
-                        }
-                    }
-                    if (!__syncthreads_and(ok)) break;            // uniform: a dependency wait timed out (pvc_synchronize reports it)
-                    if (loadRows)
-                    {
-                        const float* gp = ((g & 1) ? A.p1 : A.p0) + src0;
-                        const float* gx = ((g & 1) ? A.vx1 : A.vx0) + src0;
-                        const float* gy = ((g & 1) ? A.vy1 : A.vy0) + src0;
+                        int bad = 0;
                         #pragma unroll
                         for (int j = 0; j < R; ++j)
                             if ((loadRows >> j) & 1u)
                             {
-                                const float4 a = __ldcg(reinterpret_cast<const float4*>(gp + (size_t)j * L.pitch));
-                                const float4 b = __ldcg(reinterpret_cast<const float4*>(gx + (size_t)j * L.pitch));
-                                const float4 c = __ldcg(reinterpret_cast<const float4*>(gy + (size_t)j * L.pitch));
-                                p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
-                                vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
-                                vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+                                #pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                {
+                                    const float4 v = loadWord(q0 + (size_t)j * L.pitch + k);
+                                    p[j][k] = v.x; vx[j][k] = v.y; vy[j][k] = v.z;
+                                    bad |= __float_as_int(v.w) ^ tag;
+                                }
                             }
+                        if (bad == 0) break;
+                        // not there yet (or a neighbour died): bounded, and a raised abort flag ends every later wait at once
+                        if ((spins & 0x3fu) == 0u && (spins > (1u << 18) || *(volatile int*)A.abortFlag)) { atomicExch(A.abortFlag, 1); break; }
+                        ++spins;
+                        __nanosleep(20);
                     }
                 }
+                PVC_STAMP(A, g, 1);
                 sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
                 phaseSync<NW, PAIR>(wp);
+                PVC_STAMP(A, g, 2);
 
                 uint32_t activity = 0u;
                 if (firstGen == kNeverActive)
@@ -383,12 +405,28 @@ namespace pvc
                     else stepLoop<NW, R, PAIR, false, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
                 }
 
-                // ---- hand the strips (last pass: every owned cell -- the final state) to buffer (g + 1) & 1
+                PVC_STAMP(A, g, 3);
                 const bool lastPass = g + 1 == A.numGen;
-                const uint32_t outRows = lastPass ? ownRows : storeRows;
-                if (outRows)
+                if (!lastPass)
                 {
-                    if (lastPass && sp.dead && A.T == t0 + nsteps)
+                    // ---- mail the cells the neighbours need for pass g + 1
+                    if (sendRows)
+                    {
+                        float4* q0 = A.xchg + (size_t)((g + 1) & (kSlots - 1)) * A.xchgSlot + src0;
+                        const int tag = A.tagBase + g + 1;
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            if ((sendRows >> j) & 1u)
+                            {
+                                #pragma unroll
+                                for (int k = 0; k < 4; ++k) storeWord(q0 + (size_t)j * L.pitch + k, p[j][k], vx[j][k], vy[j][k], tag);
+                            }
+                    }
+                }
+                else if (ownRows)
+                {
+                    // ---- the final state of every owned cell into the state planes (Grid's m_grid after the last step)
+                    if (sp.dead && A.T == t0 + nsteps)
                     {
                         // the reference injects the last pulse sample even into a wall / padding cell, where nothing ever reads it
                         // again (FDTD.cpp:234): it only shows in the final state
@@ -408,18 +446,14 @@ namespace pvc
                     float* gy = ((g & 1) ? A.vy0 : A.vy1) + src0;
                     #pragma unroll
                     for (int j = 0; j < R; ++j)
-                        if ((outRows >> j) & 1u)
+                        if ((ownRows >> j) & 1u)
                         {
                             __stcg(reinterpret_cast<float4*>(gp + (size_t)j * L.pitch), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
                             __stcg(reinterpret_cast<float4*>(gx + (size_t)j * L.pitch), make_float4(vx[j][0], vx[j][1], vx[j][2], vx[j][3]));
                             __stcg(reinterpret_cast<float4*>(gy + (size_t)j * L.pitch), make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]));
                         }
                 }
-                // every warp has stored its strips and finished reading the exchange rows: publish pass g.  (A CTA barrier, not
-                // per-warp arrivals on the counter: neighbour-only synchronisation lets the first warp of a 20-warp tile run up
-                // to two passes ahead of the last one, which a count could not tell from two warps of the same pass.)
-                __syncthreads();
-                if (threadIdx.x == 0) storeRelease(myFlag, g + 1);
+                PVC_STAMP(A, g, 4);
             }
             if (lane == 0 && firstGen != kNeverActive && A.firstActive)
                 A.firstActive[((size_t)s * tps + tile) * 32 + wp] = firstGen;
@@ -490,22 +524,43 @@ namespace pvc
         {
             const Layout& L = s->L;
             if (t0 != 0 || s->cur != 0) { setError("resident step kernel: must start at step 0"); return PVC_ERR_INVALID; }
-            if (!hist || !s->lin[0] || !s->resFlags) { setError("resident step kernel: history / coefficient planes missing"); return PVC_ERR_INVALID; }
+            if (!hist || !s->lin[0] || !s->resXchg) { setError("resident step kernel: history / coefficient planes / mailbox missing"); return PVC_ERR_INVALID; }
             if (L.hist_chunk != kHistChunkDefault || L.tile_rows != NW * R) { setError("resident step kernel: layout does not match the variant"); return PVC_ERR_INVALID; }
             const int tps = L.tiles_x * L.tiles_y;
             const int cap = capacity<NW, R, MINB>(s->device);
             if (cap < tps) { setError("resident step kernel: %d tiles per source exceed the %d co-resident CTAs of this device", tps, cap); return PVC_ERR_INVALID; }
             const int perLaunch = cap / tps;
             const int gens = (t1 + kTileK - 1) / kTileK;
-            cudaMemsetAsync(s->resFlags, 0, sizeof(int) * (size_t)tps * nsrc, s->stream);
+            if (gens >= 65536) { setError("resident step kernel: %d passes exceed the 16-bit pass field of the mailbox tag", gens); return PVC_ERR_INVALID; }
+            // every solve gets its own tag epoch, so words left in the mailbox by earlier solves can never match; when the 15-bit
+            // epoch wraps the mailbox is cleared once
+            s->resEpoch = (s->resEpoch + 1) & 0x7fff;
+            if (s->resEpoch == 0)
+            {
+                s->resEpoch = 1;
+                cudaMemsetAsync(s->resXchg, 0, sizeof(float4) * (size_t)res::kSlots * s->cfg.max_sources * L.plane, s->stream);
+            }
             cudaMemsetAsync(s->tileCounters, 0, sizeof(int), s->stream);            // slot 0 of the pool is the abort flag
             Args A;
             A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
             A.hist = hist; A.mode = s->slowMask; A.cP = s->lin[0]; A.sX = s->lin[1]; A.sY = s->lin[2];
             A.firstActive = s->firstActive; A.src = s->src; A.pulse = s->pulse;
-            A.flags = s->resFlags; A.abortFlag = s->tileCounters;
+            A.xchg = reinterpret_cast<float4*>(s->resXchg); A.xchgSlot = (size_t)s->cfg.max_sources * L.plane; A.tagBase = s->resEpoch << 16;
+            A.abortFlag = s->tileCounters;
             A.tilesPerSource = tps; A.numGen = gens; A.T = t1; A.courant = s->cfg.courant;
+#ifdef PVC_TUNING
+            { static const char* d = getenv("PVC_RES_DEBUG"); A.dbg = d ? atoi(d) : 0; }
+            A.trace = nullptr;
+            static unsigned long long* traceBuf = nullptr;
+            const size_t traceWords = (size_t)cap * kTracePasses * kTraceSlots;
+            if (getenv("PVC_RES_TRACE"))
+            {
+                if (!traceBuf) cudaMalloc(&traceBuf, traceWords * sizeof(unsigned long long));
+                cudaMemsetAsync(traceBuf, 0, traceWords * sizeof(unsigned long long), s->stream);
+                A.trace = traceBuf;
+            }
+#endif
             Layout Lc = L;
             for (int s0 = 0; s0 < nsrc; s0 += perLaunch)
             {
@@ -517,6 +572,31 @@ namespace pvc
                 if (e != cudaSuccess) { setError("resident step kernel launch (%d CTAs): %s", tps * A.nsrc, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
                 *launches += 1;
             }
+#ifdef PVC_TUNING
+            if (A.trace && gens >= kTracePass0 + kTracePasses)
+            {
+                cudaStreamSynchronize(s->stream);
+                std::vector<unsigned long long> h(traceWords);
+                cudaMemcpy(h.data(), traceBuf, traceWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                const int ctas = tps * A.nsrc;
+                double sum[5] = {}; long cnt = 0;
+                for (int c = 0; c < ctas; ++c)
+                    for (int k = 1; k + 1 < kTracePasses; ++k)
+                    {
+                        const unsigned long long* a = h.data() + ((size_t)c * kTracePasses + k) * kTraceSlots;
+                        const unsigned long long* nx = a + kTraceSlots;
+                        if (!a[0] || !a[1] || !a[2] || !a[3] || !a[4] || !nx[0]) continue;
+                        sum[0] += (double)a[1] - (double)a[0];       // halo reload (the poll)
+                        sum[1] += (double)a[2] - (double)a[1];       // first exchange row + sync
+                        sum[2] += (double)a[3] - (double)a[2];       // 4 steps
+                        sum[3] += (double)a[4] - (double)a[3];       // strips mailed
+                        sum[4] += (double)nx[0] - (double)a[0];      // pass period
+                        ++cnt;
+                    }
+                if (cnt) fprintf(stderr, "[res trace] NW=%d ctas=%d n=%ld  reload %.0f  exchange+sync %.0f  steps %.0f  mail %.0f | period %.0f ns (thread 0 of every CTA)\n",
+                                 NW, ctas, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt);
+            }
+#endif
             s->cur = gens & 1;
             s->checkAbort = 1;
             return PVC_OK;
@@ -532,6 +612,7 @@ namespace pvc
             case 62: return res::launch<12, 4, 2>(s, nsrc, t0, t1, hist, launches);
             case 63: return res::launch<16, 4, 1>(s, nsrc, t0, t1, hist, launches);
             case 64: return res::launch<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 65: return res::launch<18, 4, 1>(s, nsrc, t0, t1, hist, launches);
             default: setError("resident step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -545,6 +626,7 @@ namespace pvc
             case 62: return res::capacity<12, 4, 2>(device);
             case 63: return res::capacity<16, 4, 1>(device);
             case 64: return res::capacity<20, 4, 1>(device);
+            case 65: return res::capacity<18, 4, 1>(device);
             default: return 0;
         }
     }

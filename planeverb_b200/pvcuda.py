@@ -22,7 +22,7 @@ _STATUS = {1: "invalid argument/config", 2: "device memory", 3: "CUDA error", 4:
 
 # every symbol include/planeverb_cuda.h and include/planeverb_ext.h declare
 PVC_SYMBOLS = [
-    "pvc_device_count", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
+    "pvc_device_count", "pvc_device_memory", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_gather_results_async", "pvc_gather_wait", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
@@ -33,6 +33,8 @@ PVX_SYMBOLS = [
     "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
     "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup", "pvx_lookup_async", "pvx_lookup_wait",
     "pvx_impulse_response", "pvx_solver",
+    "pvx_create_multi", "pvx_destroy_multi", "pvx_multi_devices", "pvx_multi_scene", "pvx_multi_batch", "pvx_multi_add_aabb",
+    "pvx_multi_remove_aabb", "pvx_multi_solve", "pvx_multi_last_error", "pvx_shard_bounds",
     "pvx_derive", "pvx_derive_pulse", "pvx_derive_rect", "pvx_derive_listener", "pvx_derive_emitter_cell",
 ]
 
@@ -121,6 +123,18 @@ def lib():
         L.pvc_mark_elapsed.argtypes = [_vp, _vp]
         L.pvc_clear_geometry.argtypes = [_vp]
         L.pvc_set_walk_mode.argtypes = [_vp, _i]
+        L.pvx_create_multi.argtypes = [_vp, _i, _f, _f, _i, _i, _f, _i, _i, _i, _vp]
+        L.pvx_destroy_multi.argtypes = [_vp]
+        L.pvx_multi_devices.argtypes = [_vp]
+        L.pvx_multi_scene.argtypes = [_vp, _i]
+        L.pvx_multi_scene.restype = _vp
+        L.pvx_multi_batch.argtypes = [_vp, _i]
+        L.pvx_multi_add_aabb.argtypes = [_vp] + [_f] * 5
+        L.pvx_multi_remove_aabb.argtypes = [_vp] + [_f] * 5
+        L.pvx_multi_solve.argtypes = [_vp, _vp, _i, _vp, _i, _vp]
+        L.pvx_multi_last_error.argtypes = [_vp]
+        L.pvx_multi_last_error.restype = C.c_char_p
+        L.pvx_shard_bounds.argtypes = [_i, _i, _i, _vp, _vp]
         L.pvc_step_variant.argtypes = [_vp]
         _lib = L
     return _lib
@@ -385,3 +399,48 @@ class Scene:
         a, b = C.c_int(), C.c_int()
         _check(lib().pvc_last_launch_counts(self._solver, C.byref(a), C.byref(b)), "pvc_last_launch_counts")
         return int(a.value), int(b.value)
+
+
+def shard_bounds(n_items, parts, part):
+    """the C-ABI's sharding rule (pvx_shard_bounds, host arithmetic): contiguous balanced shard [lo, hi)"""
+    lo, hi = C.c_int(), C.c_int()
+    _check(lib().pvx_shard_bounds(int(n_items), int(parts), int(part), C.byref(lo), C.byref(hi)), "pvx_shard_bounds")
+    return lo.value, hi.value
+
+
+class MultiScene:
+    """pvx_create_multi / pvx_multi_solve: one scene per device, listeners sharded contiguously, one host thread per device,
+    per-emitter outputs gathered into one host table (no torch, no collective)."""
+
+    def __init__(self, devices, size_x, size_y, resolution, T=0, efree=-1.0, max_sources=1, max_batch=0, max_emitters=8):
+        dev = np.ascontiguousarray(np.asarray(devices, np.int32))
+        h = _vp()
+        _check(lib().pvx_create_multi(_p(dev), int(dev.size), size_x, size_y, int(resolution), int(T), float(efree), int(max_sources),
+                                      int(max_batch), int(max_emitters), C.byref(h)), "pvx_create_multi")
+        self._h = h
+        self.n_devices = int(lib().pvx_multi_devices(h))
+        self.batches = [int(lib().pvx_multi_batch(h, k)) for k in range(self.n_devices)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pvx_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_aabb(self, px, py, w, h, absorption):
+        _check(lib().pvx_multi_add_aabb(self._h, px, py, w, h, absorption), "pvx_multi_add_aabb")
+
+    def remove_aabb(self, px, py, w, h, absorption=0.0):
+        _check(lib().pvx_multi_remove_aabb(self._h, px, py, w, h, absorption), "pvx_multi_remove_aabb")
+
+    def solve(self, listeners, emitters):
+        """-> float32 [n_listeners, n_emitters, 8]"""
+        a = np.ascontiguousarray(np.asarray(listeners, np.float32).reshape(-1, 3))
+        e = np.ascontiguousarray(np.asarray(emitters, np.float32).reshape(-1, 3))
+        out = np.zeros((a.shape[0], e.shape[0], 8), np.float32)
+        rc = lib().pvx_multi_solve(self._h, _p(a), int(a.shape[0]), _p(e), int(e.shape[0]), _p(out))
+        if rc:
+            raise PlaneverbCudaError(f"pvx_multi_solve: {_STATUS.get(rc, rc)} ({lib().pvx_multi_last_error(self._h).decode(errors='replace')})")
+        return out

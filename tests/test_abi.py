@@ -152,3 +152,16 @@ def test_product_scene_scaling_matches_the_oracle():
         a = pscenes.scaled_config(n)
         b = common.scaled_config(n)
         assert np.float32(a[0]) == np.float32(b[0]) and a[1] == b[1], (n, a, b)
+
+
+def test_c_abi_sharding_rule_matches_the_python_harness():
+    """pvx_shard_bounds (the rule pvx_multi_solve shards listeners by) == planeverb_b200.sharding.shard_bounds (torchrun harness)"""
+    from planeverb_b200 import sharding
+    for n in (0, 1, 5, 8, 13):
+        for parts in (1, 2, 3, 8):
+            covered = []
+            for k in range(parts):
+                assert pvcuda.shard_bounds(n, parts, k) == sharding.shard_bounds(n, parts, k)
+                lo, hi = pvcuda.shard_bounds(n, parts, k)
+                covered += list(range(lo, hi))
+            assert covered == list(range(n))

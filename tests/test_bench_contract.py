@@ -28,9 +28,14 @@ def test_reference_arm_prints_the_contract_line():
     assert line["metric"].startswith("Mcell-updates/sec")
     assert line["value"] > 1.0 and line["ms_per_step"] > 0
     assert line["config"]["grid"] == [1024, 1024] and "BigRoom" in line["config"]["workload"]
+    # the arm describes what IT ran (a bounded sample: 128 steps, 1 listener), not the GPU arm's workload
+    assert line["config"]["time_steps"] == 128 and line["config"]["sources"] == 1 and "BOUNDED SAMPLE" in line["config"]["workload"]
+    assert "4000 time steps" in line["config"]["gpu_arm_workload"]
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == line["value"]
     assert "1024x1024" in cb["sample"]
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpvref_fast.so")) and " avx2" in open("/proc/cpuinfo").read():
+        assert cb["fast_math"]["value"] > 1.0 and "-ffast-math" in cb["fast_math"]["flags"]      # BASELINE.md section 3, second row
     assert line["e2e"] == {"value": line["value"], "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
 

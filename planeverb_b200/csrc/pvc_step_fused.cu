@@ -1137,7 +1137,8 @@ namespace pvc
                                          {8, 4, 1, 5, 1}, {10, 4, 1, 5, 0},                              // 50 (default when few work items), 51
                                          {12, 4, 1, 5, 0}, {12, 5, 1, 5, 0},                             // 52, 53
                                          {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0},   // 54..59 unused
-                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1} };   // 60..65: resident
+                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1},    // 60..65: resident (CTA / named barriers)
+                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1} };  // 66..71: resident, mbarrier edge synchronisation
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     bool variantAvailable(int variant)

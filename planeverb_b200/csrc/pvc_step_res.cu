@@ -42,6 +42,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <utility>
 #include <vector>
 #include "pvc_internal.h"
 
@@ -61,18 +63,53 @@ namespace pvc
             return v;
         }
         constexpr int kSlots = 8;
+        // A mailbox word is a register QUAD {p, vx, vy, tag} of ONE cell, while the step loop wants the four p (vx, vy) of a ROW in
+        // a quad (128-bit shared / history accesses).  Left to itself the register allocator coalesces the two and pays with ~30
+        // moves per time step; copying through an integer op with a run-time zero keeps the mailbox quads temporaries.
+        __device__ __forceinline__ float opaqueCopy(float v, int zero) { return __int_as_float(__float_as_int(v) ^ zero); }
         __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-        // neighbour-only synchronisation of the step loop (see pvc_step_ws2.cu::phaseSync): a warp meets the warp above and
-        // the warp below on the named barrier of their common edge (id = upper warp + 1), even warps the lower edge first
-        template <int NW, bool PAIR>
-        __device__ __forceinline__ void phaseSync(int wp)
+        __device__ __forceinline__ uint32_t smemAddr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+        __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
         {
-            if (PAIR)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+        }
+        __device__ __forceinline__ void mbarArrive(uint64_t* bar)
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+        }
+        __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+        {
+            asm volatile("{\n.reg .pred r;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 r, [%0], %1;\n@!r bra W_%=;\n}\n"
+                         ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+        }
+        // Synchronisation of the step loop: a warp exchanges halo rows only with the warp above and the warp below.
+        //   kSyncCta   one CTA barrier (every warp waits for the slowest)
+        //   kSyncNamed the named barrier of each shared edge (id = upper warp + 1, 64 threads; even warps take the lower edge first,
+        //              odd warps the upper one: no cycle) -- at most 16 ids, and named barriers are an SM resource
+        //   kSyncMbar  one shared-memory mbarrier per edge (2 arrivals): arrive on both edges, then wait for both -- any tile height,
+        //              any number of CTAs per SM.  Warps far from a slow warp run ahead of it by up to their distance in edges.
+        enum { kSyncCta = 0, kSyncNamed = 1, kSyncMbar = 2 };
+        template <int NW, int SYNC>
+        __device__ __forceinline__ void phaseSync(int wp, uint64_t* edge, uint32_t& parity)
+        {
+            if (SYNC == kSyncNamed)
             {
                 if (wp & 1) { pairBarrier(wp); if (wp + 1 < NW) pairBarrier(wp + 1); }
                 else { if (wp + 1 < NW) pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
             }
-            else __syncthreads();            // taller tiles (16 named barriers per CTA) and two-CTA-per-SM variants (barriers are an SM resource)
+            else if (SYNC == kSyncMbar)
+            {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0)
+                {
+                    if (wp > 0) mbarArrive(edge + wp);
+                    if (wp + 1 < NW) mbarArrive(edge + wp + 1);
+                }
+                if (wp > 0) mbarWait(edge + wp, parity);
+                if (wp + 1 < NW) mbarWait(edge + wp + 1, parity);
+                parity ^= 1u;
+            }
+            else __syncthreads();
         }
         // 1.0f where x < 0 (one FSET): the k of the linear-form velocity rule, folded into the sign of its coefficient
         __device__ __forceinline__ float signFlag(float x)
@@ -95,6 +132,7 @@ namespace pvc
             float4* xchg;                          // mailbox [kSlots][max_sources][rows_alloc][pitch] of {p, vx, vy, tag}
             size_t xchgSlot;                       // float4s between slots: max_sources * plane
             int tagBase;                           // solve epoch << 16
+            int zero;                              // 0, unknown to the compiler (see opaqueCopy)
             int* abortFlag;
             int tilesPerSource, s0, nsrc;          // this launch solves sources s0 .. s0 + nsrc - 1
             int numGen, T;
@@ -191,7 +229,8 @@ namespace pvc
             static constexpr size_t offVxTop = 0;
             static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
             static constexpr size_t offCoef = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);        // [3][TR][32] float4: cP, sX, sY
-            static constexpr size_t total = offCoef + (size_t)3 * TR * 32 * sizeof(float4);
+            static constexpr size_t offEdge = offCoef + (size_t)3 * TR * 32 * sizeof(float4);          // [NW + 1] mbarriers, one per warp edge
+            static constexpr size_t total = offEdge + (size_t)(NW + 2) * sizeof(uint64_t);
         };
 
         // everything of a thread that is fixed for the solve
@@ -205,10 +244,12 @@ namespace pvc
             int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
             const float* pulse;
             const float4* cP; const float4* sX; const float4* sY;       // this thread's coefficient float4s (row stride 32), shared memory
+            uint64_t* edge;           // kSyncMbar: the CTA's edge barriers
+            uint32_t parity;          // kSyncMbar: phase parity of the next synchronisation
         };
 
         // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised
-        template <int NW, int R, bool PAIR, bool GEN, bool TRACK>
+        template <int NW, int R, int SYNC, bool GEN, bool TRACK>
         __device__ __forceinline__ void stepLoop(Ctx& X, const int t0, const int nsteps, float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
                                                  float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
         {
@@ -219,7 +260,7 @@ namespace pvc
                 // ---- pressure sub-step (FDTD.cpp:125-141)
                 pressureStep<R, GEN>(p, vx, vy, sVxTop[wp + 1][lane], X.C, X.cP);
                 sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
-                phaseSync<NW, PAIR>(wp);
+                phaseSync<NW, SYNC>(wp, X.edge, X.parity);
                 // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
                 velocityStep<R, GEN>(p, vx, vy, sPBot[wp][lane], X.C, X.sX, X.sY);
                 // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
@@ -254,18 +295,18 @@ namespace pvc
                 if (step + 1 < nsteps)
                 {
                     sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-                    phaseSync<NW, PAIR>(wp);            // also the write-after-read fence of sPBot
+                    phaseSync<NW, SYNC>(wp, X.edge, X.parity);            // also the write-after-read fence of sPBot
                 }
             }
         }
 
-        template <int NW, int R, int MINB>
+        template <int NW, int R, int MINB, int SYNC>
         __global__ void __launch_bounds__(NW * 32, MINB)
         residentKernel(const Layout L, const Args A)
         {
             using SM = Smem<NW, R>;
             constexpr int TR = SM::TR;
-            constexpr bool PAIR = (MINB == 1) && (NW <= 16);
+            static_assert(SYNC != kSyncNamed || NW <= 16, "16 named barriers per CTA");
             extern __shared__ __align__(128) unsigned char smemRaw[];
             float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
             float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
@@ -283,10 +324,13 @@ namespace pvc
             const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
             const size_t src0 = (size_t)s * L.plane + cell0;
 
+            uint64_t* const edge = reinterpret_cast<uint64_t*>(smemRaw + SM::offEdge);
             if (wp == 0)
             {
                 sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (SYNC == kSyncMbar && lane <= NW) mbarInit(edge + lane, 2);
+                if (SYNC == kSyncMbar) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             const bool general = A.mode[(size_t)tile * 32 + wp] != 0u;
             if (general)
@@ -341,6 +385,7 @@ namespace pvc
                 X.sj = (hasSrc && !sp.dead) ? sj : -1; X.sk = sk;
             }
             X.pulse = A.pulse;
+            X.edge = edge; X.parity = 0u;
             X.cP = sCoef + (size_t)(wp * R) * 32 + lane;
             X.sX = X.cP + (size_t)TR * 32;
             X.sY = X.cP + (size_t)2 * TR * 32;
@@ -375,7 +420,7 @@ namespace pvc
                                 for (int k = 0; k < 4; ++k)
                                 {
                                     const float4 v = loadWord(q0 + (size_t)j * L.pitch + k);
-                                    p[j][k] = v.x; vx[j][k] = v.y; vy[j][k] = v.z;
+                                    p[j][k] = opaqueCopy(v.x, A.zero); vx[j][k] = opaqueCopy(v.y, A.zero); vy[j][k] = opaqueCopy(v.z, A.zero);
                                     bad |= __float_as_int(v.w) ^ tag;
                                 }
                             }
@@ -386,23 +431,24 @@ namespace pvc
                         __nanosleep(20);
                     }
                 }
+                __syncwarp();            // the lanes that polled rejoin the others before the (warp-aligned) barriers below
                 PVC_STAMP(A, g, 1);
                 sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-                phaseSync<NW, PAIR>(wp);
+                phaseSync<NW, SYNC>(wp, X.edge, X.parity);
                 PVC_STAMP(A, g, 2);
 
                 uint32_t activity = 0u;
                 if (firstGen == kNeverActive)
                 {
-                    if (general) stepLoop<NW, R, PAIR, true, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
-                    else stepLoop<NW, R, PAIR, false, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    if (general) stepLoop<NW, R, SYNC, true, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    else stepLoop<NW, R, SYNC, false, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
                     const bool hot = ((activity & 0x7fffffffu) != 0u) && !haloLane;
                     if (__any_sync(0xffffffffu, hot)) firstGen = g;
                 }
                 else
                 {
-                    if (general) stepLoop<NW, R, PAIR, true, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
-                    else stepLoop<NW, R, PAIR, false, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    if (general) stepLoop<NW, R, SYNC, true, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    else stepLoop<NW, R, SYNC, false, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
                 }
 
                 PVC_STAMP(A, g, 3);
@@ -419,7 +465,8 @@ namespace pvc
                             if ((sendRows >> j) & 1u)
                             {
                                 #pragma unroll
-                                for (int k = 0; k < 4; ++k) storeWord(q0 + (size_t)j * L.pitch + k, p[j][k], vx[j][k], vy[j][k], tag);
+                                for (int k = 0; k < 4; ++k)
+                                    storeWord(q0 + (size_t)j * L.pitch + k, opaqueCopy(p[j][k], A.zero), opaqueCopy(vx[j][k], A.zero), opaqueCopy(vy[j][k], A.zero), tag);
                             }
                     }
                 }
@@ -504,22 +551,22 @@ namespace pvc
             src[i].dead = (interior && __float_as_uint(w[cellIndex(L, r, c)]) == kAirBits) ? 0 : 1;
         }
 
-        template <int NW, int R, int MINB>
+        template <int NW, int R, int MINB, int SYNC>
         static int capacity(int device)
         {
             static int cached[64] = {};
             int& c = cached[device & 63];
             if (c) return c;
             const size_t smem = Smem<NW, R>::total;
-            if (cudaFuncSetAttribute(residentKernel<NW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (cudaFuncSetAttribute(residentKernel<NW, R, MINB, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
             int perSm = 0, sms = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, residentKernel<NW, R, MINB>, NW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, residentKernel<NW, R, MINB, SYNC>, NW * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
             if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); return 0; }
             c = perSm * sms;
             return c;
         }
 
-        template <int NW, int R, int MINB>
+        template <int NW, int R, int MINB, int SYNC>
         static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
         {
             const Layout& L = s->L;
@@ -527,7 +574,7 @@ namespace pvc
             if (!hist || !s->lin[0] || !s->resXchg) { setError("resident step kernel: history / coefficient planes / mailbox missing"); return PVC_ERR_INVALID; }
             if (L.hist_chunk != kHistChunkDefault || L.tile_rows != NW * R) { setError("resident step kernel: layout does not match the variant"); return PVC_ERR_INVALID; }
             const int tps = L.tiles_x * L.tiles_y;
-            const int cap = capacity<NW, R, MINB>(s->device);
+            const int cap = capacity<NW, R, MINB, SYNC>(s->device);
             if (cap < tps) { setError("resident step kernel: %d tiles per source exceed the %d co-resident CTAs of this device", tps, cap); return PVC_ERR_INVALID; }
             const int perLaunch = cap / tps;
             const int gens = (t1 + kTileK - 1) / kTileK;
@@ -547,7 +594,7 @@ namespace pvc
             A.hist = hist; A.mode = s->slowMask; A.cP = s->lin[0]; A.sX = s->lin[1]; A.sY = s->lin[2];
             A.firstActive = s->firstActive; A.src = s->src; A.pulse = s->pulse;
             A.xchg = reinterpret_cast<float4*>(s->resXchg); A.xchgSlot = (size_t)s->cfg.max_sources * L.plane; A.tagBase = s->resEpoch << 16;
-            A.abortFlag = s->tileCounters;
+            A.abortFlag = s->tileCounters; A.zero = 0;
             A.tilesPerSource = tps; A.numGen = gens; A.T = t1; A.courant = s->cfg.courant;
 #ifdef PVC_TUNING
             { static const char* d = getenv("PVC_RES_DEBUG"); A.dbg = d ? atoi(d) : 0; }
@@ -567,7 +614,7 @@ namespace pvc
                 A.s0 = s0; A.nsrc = (nsrc - s0 < perLaunch) ? (nsrc - s0) : perLaunch;
                 void* params[2] = { &Lc, &A };
                 // cooperative launch: fails instead of deadlocking if the CTAs could not all be resident
-                const cudaError_t e = cudaLaunchCooperativeKernel((const void*)residentKernel<NW, R, MINB>, dim3((unsigned)(tps * A.nsrc)), dim3(NW * 32), params,
+                const cudaError_t e = cudaLaunchCooperativeKernel((const void*)residentKernel<NW, R, MINB, SYNC>, dim3((unsigned)(tps * A.nsrc)), dim3(NW * 32), params,
                                                                   Smem<NW, R>::total, s->stream);
                 if (e != cudaSuccess) { setError("resident step kernel launch (%d CTAs): %s", tps * A.nsrc, cudaGetErrorString(e)); return PVC_ERR_CUDA; }
                 *launches += 1;
@@ -580,7 +627,12 @@ namespace pvc
                 cudaMemcpy(h.data(), traceBuf, traceWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
                 const int ctas = tps * A.nsrc;
                 double sum[5] = {}; long cnt = 0;
+                std::vector<std::pair<double, int>> busy;      // per CTA: mean (steps + mail) and its index
+                std::vector<uint32_t> modes((size_t)tps * 32);
+                cudaMemcpy(modes.data(), s->slowMask, sizeof(uint32_t) * modes.size(), cudaMemcpyDeviceToHost);
                 for (int c = 0; c < ctas; ++c)
+                {
+                    double b = 0; long n = 0;
                     for (int k = 1; k + 1 < kTracePasses; ++k)
                     {
                         const unsigned long long* a = h.data() + ((size_t)c * kTracePasses + k) * kTraceSlots;
@@ -591,10 +643,32 @@ namespace pvc
                         sum[2] += (double)a[3] - (double)a[2];       // 4 steps
                         sum[3] += (double)a[4] - (double)a[3];       // strips mailed
                         sum[4] += (double)nx[0] - (double)a[0];      // pass period
+                        b += (double)a[4] - (double)a[1]; ++n;
                         ++cnt;
                     }
+                    if (n) busy.push_back(std::make_pair(b / n, c));
+                }
                 if (cnt) fprintf(stderr, "[res trace] NW=%d ctas=%d n=%ld  reload %.0f  exchange+sync %.0f  steps %.0f  mail %.0f | period %.0f ns (thread 0 of every CTA)\n",
                                  NW, ctas, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt);
+                if (!busy.empty())
+                {
+                    std::sort(busy.begin(), busy.end());
+                    fprintf(stderr, "[res trace] busy time per pass (exchange+steps+mail) over CTAs: min %.0f  median %.0f  max %.0f ns; slowest:", busy.front().first, busy[busy.size() / 2].first, busy.back().first);
+                    for (size_t k = 0; k < 6 && k < busy.size(); ++k)
+                    {
+                        const int c = busy[busy.size() - 1 - k].second, tile = c % tps;
+                        int gen = 0; for (int w = 0; w < NW; ++w) gen += modes[(size_t)tile * 32 + w] != 0u;
+                        fprintf(stderr, " tile(%d,%d) %.0f ns %d/%d general;", tile % L.tiles_x, tile / L.tiles_x, busy[busy.size() - 1 - k].first, gen, NW);
+                    }
+                    fprintf(stderr, " fastest:");
+                    for (size_t k = 0; k < 3 && k < busy.size(); ++k)
+                    {
+                        const int c = busy[k].second, tile = c % tps;
+                        int gen = 0; for (int w = 0; w < NW; ++w) gen += modes[(size_t)tile * 32 + w] != 0u;
+                        fprintf(stderr, " tile(%d,%d) %.0f ns %d/%d general;", tile % L.tiles_x, tile / L.tiles_x, busy[k].first, gen, NW);
+                    }
+                    fprintf(stderr, "\n");
+                }
             }
 #endif
             s->cur = gens & 1;
@@ -607,12 +681,18 @@ namespace pvc
     {
         switch (variant)
         {
-            case 60: return res::launch<8, 4, 2>(s, nsrc, t0, t1, hist, launches);
-            case 61: return res::launch<10, 4, 2>(s, nsrc, t0, t1, hist, launches);
-            case 62: return res::launch<12, 4, 2>(s, nsrc, t0, t1, hist, launches);
-            case 63: return res::launch<16, 4, 1>(s, nsrc, t0, t1, hist, launches);
-            case 64: return res::launch<20, 4, 1>(s, nsrc, t0, t1, hist, launches);
-            case 65: return res::launch<18, 4, 1>(s, nsrc, t0, t1, hist, launches);
+            case 60: return res::launch<8, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 61: return res::launch<10, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 62: return res::launch<12, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 63: return res::launch<16, 4, 1, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
+            case 64: return res::launch<20, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 65: return res::launch<18, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 66: return res::launch<8, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 67: return res::launch<10, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 68: return res::launch<12, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 69: return res::launch<16, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 70: return res::launch<20, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 71: return res::launch<18, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
             default: setError("resident step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -621,12 +701,18 @@ namespace pvc
     {
         switch (variant)
         {
-            case 60: return res::capacity<8, 4, 2>(device);
-            case 61: return res::capacity<10, 4, 2>(device);
-            case 62: return res::capacity<12, 4, 2>(device);
-            case 63: return res::capacity<16, 4, 1>(device);
-            case 64: return res::capacity<20, 4, 1>(device);
-            case 65: return res::capacity<18, 4, 1>(device);
+            case 60: return res::capacity<8, 4, 2, res::kSyncCta>(device);
+            case 61: return res::capacity<10, 4, 2, res::kSyncCta>(device);
+            case 62: return res::capacity<12, 4, 2, res::kSyncCta>(device);
+            case 63: return res::capacity<16, 4, 1, res::kSyncNamed>(device);
+            case 64: return res::capacity<20, 4, 1, res::kSyncCta>(device);
+            case 65: return res::capacity<18, 4, 1, res::kSyncCta>(device);
+            case 66: return res::capacity<8, 4, 2, res::kSyncMbar>(device);
+            case 67: return res::capacity<10, 4, 2, res::kSyncMbar>(device);
+            case 68: return res::capacity<12, 4, 2, res::kSyncMbar>(device);
+            case 69: return res::capacity<16, 4, 1, res::kSyncMbar>(device);
+            case 70: return res::capacity<20, 4, 1, res::kSyncMbar>(device);
+            case 71: return res::capacity<18, 4, 1, res::kSyncMbar>(device);
             default: return 0;
         }
     }

@@ -538,8 +538,8 @@ def main():
                        50: "pvc::ws2::stepKernel<8,4,1,false,true> (generational kernel, 32-row tiles)",
                        18: "pvc::fusedStepKernel<8,6,2> (one launch per 4 time steps)",
                        60: "pvc::res::residentKernel<8,4,2>", 61: "pvc::res::residentKernel<10,4,2>", 62: "pvc::res::residentKernel<12,4,2>",
-                       63: "pvc::res::residentKernel<16,4,1>", 64: "pvc::res::residentKernel<20,4,1>", 65: "pvc::res::residentKernel<18,4,1>"}.get(kernel_variant, f"step kernel variant {kernel_variant}")
-        if kernel_variant in (60, 61, 62, 63, 64, 65):
+                       63: "pvc::res::residentKernel<16,4,1>", 64: "pvc::res::residentKernel<20,4,1>", 65: "pvc::res::residentKernel<18,4,1>", 66: "pvc::res::residentKernel<16,5,1>"}.get(kernel_variant, f"step kernel variant {kernel_variant}")
+        if kernel_variant in (60, 61, 62, 63, 64, 65, 66):
             kernel_name += " (resident kernel: one launch per source batch runs all time steps with the tile state in registers; only halo strips pass through L2)"
         if args.step_kernel == 1:
             kernel_name = "pvc::baselinePressureKernel + pvc::baselineVelocityKernel"

@@ -21,7 +21,7 @@ int main(int argc, char** argv)
     if (argc < 2)
     {
         std::fprintf(stderr, "usage: %s scene.pv [--size metres] [--res 275|375|500|750] [--listener x z] [--emitter x z]... "
-                             "[--frames n] [--move id dx dy] [--ir]\n", argv[0]);
+                             "[--frames n] [--move id dx dy] [--ir] [--save out.pv]\n", argv[0]);
         return 2;
     }
     float size = 25.f;                                  // Sandbox world (main.cpp:17)
@@ -31,6 +31,7 @@ int main(int argc, char** argv)
     int frames = 2, moveId = -1;
     float moveDx = 0.f, moveDy = 0.f;
     bool printIr = false;
+    const char* savePath = nullptr;
     for (int i = 2; i < argc; ++i)
     {
         if (!std::strcmp(argv[i], "--size") && i + 1 < argc) size = (float)std::atof(argv[++i]);
@@ -40,6 +41,7 @@ int main(int argc, char** argv)
         else if (!std::strcmp(argv[i], "--frames") && i + 1 < argc) frames = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--move") && i + 3 < argc) { moveId = std::atoi(argv[++i]); moveDx = (float)std::atof(argv[++i]); moveDy = (float)std::atof(argv[++i]); }
         else if (!std::strcmp(argv[i], "--ir")) printIr = true;
+        else if (!std::strcmp(argv[i], "--save") && i + 1 < argc) savePath = argv[++i];
         else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     if (emitters.empty()) emitters.push_back(Planeverb::vec3(5.f, 0.f, 6.f));
@@ -115,6 +117,21 @@ int main(int argc, char** argv)
         std::printf("emitter %zu at %.4f %.4f : occlusion %.9g wetGain %.9g rt60 %.9g lowpass %.9g direction %.9g %.9g sourceDirectivity %.9g %.9g\n",
                     i, emitters[i].x, emitters[i].z, o.occlusion, o.wetGain, o.rt60, o.lowpass, o.direction.x, o.direction.y,
                     o.sourceDirectivity.x, o.sourceDirectivity.y);
+    }
+    if (savePath)
+    {
+        // the Sandbox's scene writer (PlaneverbSandbox/src/Editor/Editor.cpp:219-243): object count, then one line per object
+        // "id posX posY width height absorption" with the ids AddGeometry handed out -- after the optional --move, so the file
+        // holds the scene as it was last solved
+        std::ofstream out(savePath);
+        if (!out) { std::fprintf(stderr, "cannot write %s\n", savePath); Planeverb::Exit(); return 1; }
+        out << boxes.size() << std::endl;
+        for (size_t i = 0; i < boxes.size(); ++i)
+        {
+            Planeverb::AABB b = boxes[i];
+            if ((int)i == moveId) { b.position.x += moveDx; b.position.y += moveDy; }
+            out << ids[i] << " " << b.position.x << " " << b.position.y << " " << b.width << " " << b.height << " " << b.absorption << std::endl;
+        }
     }
     if (printIr)
     {

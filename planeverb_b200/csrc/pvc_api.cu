@@ -64,11 +64,11 @@ namespace pvc
     static ResidentChoice bestResident(const pvc_config& c, int sms)
     {
         ResidentChoice best = { 0, 0.0 };
-        for (int v = 60; v <= 65; ++v)
+        for (int v = 60; v <= 71; ++v)
         {
             if (!variantAvailable(v)) continue;
             const int nw = variantWarps(v), perSm = variantMinBlocks(v);
-            const int vr = nw * 4 - 2 * kTileK;
+            const int vr = fusedTileRows(v) - 2 * kTileK;
             const long tiles = (long)((c.gx + vr - 1) / vr) * ((c.gy + 1 + kValidCols - 1) / kValidCols);
             const long cap = (long)sms * perSm;
             if (tiles > cap) continue;

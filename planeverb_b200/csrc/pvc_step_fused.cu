@@ -1121,7 +1121,7 @@ namespace pvc
     // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, kind
     //   kind 0 one launch per 4 steps (fusedStepKernel)      1 persistent        2 TMA persistent   3 generational
     //        4 first warp-specialised generational           5 ws2 (pvc_step_ws2.cu)                6 resident (pvc_step_res.cu)
-    // The default build carries what the product selects -- 47 / 50 (ws2), 60..65 (resident), 18 (fallback without the TMA
+    // The default build carries what the product selects -- 47 / 50 (ws2), 60..71 (resident), 18 (fallback without the TMA
     // driver entry point) -- plus step_kernel = 1 (two-launch baseline, pvc_step.cu).  Everything else documents the
     // search (profiles/r01_variants.txt) and is compiled only with make EXTRA=-DPVC_ALL_VARIANTS.
     struct Variant { int nw, r, minBlocks, persistent, builtin; };
@@ -1138,7 +1138,7 @@ namespace pvc
                                          {12, 4, 1, 5, 0}, {12, 5, 1, 5, 0},                             // 52, 53
                                          {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0},   // 54..59 unused
                                          {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1},    // 60..65: resident (CTA / named barriers)
-                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1} };  // 66..71: resident, mbarrier edge synchronisation
+                                         {16, 5, 1, 6, 1}, {18, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1} };                                                        // 66: resident, 5 rows per warp; 67, 68: 65 / 64 with the CTA barrier
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     bool variantAvailable(int variant)
@@ -1490,6 +1490,7 @@ namespace pvc
             case 1604: return maskVariant<16, 4, 1>(s);
             case 2004: return maskVariant<20, 4, 1>(s);
             case 1804: return maskVariant<18, 4, 1>(s);
+            case 1605: return maskVariant<16, 5, 1>(s);
 #ifdef PVC_ALL_VARIANTS
             case 1008: return maskVariant<10, 8, 1>(s);
             case 3002: return maskVariant<30, 2, 1>(s);

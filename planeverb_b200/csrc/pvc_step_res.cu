@@ -68,46 +68,33 @@ namespace pvc
         // moves per time step; copying through an integer op with a run-time zero keeps the mailbox quads temporaries.
         __device__ __forceinline__ float opaqueCopy(float v, int zero) { return __int_as_float(__float_as_int(v) ^ zero); }
         __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-        __device__ __forceinline__ uint32_t smemAddr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-        __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
-        {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
-        }
-        __device__ __forceinline__ void mbarArrive(uint64_t* bar)
-        {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
-        }
-        __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
-        {
-            asm volatile("{\n.reg .pred r;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 r, [%0], %1;\n@!r bra W_%=;\n}\n"
-                         ::"r"(smemAddr(bar)), "r"(parity) : "memory");
-        }
         // Synchronisation of the step loop: a warp exchanges halo rows only with the warp above and the warp below.
         //   kSyncCta   one CTA barrier (every warp waits for the slowest)
         //   kSyncNamed the named barrier of each shared edge (id = upper warp + 1, 64 threads; even warps take the lower edge first,
         //              odd warps the upper one: no cycle) -- at most 16 ids, and named barriers are an SM resource
-        //   kSyncMbar  one shared-memory mbarrier per edge (2 arrivals): arrive on both edges, then wait for both -- any tile height,
-        //              any number of CTAs per SM.  Warps far from a slow warp run ahead of it by up to their distance in edges.
-        enum { kSyncCta = 0, kSyncNamed = 1, kSyncMbar = 2 };
+        // (One shared-memory mbarrier per edge -- any tile height, any number of CTAs per SM -- was measured too: 1.8x slower than
+        // the CTA barrier on every grid, profiles/r02_resident_variants.txt; try_wait costs ~90 cycles even when the phase is over.)
+        //   kSyncTail  tiles taller than 16 warps: named barriers for the edges 1 .. 15 as above, and ONE barrier (id 0) shared by
+        //              the warps 15 .. NW-1 in place of the edges below warp 15 -- 16 ids, and only the last few warps are coupled
+        enum { kSyncCta = 0, kSyncNamed = 1, kSyncTail = 2 };
         template <int NW, int SYNC>
-        __device__ __forceinline__ void phaseSync(int wp, uint64_t* edge, uint32_t& parity)
+        __device__ __forceinline__ void phaseSync(int wp)
         {
             if (SYNC == kSyncNamed)
             {
                 if (wp & 1) { pairBarrier(wp); if (wp + 1 < NW) pairBarrier(wp + 1); }
                 else { if (wp + 1 < NW) pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
             }
-            else if (SYNC == kSyncMbar)
+            else if (SYNC == kSyncTail)
             {
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0)
+                // warp 15 (odd) meets warp 14 on edge 15 first, then the tail group; warp 14 (even) takes edge 15 first as well: no cycle
+                if (wp >= 15)
                 {
-                    if (wp > 0) mbarArrive(edge + wp);
-                    if (wp + 1 < NW) mbarArrive(edge + wp + 1);
+                    if (wp == 15) pairBarrier(15);
+                    asm volatile("bar.sync 0, %0;" ::"n"((NW - 15) * 32) : "memory");
                 }
-                if (wp > 0) mbarWait(edge + wp, parity);
-                if (wp + 1 < NW) mbarWait(edge + wp + 1, parity);
-                parity ^= 1u;
+                else if (wp & 1) { pairBarrier(wp); pairBarrier(wp + 1); }
+                else { pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
             }
             else __syncthreads();
         }
@@ -138,7 +125,7 @@ namespace pvc
             int numGen, T;
             float courant;
 #ifdef PVC_TUNING
-            int dbg;                               // tuning builds only (results invalid): bit 0 no history stores, bit 1 no neighbour wait / halo reload
+            int dbg;                               // tuning builds only: bit 0 no history stores, bit 1 no neighbour wait / halo reload (both: results invalid), bit 2 no nanosleep in the poll
             unsigned long long* trace;             // per CTA x traced pass x 8 %globaltimer stamps (null: off)
 #endif
         };
@@ -229,8 +216,7 @@ namespace pvc
             static constexpr size_t offVxTop = 0;
             static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
             static constexpr size_t offCoef = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);        // [3][TR][32] float4: cP, sX, sY
-            static constexpr size_t offEdge = offCoef + (size_t)3 * TR * 32 * sizeof(float4);          // [NW + 1] mbarriers, one per warp edge
-            static constexpr size_t total = offEdge + (size_t)(NW + 2) * sizeof(uint64_t);
+            static constexpr size_t total = offCoef + (size_t)3 * TR * 32 * sizeof(float4);
         };
 
         // everything of a thread that is fixed for the solve
@@ -244,11 +230,50 @@ namespace pvc
             int sj, sk;               // pulse cell inside the thread's block (sj < 0: not here)
             const float* pulse;
             const float4* cP; const float4* sX; const float4* sY;       // this thread's coefficient float4s (row stride 32), shared memory
-            uint64_t* edge;           // kSyncMbar: the CTA's edge barriers
-            uint32_t parity;          // kSyncMbar: phase parity of the next synchronisation
+            int zero;
         };
 
         // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised
+        // record sample (FDTD.cpp:226-231): the pressure of the thread's owned rows into the time-major history, streaming stores
+        template <int R>
+        __device__ __forceinline__ void recordSample(Ctx& X, const float (&p)[R][4])
+        {
+            #pragma unroll
+            for (int j = 0; j < R; ++j)
+                if ((X.ownRows >> j) & 1u)
+                {
+#ifdef PVC_RES_COPYREC
+                    // experiment: store from copies, so that the next pressure update does not wait for the store to have read p
+                    __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow),
+                           make_float4(opaqueCopy(p[j][0], X.zero), opaqueCopy(p[j][1], X.zero), opaqueCopy(p[j][2], X.zero), opaqueCopy(p[j][3], X.zero)));
+#else
+                    __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
+#endif
+                }
+            X.hist += kHistChunkDefault;
+        }
+        // inject (FDTD.cpp:234): pulse sample t into the source cell, if this thread holds it
+        template <int R>
+        __device__ __forceinline__ void injectSample(const Ctx& X, float (&p)[R][4], const int t)
+        {
+            if (X.sj >= 0)
+            {
+                // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
+                const float add = __ldg(X.pulse + t);
+                const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
+                const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if (j == X.sj)
+                    {
+                        p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
+                        p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
+                    }
+            }
+        }
+
+        // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised.  The record + inject of
+        // the LAST step are left to the caller, which mails the strips first: the neighbours wait for those, nobody for the history.
         template <int NW, int R, int SYNC, bool GEN, bool TRACK>
         __device__ __forceinline__ void stepLoop(Ctx& X, const int t0, const int nsteps, float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
                                                  float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
@@ -260,15 +285,9 @@ namespace pvc
                 // ---- pressure sub-step (FDTD.cpp:125-141)
                 pressureStep<R, GEN>(p, vx, vy, sVxTop[wp + 1][lane], X.C, X.cP);
                 sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
-                phaseSync<NW, SYNC>(wp, X.edge, X.parity);
+                phaseSync<NW, SYNC>(wp);
                 // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
                 velocityStep<R, GEN>(p, vx, vy, sPBot[wp][lane], X.C, X.sX, X.sY);
-                // ---- record sample t0 + step (FDTD.cpp:226-231), then inject (FDTD.cpp:234)
-                #pragma unroll
-                for (int j = 0; j < R; ++j)
-                    if ((X.ownRows >> j) & 1u)
-                        __stcs(reinterpret_cast<float4*>(X.hist + (size_t)j * X.histRow), make_float4(p[j][0], p[j][1], p[j][2], p[j][3]));
-                X.hist += kHistChunkDefault;
                 if (TRACK)
                 {
                     #pragma unroll
@@ -278,24 +297,13 @@ namespace pvc
                         activity |= __float_as_uint(p[j][2]) | __float_as_uint(p[j][3]);
                     }
                 }
-                if (X.sj >= 0)
-                {
-                    // adding +0 to the three other cells of the row is exact (it can only turn -0 into +0)
-                    const float add = __ldg(X.pulse + t0 + step);
-                    const float a0 = (X.sk == 0) ? add : 0.f, a1 = (X.sk == 1) ? add : 0.f;
-                    const float a2 = (X.sk == 2) ? add : 0.f, a3 = (X.sk == 3) ? add : 0.f;
-                    #pragma unroll
-                    for (int j = 0; j < R; ++j)
-                        if (j == X.sj)
-                        {
-                            p[j][0] = __fadd_rn(p[j][0], a0); p[j][1] = __fadd_rn(p[j][1], a1);
-                            p[j][2] = __fadd_rn(p[j][2], a2); p[j][3] = __fadd_rn(p[j][3], a3);
-                        }
-                }
                 if (step + 1 < nsteps)
                 {
+                    // ---- record sample t0 + step, then inject
+                    recordSample<R>(X, p);
+                    injectSample<R>(X, p, t0 + step);
                     sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-                    phaseSync<NW, SYNC>(wp, X.edge, X.parity);            // also the write-after-read fence of sPBot
+                    phaseSync<NW, SYNC>(wp);            // also the write-after-read fence of sPBot
                 }
             }
         }
@@ -307,6 +315,7 @@ namespace pvc
             using SM = Smem<NW, R>;
             constexpr int TR = SM::TR;
             static_assert(SYNC != kSyncNamed || NW <= 16, "16 named barriers per CTA");
+            static_assert(SYNC != kSyncTail || NW > 16, "the tail group starts at warp 15");
             extern __shared__ __align__(128) unsigned char smemRaw[];
             float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
             float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
@@ -324,13 +333,10 @@ namespace pvc
             const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
             const size_t src0 = (size_t)s * L.plane + cell0;
 
-            uint64_t* const edge = reinterpret_cast<uint64_t*>(smemRaw + SM::offEdge);
             if (wp == 0)
             {
                 sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (SYNC == kSyncMbar && lane <= NW) mbarInit(edge + lane, 2);
-                if (SYNC == kSyncMbar) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             const bool general = A.mode[(size_t)tile * 32 + wp] != 0u;
             if (general)
@@ -360,15 +366,18 @@ namespace pvc
                 // owned row gx - 1 of the same step, so it is always current there and is recorded / stored with the owned rows
                 const bool owned = (!top && !bottom && r < L.rows) || (bottom && r == L.gx);
                 if (owned) ownRows |= 1u << j;
-                // a halo cell is reloaded iff the tile that owns it exists; everything else outside the tile is guard band (zero for ever)
-                const bool rowOk = top ? up : (bottom ? down : true);
+                // A halo cell is reloaded iff the tile that owns it exists; everything else outside the tile is guard band (zero for
+                // ever).  The padding row in the bottom halo is LIVE (vx = p of the row above it): in the halo lanes it is refreshed
+                // from the left / right tile, which keeps it current the same way, or its error would creep into the halo columns.
+                const bool liveRow = bottom && r == L.gx;
+                const bool rowOk = top ? up : (bottom ? (down || liveRow) : true);
                 const bool colOk = (lane == 0) ? left : (lane == 31 ? right : true);
-                if ((top || bottom || haloLane) && rowOk && colOk) loadRows |= 1u << j;
+                if ((top || (bottom && !liveRow) || haloLane) && rowOk && colOk) loadRows |= 1u << j;
                 // an owned cell is mailed iff it lies within 4 cells of an edge behind which a tile exists (corners go with the rows)
-                const bool inTile = !top && !bottom && !haloLane;
-                const bool nearRow = (tr < 2 * kTileK && up) || (tr >= TR - 2 * kTileK && down);
+                const bool inRows = (!top && !bottom) || liveRow;
+                const bool nearRow = !liveRow && ((tr < 2 * kTileK && up) || (tr >= TR - 2 * kTileK && down));
                 const bool nearCol = (lane == 1 && left) || (lane == 30 && right);
-                if (inTile && (nearRow || nearCol)) sendRows |= 1u << j;
+                if (inRows && !haloLane && (nearRow || nearCol)) sendRows |= 1u << j;
             }
             if (haloLane || cBase >= L.cols) ownRows = 0u;
 
@@ -384,8 +393,7 @@ namespace pvc
                 const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
                 X.sj = (hasSrc && !sp.dead) ? sj : -1; X.sk = sk;
             }
-            X.pulse = A.pulse;
-            X.edge = edge; X.parity = 0u;
+            X.pulse = A.pulse; X.zero = A.zero;
             X.cP = sCoef + (size_t)(wp * R) * 32 + lane;
             X.sX = X.cP + (size_t)TR * 32;
             X.sY = X.cP + (size_t)2 * TR * 32;
@@ -408,33 +416,48 @@ namespace pvc
                     // ---- reload the halo ring from the mailbox: the words the neighbours wrote at the end of pass g - 1 carry tag g
                     const float4* q0 = A.xchg + (size_t)(g & (kSlots - 1)) * A.xchgSlot + src0;
                     const int tag = A.tagBase + g;
+                    // Poll ONE word -- the last one its writer stores -- and fetch the whole ring only when that one has arrived
+                    // (polling all 16 words of every halo thread kept ~50 KB per CTA and iteration moving through the L2 and made
+                    // the hand-over 3 us long); any word that still lags is caught by its own tag and fetched again.
+                    int jLast = 0;
+                    #pragma unroll
+                    for (int j = 0; j < R; ++j) if ((loadRows >> j) & 1u) jLast = j;
+                    const float4* qLast = q0 + (size_t)jLast * L.pitch + 3;
                     unsigned spins = 0;
+                    bool waiting = true;
                     while (true)
                     {
-                        int bad = 0;
-                        #pragma unroll
-                        for (int j = 0; j < R; ++j)
-                            if ((loadRows >> j) & 1u)
-                            {
-                                #pragma unroll
-                                for (int k = 0; k < 4; ++k)
+                        if (waiting)
+                        {
+                            if (__float_as_int(loadWord(qLast).w) == tag) waiting = false;
+                        }
+                        if (!waiting)
+                        {
+                            int bad = 0;
+                            #pragma unroll
+                            for (int j = 0; j < R; ++j)
+                                if ((loadRows >> j) & 1u)
                                 {
-                                    const float4 v = loadWord(q0 + (size_t)j * L.pitch + k);
-                                    p[j][k] = opaqueCopy(v.x, A.zero); vx[j][k] = opaqueCopy(v.y, A.zero); vy[j][k] = opaqueCopy(v.z, A.zero);
-                                    bad |= __float_as_int(v.w) ^ tag;
+                                    #pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                    {
+                                        const float4 v = loadWord(q0 + (size_t)j * L.pitch + k);
+                                        p[j][k] = opaqueCopy(v.x, A.zero); vx[j][k] = opaqueCopy(v.y, A.zero); vy[j][k] = opaqueCopy(v.z, A.zero);
+                                        bad |= __float_as_int(v.w) ^ tag;
+                                    }
                                 }
-                            }
-                        if (bad == 0) break;
+                            if (bad == 0) break;
+                        }
                         // not there yet (or a neighbour died): bounded, and a raised abort flag ends every later wait at once
                         if ((spins & 0x3fu) == 0u && (spins > (1u << 18) || *(volatile int*)A.abortFlag)) { atomicExch(A.abortFlag, 1); break; }
                         ++spins;
-                        __nanosleep(20);
+                        if (!PVC_DBG(A, 2)) __nanosleep(20);
                     }
                 }
                 __syncwarp();            // the lanes that polled rejoin the others before the (warp-aligned) barriers below
                 PVC_STAMP(A, g, 1);
                 sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-                phaseSync<NW, SYNC>(wp, X.edge, X.parity);
+                phaseSync<NW, SYNC>(wp);
                 PVC_STAMP(A, g, 2);
 
                 uint32_t activity = 0u;
@@ -453,6 +476,10 @@ namespace pvc
 
                 PVC_STAMP(A, g, 3);
                 const bool lastPass = g + 1 == A.numGen;
+                // the last step's record + inject: the thread that holds the source cell (one per tile, its mailed value includes the
+                // injection) does them now, every other thread after the strips have left
+                const int tLast = t0 + nsteps - 1;
+                if (X.sj >= 0) { recordSample<R>(X, p); injectSample<R>(X, p, tLast); }
                 if (!lastPass)
                 {
                     // ---- mail the cells the neighbours need for pass g + 1
@@ -500,6 +527,7 @@ namespace pvc
                             __stcg(reinterpret_cast<float4*>(gy + (size_t)j * L.pitch), make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]));
                         }
                 }
+                if (X.sj < 0) recordSample<R>(X, p);
                 PVC_STAMP(A, g, 4);
             }
             if (lane == 0 && firstGen != kNeverActive && A.firstActive)
@@ -648,6 +676,25 @@ namespace pvc
                     }
                     if (n) busy.push_back(std::make_pair(b / n, c));
                 }
+                {
+                    // hand-over latency seen by thread 0 (warp 0, lane 0: its halo words come from the upper-left tile, or the left one in
+                    // the top tile row): its reload of pass k completes this long after that tile finished the steps of pass k - 1
+                    double lat = 0; long nl = 0;
+                    for (int c = 0; c < ctas; ++c)
+                    {
+                        const int tile = c % tps, tx = tile % L.tiles_x, ty = tile / L.tiles_x;
+                        if (tx == 0) continue;
+                        const int nb = (c - tile) + (ty > 0 ? (ty - 1) : ty) * L.tiles_x + (tx - 1);
+                        for (int k = 2; k + 1 < kTracePasses; ++k)
+                        {
+                            const unsigned long long* a = h.data() + ((size_t)c * kTracePasses + k) * kTraceSlots;
+                            const unsigned long long* b = h.data() + ((size_t)nb * kTracePasses + (k - 1)) * kTraceSlots;
+                            if (!a[1] || !b[3]) continue;
+                            lat += (double)a[1] - (double)b[3]; ++nl;
+                        }
+                    }
+                    if (nl) fprintf(stderr, "[res trace] hand-over: reload of pass k done %.0f ns after the writer tile finished the steps of pass k-1 (n=%ld)\n", lat / nl, nl);
+                }
                 if (cnt) fprintf(stderr, "[res trace] NW=%d ctas=%d n=%ld  reload %.0f  exchange+sync %.0f  steps %.0f  mail %.0f | period %.0f ns (thread 0 of every CTA)\n",
                                  NW, ctas, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt);
                 if (!busy.empty())
@@ -685,14 +732,14 @@ namespace pvc
             case 61: return res::launch<10, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
             case 62: return res::launch<12, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
             case 63: return res::launch<16, 4, 1, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
-            case 64: return res::launch<20, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 65: return res::launch<18, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 66: return res::launch<8, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
-            case 67: return res::launch<10, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
-            case 68: return res::launch<12, 4, 2, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
-            case 69: return res::launch<16, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
-            case 70: return res::launch<20, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
-            case 71: return res::launch<18, 4, 1, res::kSyncMbar>(s, nsrc, t0, t1, hist, launches);
+            case 64: return res::launch<20, 4, 1, res::kSyncTail>(s, nsrc, t0, t1, hist, launches);
+            case 65: return res::launch<18, 4, 1, res::kSyncTail>(s, nsrc, t0, t1, hist, launches);
+            case 66: return res::launch<16, 5, 1, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
+            case 67: return res::launch<18, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 68: return res::launch<20, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
+            case 69: return res::launch<8, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
+            case 70: return res::launch<10, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
+            case 71: return res::launch<12, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
             default: setError("resident step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -705,14 +752,14 @@ namespace pvc
             case 61: return res::capacity<10, 4, 2, res::kSyncCta>(device);
             case 62: return res::capacity<12, 4, 2, res::kSyncCta>(device);
             case 63: return res::capacity<16, 4, 1, res::kSyncNamed>(device);
-            case 64: return res::capacity<20, 4, 1, res::kSyncCta>(device);
-            case 65: return res::capacity<18, 4, 1, res::kSyncCta>(device);
-            case 66: return res::capacity<8, 4, 2, res::kSyncMbar>(device);
-            case 67: return res::capacity<10, 4, 2, res::kSyncMbar>(device);
-            case 68: return res::capacity<12, 4, 2, res::kSyncMbar>(device);
-            case 69: return res::capacity<16, 4, 1, res::kSyncMbar>(device);
-            case 70: return res::capacity<20, 4, 1, res::kSyncMbar>(device);
-            case 71: return res::capacity<18, 4, 1, res::kSyncMbar>(device);
+            case 64: return res::capacity<20, 4, 1, res::kSyncTail>(device);
+            case 65: return res::capacity<18, 4, 1, res::kSyncTail>(device);
+            case 66: return res::capacity<16, 5, 1, res::kSyncNamed>(device);
+            case 67: return res::capacity<18, 4, 1, res::kSyncCta>(device);
+            case 68: return res::capacity<20, 4, 1, res::kSyncCta>(device);
+            case 69: return res::capacity<8, 4, 2, res::kSyncNamed>(device);
+            case 70: return res::capacity<10, 4, 2, res::kSyncNamed>(device);
+            case 71: return res::capacity<12, 4, 2, res::kSyncNamed>(device);
             default: return 0;
         }
     }

@@ -94,13 +94,15 @@ def timing(scene, n, T, S, variants, res=275):
 if "parity" in what:
     print("== parity")
     ok = True
-    for var in (60, 61, 62, 63, 64, 65):
+    for var in (60, 61, 62, 63, 64, 65, 66):
         ok &= parity("FloorPlanScene", 250, 301, var)
         ok &= parity("SmallRoom", None, 0, var)
     ok &= parity("BigRoom", 300, 122, 61, S=3)
     ok &= parity("Shoebox", 512, 200, 60)
     ok &= parity("HugeRoom", 384, 203, 62, S=2)
     ok &= parity(None, 257, 130, 63)
+    ok &= parity("FloorPlanScene", 240, 97, 60, listeners=[(239.5 * 0.3565818, 0, 239.5 * 0.3565818), (100 * 0.3565818, 0, 239.5 * 0.3565818)])     # padding row in the bottom halo (240 = 10 x 24)
+    ok &= parity("HugeRoom", 720, 203, 66, S=2)                                                                 # 720 = 10 x 72: the same with 5-row warps
     # listeners on a wall cell, on the padding row / column, in the corner cell
     size, scale = common.scaled_config(250)
     ok &= parity("FloorPlanScene", 250, 90, 61, listeners=[(1.05 * scale, 0, 4 * scale), (250.2 * 0.3565818 , 0, 4 * scale), (0.1, 0, 0.1), (4 * scale, 0, 250.3 * 0.3565818)])

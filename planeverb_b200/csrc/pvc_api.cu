@@ -52,52 +52,49 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto.
-    //   * resident kernel (pvc_step_res.cu, variants 60..64) whenever every tile of at least one source fits the GPU at once:
-    //     state in registers for the whole solve, only halo strips through the L2.  Among the tilings that fit, the one with the
-    //     lowest estimated solve time: passes x launches x (exchange latency + per-warp step time x warps sharing an SM).
-    //   * else the warp-specialised generational kernel (pvc_step_ws2.cu): variant 47 (14 compute warps x 4 rows + producer +
-    //     publisher warp, source groups that keep a group's state L2-resident), or variant 50 (32-row tiles) when the default
-    //     tiling yields fewer than ~1.4 work items per SM and generation (measured cross-over, profiles/r01_variants.txt).
-    //   * without cuTensorMapEncodeTiled in the driver the generational kernels cannot run: the plain 8 x 6 kernel (18).
-    struct ResidentChoice { int variant; double cost; };
-    static ResidentChoice bestResident(const pvc_config& c, int sms)
+    // variant 0 = auto (measurements: profiles/r02_resident_variants.txt).
+    //   * The generational kernel (pvc_step_ws2.cu, variant 47: 14 compute warps x 4 rows + producer + publisher warp, source groups
+    //     that keep a group's state L2-resident) when a generation offers at least ~1.45 work items per SM: its dynamic work queue
+    //     rides out the jitter of the tile hand-overs, which a statically tiled kernel cannot.  Also whenever the grid does not fit
+    //     the register files (beyond ~1024 x 1024); variant 50 (32-row tiles) when even that tiling leaves SMs idle.
+    //   * The resident kernel (pvc_step_res.cu) below that: state in registers for the whole solve, only halo strips through the L2.
+    //     One source or a few small ones (the plugin's case: 70^2 .. 1024^2 cells, one listener) run 1.2-1.6x faster than on the
+    //     generational kernel.  Tiling: the shortest tiles that still hold all sources of a solve co-resident (more CTAs = more SMs at
+    //     work, and the pass time grows with the warps of a tile); if no tiling holds them all, the tallest tiles that fit one source
+    //     and as many sources per launch as fit.
+    //   * without cuTensorMapEncodeTiled in the driver the generational kernels cannot run: the plain 8 x 6 kernel (18) if the
+    //     resident kernel does not fit either.
+    static long residentTiles(const pvc_config& c, int v)
     {
-        ResidentChoice best = { 0, 0.0 };
-        for (int v = 60; v <= 71; ++v)
+        const int vr = fusedTileRows(v) - 2 * kTileK;
+        return (long)((c.gx + vr - 1) / vr) * ((c.gy + 1 + kValidCols - 1) / kValidCols);
+    }
+    static int bestResident(const pvc_config& c, int sms)
+    {
+        static const int order[] = { 60, 61, 62, 63, 65, 64 };          // 8, 10, 12 warps (two CTAs per SM), 16, 18, 20 warps (one)
+        int fallback = 0;
+        for (int v : order)
         {
             if (!variantAvailable(v)) continue;
-            const int nw = variantWarps(v), perSm = variantMinBlocks(v);
-            const int vr = fusedTileRows(v) - 2 * kTileK;
-            const long tiles = (long)((c.gx + vr - 1) / vr) * ((c.gy + 1 + kValidCols - 1) / kValidCols);
-            const long cap = (long)sms * perSm;
-            if (tiles > cap) continue;
-            const long perLaunch = cap / tiles;
-            const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
-            const long ctas = tiles * (c.max_sources < perLaunch ? c.max_sources : perLaunch);
-            const long ctasPerSm = (ctas + sms - 1) / sms;                       // CTAs that actually share an SM
-            // microseconds per pass: hand-over latency (hidden behind the other CTA when two share an SM) + issue time of the
-            // warps on the SM (0.22 us per compute warp and pass when the SM is full, floor 1.2 us for a lone small CTA)
-            const double compute = 0.22 * nw * (double)ctasPerSm;
-            const double pass = (ctasPerSm > 1 ? 0.4 : 1.2) + (compute > 1.2 ? compute : 1.2);
-            const double cost = pass * (double)launches;
-            if (best.variant == 0 || cost < best.cost) { best.variant = v; best.cost = cost; }
+            const long tiles = residentTiles(c, v), cap = (long)sms * variantMinBlocks(v);
+            if (tiles * c.max_sources <= cap) return v;
+            if (tiles <= cap) fallback = v;                              // fits one source at a time: keep the tallest
         }
-        return best;
+        return fallback;
     }
     static int resolveVariant(const pvc_config& c)
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
         int sms = 148;
         { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, c.device) == cudaSuccess && v > 0) sms = v; else cudaGetLastError(); }
-        const ResidentChoice rc = bestResident(c, sms);
-        if (rc.variant) return rc.variant;
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
-        if (!tma) return 18;
         const long items = (long)((c.gx + 1 + 47) / 48) * ((c.gy + 1 + kValidCols - 1) / kValidCols) * c.max_sources;
+        const int resident = bestResident(c, sms);
+        if (resident && (!tma || items * 100 < (long)sms * 145)) return resident;
+        if (!tma) return 18;
         return (items * 10 <= (long)sms * 14) ? 50 : 47;
     }
 
@@ -291,7 +288,7 @@ size_t pvc_memory_requirement(const pvc_config* cfg)
     pvc_config r = *cfg; r.reserved = resolveVariant(*cfg);
     const Layout L = makeLayout(r);
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 + 32 * S : 4) * L.plane + S * L.hist_source + (size_t)cfg->T +
+    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 + 32 * S : (variantKind(r.reserved) == 5 ? 7 : 4)) * L.plane + S * L.hist_source + (size_t)cfg->T +
                             S * cells * 11 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
 }
 
@@ -331,12 +328,11 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     PVC_TRY(cudaEventCreateWithFlags(&s->evCopied, cudaEventDisableTiming));
     PVC_TRY(cudaMallocHost(&s->hostAbort, sizeof(int)));
     *s->hostAbort = 0;
+    // the six state arrays in ONE allocation, so that a single L2 access-policy window can cover the ping-pong state
+    PVC_TRY(cudaMalloc(&s->stateBlock, sizeof(float) * 6 * S * L.plane));
+    PVC_TRY(cudaMemsetAsync(s->stateBlock, 0, sizeof(float) * 6 * S * L.plane, s->stream));
     for (int b = 0; b < 2; ++b)
-        for (int f = 0; f < 3; ++f)
-        {
-            PVC_TRY(cudaMalloc(&s->state[b][f], sizeof(float) * S * L.plane));
-            PVC_TRY(cudaMemsetAsync(s->state[b][f], 0, sizeof(float) * S * L.plane, s->stream));
-        }
+        for (int f = 0; f < 3; ++f) s->state[b][f] = s->stateBlock + (size_t)(b * 3 + f) * S * L.plane;
     PVC_TRY(cudaMalloc(&s->w, sizeof(float) * L.plane));
     for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->coef[f], sizeof(float) * L.plane));
     PVC_TRY(cudaMalloc(&s->slowMask, sizeof(uint32_t) * (size_t)L.tiles_x * L.tiles_y * 32));
@@ -348,9 +344,10 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     s->tileCounterCount = cfg->T / kTileK + 2;
     PVC_TRY(cudaMalloc(&s->tileCounters, sizeof(int) * (size_t)s->tileCounterCount));
     PVC_TRY(cudaMalloc(&s->doneGen, sizeof(int) * S * (size_t)L.tiles_x * L.tiles_y));
+    if (variantKind(s->cfg.reserved) >= 5)
+        for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->lin[f], sizeof(float) * L.plane));
     if (variantKind(s->cfg.reserved) == 6)
     {
-        for (int f = 0; f < 3; ++f) PVC_TRY(cudaMalloc(&s->lin[f], sizeof(float) * L.plane));
         PVC_TRY(cudaMalloc(&s->resXchg, sizeof(float) * 4 * 8 * S * L.plane));
         PVC_TRY(cudaMemsetAsync(s->resXchg, 0, sizeof(float) * 4 * 8 * S * L.plane, s->stream));
     }
@@ -385,7 +382,7 @@ void pvc_destroy(pvc_solver* s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (int b = 0; b < 2; ++b) for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
+    cudaFree(s->stateBlock);
     cudaFree(s->w); for (int f = 0; f < 3; ++f) { cudaFree(s->coef[f]); cudaFree(s->lin[f]); } cudaFree(s->resXchg); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
     if (s->evAnalyzed) cudaEventDestroy(s->evAnalyzed);

@@ -101,7 +101,8 @@ struct pvc_solver
     int copyPending;
     int* hostAbort;          // pinned: abort flag of the run whose results are being fetched
 
-    float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats
+    float* stateBlock;       // the six state arrays, one allocation
+    float* state[2][3];      // [pingpong][p,vx,vy] each max_sources * plane floats (slices of stateBlock)
     float* w;                // wall plane (air flag / admittance), the geometry's source of truth
     float* coef[3];          // general-path coefficient planes bp, gx, gy derived from w (pvc_step_fused.cu)
     float* lin[3];           // linear-form coefficient planes cP, sX, sY derived from w (pvc_step_res.cu); null until a resident variant needs them

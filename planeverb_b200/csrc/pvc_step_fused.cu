@@ -1478,7 +1478,7 @@ namespace pvc
         const int v = s->cfg.reserved;
         if (!variantAvailable(v)) { setError("step-kernel variant %d is not compiled into this build (make EXTRA=-DPVC_ALL_VARIANTS)", v); return PVC_ERR_INVALID; }
         buildCoefficientsKernel<<<(unsigned)((s->L.plane + 255) / 256), 256, 0, s->stream>>>(s->L, s->w, s->coef[0], s->coef[1], s->coef[2]);
-        if (variantKind(v) == 5) { const int rc = rebuildWs2Descriptors(s, v); if (rc) return rc; }
+        if (variantKind(v) == 5) { int rc = rebuildWs2Descriptors(s, v); if (!rc) rc = rebuildResidentDescriptors(s, v); if (rc) return rc; }     // + the linear-form planes
         if (variantKind(v) == 6) { const int rc = rebuildResidentDescriptors(s, v); if (rc) return rc; }
         switch (kVariants[v].nw * 100 + kVariants[v].r)
         {

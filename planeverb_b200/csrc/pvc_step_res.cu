@@ -140,10 +140,21 @@ namespace pvc
                 A.trace[((size_t)blockIdx.x * kTracePasses + (g - kTracePass0)) * kTraceSlots + slot] = t;
             }
         }
+        __device__ __forceinline__ void stampAny(const Args& A, int g, int slot)
+        {
+            if (A.trace && g >= kTracePass0 && g < kTracePass0 + kTracePasses)
+            {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.trace[((size_t)blockIdx.x * kTracePasses + (g - kTracePass0)) * kTraceSlots + slot] = t;
+            }
+        }
         #define PVC_STAMP(A, g, slot) stamp(A, g, slot)
+        #define PVC_STAMP_IF(cond, A, g, slot) do { if (cond) stampAny(A, g, slot); } while (0)
         #define PVC_DBG(A, bit) (((A).dbg >> (bit)) & 1)
 #else
         #define PVC_STAMP(A, g, slot) do {} while (0)
+        #define PVC_STAMP_IF(cond, A, g, slot) do {} while (0)
         #define PVC_DBG(A, bit) 0
 #endif
 
@@ -429,23 +440,46 @@ namespace pvc
                     {
                         if (waiting)
                         {
-                            if (__float_as_int(loadWord(qLast).w) == tag) waiting = false;
+                            if (__float_as_int(loadWord(qLast).w) == tag) { waiting = false; PVC_STAMP_IF(wp == 0 && lane == 1, A, g, 6); }
                         }
                         if (!waiting)
                         {
+                            // The loads are volatile asm statements; a load followed by its use, word after word, made the reload
+                            // sixteen L2 round trips long (4 us of an 8.9 us pass), four words of a row at a time still four.  A thread
+                            // that reloads ALL its rows (halo warps; lanes 0 / 31 of the others) overwrites its whole state, so the
+                            // registers for sixteen words in flight are there: one round trip.  Partial reloads go row by row.
                             int bad = 0;
-                            #pragma unroll
-                            for (int j = 0; j < R; ++j)
-                                if ((loadRows >> j) & 1u)
-                                {
+                            if (loadRows == (1u << R) - 1u)
+                            {
+                                float4 v[R][4];
+                                #pragma unroll
+                                for (int j = 0; j < R; ++j)
+                                    #pragma unroll
+                                    for (int k = 0; k < 4; ++k) v[j][k] = loadWord(q0 + (size_t)j * L.pitch + k);
+                                #pragma unroll
+                                for (int j = 0; j < R; ++j)
                                     #pragma unroll
                                     for (int k = 0; k < 4; ++k)
                                     {
-                                        const float4 v = loadWord(q0 + (size_t)j * L.pitch + k);
-                                        p[j][k] = opaqueCopy(v.x, A.zero); vx[j][k] = opaqueCopy(v.y, A.zero); vy[j][k] = opaqueCopy(v.z, A.zero);
-                                        bad |= __float_as_int(v.w) ^ tag;
+                                        p[j][k] = opaqueCopy(v[j][k].x, A.zero); vx[j][k] = opaqueCopy(v[j][k].y, A.zero); vy[j][k] = opaqueCopy(v[j][k].z, A.zero);
+                                        bad |= __float_as_int(v[j][k].w) ^ tag;
                                     }
-                                }
+                            }
+                            else
+                            {
+                                #pragma unroll
+                                for (int j = 0; j < R; ++j)
+                                    if ((loadRows >> j) & 1u)
+                                    {
+                                        const float4* q = q0 + (size_t)j * L.pitch;
+                                        const float4 v0 = loadWord(q), v1 = loadWord(q + 1), v2 = loadWord(q + 2), v3 = loadWord(q + 3);
+                                        p[j][0] = opaqueCopy(v0.x, A.zero); vx[j][0] = opaqueCopy(v0.y, A.zero); vy[j][0] = opaqueCopy(v0.z, A.zero);
+                                        p[j][1] = opaqueCopy(v1.x, A.zero); vx[j][1] = opaqueCopy(v1.y, A.zero); vy[j][1] = opaqueCopy(v1.z, A.zero);
+                                        p[j][2] = opaqueCopy(v2.x, A.zero); vx[j][2] = opaqueCopy(v2.y, A.zero); vy[j][2] = opaqueCopy(v2.z, A.zero);
+                                        p[j][3] = opaqueCopy(v3.x, A.zero); vx[j][3] = opaqueCopy(v3.y, A.zero); vy[j][3] = opaqueCopy(v3.z, A.zero);
+                                        bad |= (__float_as_int(v0.w) ^ tag) | (__float_as_int(v1.w) ^ tag) | (__float_as_int(v2.w) ^ tag) | (__float_as_int(v3.w) ^ tag);
+                                    }
+                            }
                             if (bad == 0) break;
                         }
                         // not there yet (or a neighbour died): bounded, and a raised abort flag ends every later wait at once
@@ -454,6 +488,7 @@ namespace pvc
                         if (!PVC_DBG(A, 2)) __nanosleep(20);
                     }
                 }
+                PVC_STAMP_IF(wp == 0 && lane == 1, A, g, 7);
                 __syncwarp();            // the lanes that polled rejoin the others before the (warp-aligned) barriers below
                 PVC_STAMP(A, g, 1);
                 sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
@@ -527,6 +562,7 @@ namespace pvc
                             __stcg(reinterpret_cast<float4*>(gy + (size_t)j * L.pitch), make_float4(vy[j][0], vy[j][1], vy[j][2], vy[j][3]));
                         }
                 }
+                PVC_STAMP_IF(wp == NW - 2 && lane == 1, A, g, 5);
                 if (X.sj < 0) recordSample<R>(X, p);
                 PVC_STAMP(A, g, 4);
             }
@@ -694,6 +730,25 @@ namespace pvc
                         }
                     }
                     if (nl) fprintf(stderr, "[res trace] hand-over: reload of pass k done %.0f ns after the writer tile finished the steps of pass k-1 (n=%ld)\n", lat / nl, nl);
+                    // vertical pairs, thread to thread: (warp NW-2, lane 1) of the upper tile mails the words that (warp 0, lane 1) of this
+                    // tile polls: mail issued -> first word seen -> all 16 words loaded; and how long that reader had been polling
+                    double seen = 0, loaded = 0, polled = 0, skew = 0; long nv = 0;
+                    for (int c = 0; c < ctas; ++c)
+                    {
+                        const int tile = c % tps, ty = tile / L.tiles_x;
+                        if (ty == 0) continue;
+                        const int nb = c - L.tiles_x;
+                        for (int k = 2; k + 1 < kTracePasses; ++k)
+                        {
+                            const unsigned long long* a = h.data() + ((size_t)c * kTracePasses + k) * kTraceSlots;
+                            const unsigned long long* b = h.data() + ((size_t)nb * kTracePasses + (k - 1)) * kTraceSlots;
+                            if (!a[6] || !a[7] || !b[5] || !a[0] || !b[3]) continue;
+                            seen += (double)a[6] - (double)b[5]; loaded += (double)a[7] - (double)a[6]; polled += (double)a[6] - (double)a[0];
+                            skew += (double)b[5] - (double)b[3]; ++nv;
+                        }
+                    }
+                    if (nv) fprintf(stderr, "[res trace] vertical pairs (n=%ld): writer thread mails %.0f ns after its tile's thread 0 finished the steps; word seen %.0f ns after the mail; ring loaded %.0f ns later; the reader had polled for %.0f ns\n",
+                                    nv, skew / nv, seen / nv, loaded / nv, polled / nv);
                 }
                 if (cnt) fprintf(stderr, "[res trace] NW=%d ctas=%d n=%ld  reload %.0f  exchange+sync %.0f  steps %.0f  mail %.0f | period %.0f ns (thread 0 of every CTA)\n",
                                  NW, ctas, cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt);

@@ -141,6 +141,13 @@ namespace pvc
             else computeBarrier<NW>();
         }
         __device__ __forceinline__ bool isAirF(float w) { return __float_as_uint(w) == kAirBits; }
+        // 1.0f where x < 0 (one FSET): the k of the linear-form velocity rule, folded into the sign of its coefficient
+        __device__ __forceinline__ float signFlag(float x)
+        {
+            float r;
+            asm("set.lt.f32.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+            return r;
+        }
 
         // ---------------------------------------------------------------- kernel arguments (never indexed dynamically)
         struct Args
@@ -178,7 +185,8 @@ namespace pvc
             int valid, s, tx, ty, gen;
             int coefBuf, coefParity;               // coefBuf < 0: no general-path warp in this tile
             int srcR, srcC;
-            int pad[3];
+            int srcDead;                           // the pulse cell is not an interior air cell (SourceParams::dead)
+            int pad[2];
             float pulse[4];
             int mode[32];
             int hint[32];
@@ -208,8 +216,11 @@ namespace pvc
         //   edge     no wall, but the warp touches the grid edge / padding / guard band: position-only overwrites
         //   general  some cell or neighbour is a wall: coefficient planes gx, gy from shared memory, bp from a bit mask
         // All arithmetic is explicit round-to-nearest mul/add/sub in the reference's operation order (no FMA).
-        // BPF: the air flag of the general path comes from a third staged coefficient plane (bp = 1.0 / 0.0 per cell) instead of
-        // the per-thread bit mask: a multiply / one compare per cell where the bit tests cost 5 instructions
+        // BPF (three staged coefficient planes, every product variant): the general path is the LINEAR FORM of pvc_step_res.cu --
+        // p' = p - cP*div, v' = fma(k, v, -(c*(p - p_prev))) with k folded into the sign of c -- which costs what the fast path
+        // costs plus one FSET per velocity component; the planes are sX, sY, cP (buildLinearKernel).  It relies on p == 0 in every
+        // cell that is not interior air, so nothing may be injected there (Meta::srcDead).  Without BPF (two planes + a per-thread
+        // bit mask of the air flag; experiment variants whose shared memory cannot hold three): the select form over gx, gy.
         template <int NW, int R, int MODE, bool BPF = false>
         struct Stepper
         {
@@ -247,17 +258,16 @@ namespace pvc
                     }
                     else
                     {
-                        float bpv[4] = { 1.f, 1.f, 1.f, 1.f };
-                        if (MODE == kGeneral && BPF) { const float4 b4 = cBp[j * 32]; bpv[0] = b4.x; bpv[1] = b4.y; bpv[2] = b4.z; bpv[3] = b4.w; }
+                        float ck[4] = { C, C, C, C };
+                        if (MODE == kGeneral && BPF) { const float4 c4 = cBp[j * 32]; ck[0] = c4.x; ck[1] = c4.y; ck[2] = c4.z; ck[3] = c4.w; }
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
                             const float vxd = (j + 1 < R) ? vx[j + 1][k] : vb[k];
                             const float vyr = (k < 3) ? vy[j][k + 1] : vyRight;
                             const float div = __fadd_rn(__fsub_rn(vxd, vx[j][k]), __fsub_rn(vyr, vy[j][k]));
-                            const float pn = __fsub_rn(p[j][k], __fmul_rn(C, div));
-                            if (MODE == kFast) p[j][k] = pn;
-                            else if (BPF) p[j][k] = __fmul_rn(pn, bpv[k]);          // x 1.0 is exact, x 0.0 gives the reference's b * (...) = 0
+                            const float pn = __fsub_rn(p[j][k], __fmul_rn(ck[k], div));     // cP = 0 where the cell is not interior air: p stays 0
+                            if (MODE == kFast || BPF) p[j][k] = pn;
                             else p[j][k] = ((bpBits >> (j * 4 + k)) & 1u) ? pn : 0.f;
                         }
                     }
@@ -337,21 +347,30 @@ namespace pvc
                         const float4 y4 = cGy[j * 32];
                         const float ga[4] = { x4.x, x4.y, x4.z, x4.w };
                         const float ha[4] = { y4.x, y4.y, y4.z, y4.w };
-                        float bpv[4] = { 1.f, 1.f, 1.f, 1.f };
-                        if (BPF) { const float4 b4 = cBp[j * 32]; bpv[0] = b4.x; bpv[1] = b4.y; bpv[2] = b4.z; bpv[3] = b4.w; }
                         #pragma unroll
                         for (int k = 0; k < 4; ++k)
                         {
                             const float pu = (j > 0) ? p[j - 1][k] : pa[k];
                             const float pl = (k > 0) ? p[j][k - 1] : pLeft;
                             const float pt = p[j][k];
-                            const bool air = BPF ? (bpv[k] != 0.f) : (((bpBits >> (j * 4 + k)) & 1u) != 0u);
-                            const float airX = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
-                            const float airY = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
-                            const float wallX = __fmul_rn(ga[k], air ? pt : pu);
-                            const float wallY = __fmul_rn(ha[k], air ? pt : pl);
-                            vx[j][k] = (air && isAirF(ga[k])) ? airX : wallX;
-                            vy[j][k] = (air && isAirF(ha[k])) ? airY : wallY;
+                            if (BPF)
+                            {
+                                // fma(k, v, -(|s| * d)): k * v is exact (k is 0 or 1), so this is the reference's v - c*d (k = 1) or -(c*d)
+                                const float tx = __fmul_rn(fabsf(ga[k]), __fsub_rn(pt, pu));
+                                const float ty = __fmul_rn(fabsf(ha[k]), __fsub_rn(pt, pl));
+                                vx[j][k] = __fmaf_rn(signFlag(ga[k]), vx[j][k], -tx);
+                                vy[j][k] = __fmaf_rn(signFlag(ha[k]), vy[j][k], -ty);
+                            }
+                            else
+                            {
+                                const bool air = ((bpBits >> (j * 4 + k)) & 1u) != 0u;
+                                const float airX = __fsub_rn(vx[j][k], __fmul_rn(C, __fsub_rn(pt, pu)));
+                                const float airY = __fsub_rn(vy[j][k], __fmul_rn(C, __fsub_rn(pt, pl)));
+                                const float wallX = __fmul_rn(ga[k], air ? pt : pu);
+                                const float wallY = __fmul_rn(ha[k], air ? pt : pl);
+                                vx[j][k] = (air && isAirF(ga[k])) ? airX : wallX;
+                                vy[j][k] = (air && isAirF(ha[k])) ? airY : wallY;
+                            }
                         }
                     }
                 }
@@ -747,6 +766,7 @@ namespace pvc
                     }
                     if (lane == 0) nx.misc = A.src[nx.s].cell_r;
                     else if (lane == 1) nx.misc = A.src[nx.s].cell_c;
+                    else if (lane == 2) nx.misc = A.src[nx.s].dead;
                     else if (lane >= 4 && lane < 8)
                     {
                         const int t = nx.gen * kTileK + (lane - 4) - (TS ? 1 : 0);          // TS: [pending sample of the previous pass, samples 0..2]
@@ -834,6 +854,7 @@ namespace pvc
                     if (lane < NW) { m->mode[lane] = it.mode; m->hint[lane] = it.hint; }
                     if (lane == 0) m->srcR = it.misc;
                     else if (lane == 1) m->srcC = it.misc;
+                    else if (lane == 2) m->srcDead = it.misc;
                     else if (lane >= 4 && lane < 8) m->pulse[lane - 4] = __int_as_float(it.misc);
                     else if (lane == 8) { m->valid = 1; m->s = s; m->tx = tx; m->ty = ty; m->gen = gen; m->coefBuf = coefBuf; m->coefParity = coefParity; }
                     else if (PUB && lane == 9) { pubRing[(seq & 3) * 4] = s * tps + id; pubRing[(seq & 3) * 4 + 1] = gen; pubRing[(seq & 3) * 4 + 2] = s; pubRing[(seq & 3) * 4 + 3] = id; }
@@ -977,12 +998,12 @@ namespace pvc
                     const int sj = m->srcR - rBase, sk = m->srcC - cBase;
                     const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
                     X.sj = hasSrc ? sj : -1; X.sk = sk;
-                    // A listener on the padding row / column (b == 0): the reference zeroes the injected sample in the next
+                    // A listener on the padding row / column or in a wall cell (b == 0): the reference zeroes the injected sample in the next
                     // pressure sub-step before anything reads it (FDTD.cpp:125-141, :234), so the cell records 0 for ever and
                     // only the very last sample survives in the final state.  The edge path never recomputes such cells, so
                     // the injection is dropped instead -- except for that last sample.
                     X.onlyLast = false;
-                    if (hasSrc && (m->srcR >= L.gx || m->srcC >= L.gy))
+                    if (hasSrc && (m->srcR >= L.gx || m->srcC >= L.gy || m->srcDead))
                     {
                         if (TS || t0 + nsteps < A.T) X.sj = -1;
                         else X.onlyLast = true;
@@ -1149,7 +1170,7 @@ namespace pvc
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
         // 2-D tensor maps {pitch, rows_alloc} of the gx / gy coefficient planes, box 128 x tileRows
-        static int buildCoefMaps(pvc_solver* s, CUtensorMap* out)
+        static int buildCoefMaps(pvc_solver* s, CUtensorMap* out, bool linear)
         {
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult q;
@@ -1162,7 +1183,9 @@ namespace pvc
                 const cuuint64_t strides[1] = { (cuuint64_t)L.pitch * sizeof(float) };
                 const cuuint32_t box[2] = { (cuuint32_t)kTileCols, (cuuint32_t)L.tile_rows };
                 const cuuint32_t estr[2] = { 1u, 1u };
-                const CUresult r = ((EncodeFn)fn)(&out[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->coef[(1 + f) % 3], dims, strides, box, estr,
+                // staged plane order: select form gx, gy, bp (s->coef = bp, gx, gy); linear form sX, sY, cP (s->lin = cP, sX, sY)
+                float* plane = linear ? s->lin[(1 + f) % 3] : s->coef[(1 + f) % 3];
+                const CUresult r = ((EncodeFn)fn)(&out[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr,
                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) { setError("ws2 step kernel: coefficient tensor map %d failed (%d)", f, (int)r); return PVC_ERR_CUDA; }
@@ -1226,7 +1249,8 @@ namespace pvc
             }
             Maps maps;
             memcpy(maps.state, s->tensorMaps, sizeof(maps.state));
-            int rc = buildCoefMaps(s, maps.coef);
+            if (SM::NP == 3 && !s->lin[0]) { setError("ws2 step kernel: linear coefficient planes missing"); return PVC_ERR_INVALID; }
+            int rc = buildCoefMaps(s, maps.coef, SM::NP == 3);
             if (rc) return rc;
             memset(maps.store, 0, sizeof(maps.store)); memset(&maps.hist, 0, sizeof(maps.hist));
             const int numTiles = L.tiles_x * L.tiles_y * nsrc;
@@ -1315,6 +1339,29 @@ namespace pvc
 #endif
                 if (A.srcGroup > nsrc) A.srcGroup = nsrc;
             }
+#ifdef PVC_TUNING
+            {
+                // experiment (PVC_L2_PERSIST=<MB>): pin the ping-pong state of the batch in the L2 with an access-policy window
+                static const char* lp = getenv("PVC_L2_PERSIST");
+                if (lp && atoi(lp) > 0)
+                {
+                    static bool limitSet = false;
+                    if (!limitSet) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(lp) << 20); limitSet = true; }
+                    int maxWin = 0; cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
+                    cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
+                    size_t bytes = sizeof(float) * 6 * (size_t)s->cfg.max_sources * L.plane;
+                    if (maxWin > 0 && bytes > (size_t)maxWin) bytes = (size_t)maxWin;
+                    av.accessPolicyWindow.base_ptr = s->stateBlock;
+                    av.accessPolicyWindow.num_bytes = bytes;
+                    av.accessPolicyWindow.hitRatio = (float)(((double)((size_t)atoi(lp) << 20)) / (double)bytes > 1.0 ? 1.0 : ((double)((size_t)atoi(lp) << 20)) / (double)bytes);
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    const cudaError_t e = cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                    static bool said = false;
+                    if (!said) { fprintf(stderr, "[ws2] L2 window: %zu MB of state, set-aside %d MB, hit ratio %.2f, max window %d MB: %s\n", bytes >> 20, atoi(lp), av.accessPolicyWindow.hitRatio, maxWin >> 20, cudaGetErrorString(e)); said = true; }
+                }
+            }
+#endif
             int k = 1;
             for (int g0 = 0; g0 < gens; g0 += perLaunch, ++k)
             {

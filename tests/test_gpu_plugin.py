@@ -41,6 +41,7 @@ def plugin():
     L.PlaneverbSetListenerPosition.argtypes = [f, f, f]
     L.PlaneverbFramesCompleted.restype = C.c_ulonglong
     L.PlaneverbLastError.restype = C.c_char_p
+    L.PlaneverbWorkerState.restype = C.c_int
     yield L
     L.PlaneverbExit()
 
@@ -172,3 +173,112 @@ def test_headless_cli_links_only_the_cpp_api(tmp_path, scenes):
         assert abs(vals[3] - want[3]) <= 2.5e-7 * abs(want[3])
     ir = [l.split() for l in out.stdout.splitlines() if l.startswith("ir ") and l.split()[1].isdigit()]
     assert len(ir) == 64 and "ir samples 435" in out.stdout
+
+
+def test_listener_outside_the_grid_skips_frames_and_recovers(plugin):
+    """FDTD.cpp:97-99 turns the listener into a cell with no check (outside the grid the reference indexes out of bounds).  Here
+    such frames are skipped: the acoustics thread keeps running, GetOutput keeps serving the last good frame, the reason is in
+    PlaneverbLastError, and frames resume when the listener comes back."""
+    L = plugin
+    L.PlaneverbInit(25.0, 25.0, 275, 0, b".", 0, 1)
+    L.PlaneverbSetListenerPosition(5.0, 0.0, 4.0)
+    e = L.PlaneverbEmit(5.0, 0.0, 6.0)
+    wait_frames(L, 2)
+    good = L.PlaneverbGetOutput(e).vec()
+    assert good[0] > 0 and L.PlaneverbWorkerState() == 1
+    for bad in ((100.0, 0.0, 4.0), (float("nan"), 0.0, 4.0), (-3.0, 0.0, 4.0)):
+        L.PlaneverbSetListenerPosition(*bad)
+        time.sleep(0.05)
+        n0 = L.PlaneverbFramesCompleted()
+        time.sleep(0.05)
+        assert L.PlaneverbFramesCompleted() - n0 <= 1                    # at most the frame that was already in flight
+        assert L.PlaneverbWorkerState() == 1                             # alive, not "stopped by a device failure"
+        assert b"outside the grid" in L.PlaneverbLastError()
+        assert common.bit_equal(L.PlaneverbGetOutput(e).vec(), good).all()
+    L.PlaneverbSetListenerPosition(5.0, 0.0, 4.0)
+    wait_frames(L, 2)
+    assert common.bit_equal(L.PlaneverbGetOutput(e).vec(), good).all()
+    L.PlaneverbExit()
+    assert L.PlaneverbWorkerState() == 0
+
+
+def test_exit_while_another_thread_reads_outputs(plugin):
+    """AudioCore.cpp:95 calls GetOutput from the audio thread while the game thread may call Exit / Init (ChangeSettings): every API
+    call works on a snapshot of the context, so the result grids cannot be freed under a reader."""
+    import threading
+    L = plugin
+    stop = threading.Event()
+    seen = []
+
+    def audio_thread():
+        while not stop.is_set():
+            seen.append(L.PlaneverbGetOutput(0).occlusion)
+
+    t = threading.Thread(target=audio_thread)
+    t.start()
+    try:
+        for _ in range(6):
+            L.PlaneverbInit(25.0, 25.0, 275, 0, b".", 0, 1)
+            L.PlaneverbSetListenerPosition(5.0, 0.0, 4.0)
+            assert L.PlaneverbEmit(5.0, 0.0, 6.0) == 0
+            wait_frames(L, 1)
+            L.PlaneverbExit()
+    finally:
+        stop.set()
+        t.join()
+    assert len(seen) > 100 and all(v == -1.0 or v >= 0.0 for v in seen)   # sentinel without a context, a real value with one
+
+
+def test_world_offset_is_rejected():
+    """PlaneverbConfig::gridWorldOffset is marked "!!! Not supported !!!" in the reference (PvTypes.h:58) and applied inconsistently
+    (Grid.cpp:139-142 vs 252-255): Init refuses a non-zero offset instead of silently looking emitters up in a shifted frame."""
+    import os
+    import subprocess
+    import tempfile
+    src = r'''
+#include <cstdio>
+#include "Planeverb.h"
+#include "PlaneverbUnity.h"
+int main()
+{
+    Planeverb::PlaneverbConfig c;
+    c.gridSizeInMeters = Planeverb::vec2(25.f, 25.f); c.gridResolution = 275; c.tempFileDirectory = "."; c.threadExecutionType = Planeverb::pv_GPU;
+    c.gridWorldOffset = Planeverb::vec2(1.f, 0.f);
+    try { Planeverb::Init(&c); } catch (Planeverb::PlaneverbErrorCode e) { std::printf("threw %d: %s\n", (int)e, PlaneverbLastError()); return e == Planeverb::pv_InvalidConfig ? 0 : 3; }
+    Planeverb::Exit();
+    return 4;
+}
+'''
+    lib = os.path.join(common.ROOT, "planeverb_b200", "lib")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["g++", "-std=c++17", os.path.join(d, "t.cpp"), "-I", os.path.join(common.ROOT, "include"), "-L", lib,
+                               "-lplaneverb_b200", "-Wl,-rpath," + lib, "-pthread", "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "gridWorldOffset" in out.stdout
+
+
+def test_headless_cli_saves_the_scene_in_the_sandbox_format(tmp_path, scenes):
+    """--save writes what Editor::SaveGeometry writes (Editor.cpp:219-243): the count, then "id posX posY width height absorption"
+    per object; loading the saved file gives the same outputs again."""
+    import os
+    import subprocess
+    exe = os.path.join(common.ROOT, "planeverb_b200", "lib", "pv_headless")
+    boxes = scenes["SmallRoom"]["boxes"]
+    src = tmp_path / "SmallRoom.pv"
+    src.write_text(f"{len(boxes)}\n" + "".join(
+        f"{b['id']} {b['pos'][0]} {b['pos'][1]} {b['width']} {b['height']} {b['absorption']}\n" for b in boxes))
+    saved = tmp_path / "saved.pv"
+    a = subprocess.run([exe, str(src), "--frames", "2", "--save", str(saved)], capture_output=True, text=True, timeout=120)
+    assert a.returncode == 0, a.stderr
+    rows = saved.read_text().split("\n")
+    assert int(rows[0]) == len(boxes)
+    for k, (row, b) in enumerate(zip(rows[1:], boxes)):
+        vals = [float(v) for v in row.split()]
+        assert vals[0] == k                                                # the slot ids AddGeometry handed out
+        assert np.allclose(vals[1:], [b["pos"][0], b["pos"][1], b["width"], b["height"], b["absorption"]], rtol=1e-6)
+    b2 = subprocess.run([exe, str(saved), "--frames", "2"], capture_output=True, text=True, timeout=120)
+    assert b2.returncode == 0
+    assert [l for l in a.stdout.splitlines() if l.startswith("emitter")] == [l for l in b2.stdout.splitlines() if l.startswith("emitter")]

@@ -296,6 +296,10 @@ namespace pvc
                 // ---- pressure sub-step (FDTD.cpp:125-141)
                 pressureStep<R, GEN>(p, vx, vy, sVxTop[wp + 1][lane], X.C, X.cP);
                 sPBot[wp + 1][lane] = make_float4(p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3]);
+                // ---- record sample t0 + step (FDTD.cpp:226-231) NOW: the velocity sub-steps do not touch p, so this is the value the
+                //      reference records after them, and the stores get the whole velocity phase to read their registers and leave the SM
+                //      (recorded after it, they were still queued when the next pressure update -- or the strips -- needed the path)
+                if (step + 1 < nsteps) recordSample<R>(X, p);
                 phaseSync<NW, SYNC>(wp);
                 // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223)
                 velocityStep<R, GEN>(p, vx, vy, sPBot[wp][lane], X.C, X.sX, X.sY);
@@ -310,8 +314,7 @@ namespace pvc
                 }
                 if (step + 1 < nsteps)
                 {
-                    // ---- record sample t0 + step, then inject
-                    recordSample<R>(X, p);
+                    // ---- inject (FDTD.cpp:234)
                     injectSample<R>(X, p, t0 + step);
                     sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
                     phaseSync<NW, SYNC>(wp);            // also the write-after-read fence of sPBot

@@ -67,7 +67,8 @@ def test_multi_uses_every_visible_device(pv, scenes):
     size, scale = common.scaled_config(200)
     m = pv.MultiScene(list(range(ndev)), size, size, 275, T=120, max_sources=2 * ndev, max_emitters=2)
     assert m.n_devices == ndev and all(b == 2 for b in m.batches)
-    listeners = common.listeners_for(2 * ndev, scale)
+    # 2 listeners per device, all inside the 25 m (pre-scale) grid whatever the device count
+    listeners = [((3.0 + 2.5 * (i % 8)) * scale, 0.0, (4.0 + 5.0 * (i // 8)) * scale) for i in range(2 * ndev)]
     emitters = [(5 * scale, 0, 6 * scale), (6 * scale, 0, 5 * scale)]
     got = m.solve(listeners, emitters)
     want = _reference_outputs(pv, size, [], listeners, emitters, 120)

@@ -52,35 +52,41 @@ namespace pvc
         return L;
     }
 
-    // variant 0 = auto (measurements: profiles/r02_resident_variants.txt).
-    //   * The generational kernel (pvc_step_ws2.cu, variant 47: 14 compute warps x 4 rows + producer + publisher warp, source groups
-    //     that keep a group's state L2-resident) when a generation offers at least ~1.45 work items per SM: its dynamic work queue
-    //     rides out the jitter of the tile hand-overs, which a statically tiled kernel cannot.  Also whenever the grid does not fit
-    //     the register files (beyond ~1024 x 1024); variant 50 (32-row tiles) when even that tiling leaves SMs idle.
-    //   * The resident kernel (pvc_step_res.cu) below that: state in registers for the whole solve, only halo strips through the L2.
-    //     One source or a few small ones (the plugin's case: 70^2 .. 1024^2 cells, one listener) run 1.2-1.6x faster than on the
-    //     generational kernel.  Tiling: the shortest tiles that still hold all sources of a solve co-resident (more CTAs = more SMs at
-    //     work, and the pass time grows with the warps of a tile); if no tiling holds them all, the tallest tiles that fit one source
-    //     and as many sources per launch as fit.
-    //   * without cuTensorMapEncodeTiled in the driver the generational kernels cannot run: the plain 8 x 6 kernel (18) if the
-    //     resident kernel does not fit either.
+    // variant 0 = auto: the kernel with the smallest ESTIMATED time per pass (4 time steps of every source of the batch).  The
+    // estimates are the measured pass periods of profiles/r02_resident_variants.txt (B200, microseconds):
+    //   * resident kernel (pvc_step_res.cu; state in registers for the whole solve, only halo strips through the L2): a launch holds
+    //     as many sources as fit co-resident and advances them one pass per period -- 5.0 (8-warp tiles; x 1.4 when two CTAs share
+    //     an SM), 6.8 / 9.0 (10 / 12 warps), 6.4 / 7.4 / 7.7 (16 / 18 / 20 warps, barrier-free row exchange) -- most of it the
+    //     neighbour hand-over, so the period barely depends on how full the GPU is;
+    //   * generational kernel (pvc_step_ws2.cu, TMA-staged tiles pulled from a work queue): 5.56 us per work item and SM (variant 47,
+    //     56-row tiles), 3.9 (variant 50, 32-row tiles), and never less than the publish -> acquire -> TMA chain between generations
+    //     (11.5 / 9.1 us).
+    // So: one listener up to 1024^2 and batches of small grids (the plugin's case) run resident; a batch whose sources each fill the GPU
+    // (four 1024^2 sources: 4 x 7.4 against 792 items x 5.56 / 148 = 29.8) runs resident too; batches that leave a resident
+    // launch half empty (four 768^2 sources) and grids beyond the register files (2048^2) take the work queue.  Without
+    // cuTensorMapEncodeTiled in the driver the generational kernels cannot run: resident, else the plain 8 x 6 kernel (18).
     static long residentTiles(const pvc_config& c, int v)
     {
         const int vr = fusedTileRows(v) - 2 * kTileK;
         return (long)((c.gx + vr - 1) / vr) * ((c.gy + 1 + kValidCols - 1) / kValidCols);
     }
-    static int bestResident(const pvc_config& c, int sms)
+    static int bestResident(const pvc_config& c, int sms, double* passUs)
     {
-        static const int order[] = { 60, 61, 62, 63, 65, 64 };          // 8, 10, 12 warps (two CTAs per SM), 16, 18, 20 warps (one)
-        int fallback = 0;
-        for (int v : order)
+        static const struct { int v; double period; } cand[] = { {60, 5.0}, {61, 6.8}, {62, 9.0}, {63, 6.4}, {65, 7.4}, {64, 7.7} };
+        int best = 0;
+        double bestUs = 0;
+        for (const auto& k : cand)
         {
-            if (!variantAvailable(v)) continue;
-            const long tiles = residentTiles(c, v), cap = (long)sms * variantMinBlocks(v);
-            if (tiles * c.max_sources <= cap) return v;
-            if (tiles <= cap) fallback = v;                              // fits one source at a time: keep the tallest
+            if (!variantAvailable(k.v)) continue;
+            const long tiles = residentTiles(c, k.v), cap = (long)sms * variantMinBlocks(k.v);
+            if (tiles > cap) continue;
+            const long perLaunch = cap / tiles < c.max_sources ? cap / tiles : c.max_sources;
+            const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
+            const double us = (double)launches * k.period * (tiles * perLaunch > sms ? 1.4 : 1.0);
+            if (!best || us < bestUs) { best = k.v; bestUs = us; }
         }
-        return fallback;
+        *passUs = bestUs;
+        return best;
     }
     static int resolveVariant(const pvc_config& c)
     {
@@ -91,11 +97,15 @@ namespace pvc
         cudaDriverEntryPointQueryResult q;
         const bool tma = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn != nullptr;
         if (!tma) cudaGetLastError();
-        const long items = (long)((c.gx + 1 + 47) / 48) * ((c.gy + 1 + kValidCols - 1) / kValidCols) * c.max_sources;
-        const int resident = bestResident(c, sms);
-        if (resident && (!tma || items * 100 < (long)sms * 145)) return resident;
-        if (!tma) return 18;
-        return (items * 10 <= (long)sms * 14) ? 50 : 47;
+        double residentUs = 0;
+        const int resident = bestResident(c, sms, &residentUs);
+        if (!tma) return resident ? resident : 18;
+        const long cols = (c.gy + 1 + kValidCols - 1) / kValidCols;
+        const double items47 = (double)((c.gx + 1 + 47) / 48) * cols * c.max_sources, items50 = (double)((c.gx + 1 + 23) / 24) * cols * c.max_sources;
+        const double us47 = items47 * 5.56 / sms > 11.5 ? items47 * 5.56 / sms : 11.5;
+        const double us50 = items50 * 3.9 / sms > 9.1 ? items50 * 3.9 / sms : 9.1;
+        if (resident && residentUs <= us47 && residentUs <= us50) return resident;
+        return us50 < us47 ? 50 : 47;
     }
 
     static bool validConfig(const pvc_config* c)

@@ -188,6 +188,42 @@ namespace pvc
         return it;
     }
 
+
+#ifdef __CUDACC__
+    // ---- barrier-free row exchange between the warps of a tile (both register-tiled step kernels) ---------------------------
+    // A warp hands its boundary row (4 floats per lane) to the warp above / below through shared memory.  Instead of meeting
+    // the neighbour on a barrier, the row travels with a tag in every 8-byte unit -- {v0, tag, v1, tag}, {v2, tag, v3, tag}: an
+    // aligned 8-byte shared-memory access is indivisible -- and the reader polls the row itself (the low-latency protocol of the
+    // resident kernel's mailbox, between warps).  The reader first updates the rows that do not need the neighbour's data, so
+    // a neighbour that is a little late costs nothing; with barriers every sub-step waited for the slower of three warps twice.
+    // Tags count the rows a warp has published; every warp of a CTA publishes the same sequence, so the expected tag is the
+    // reader's own count.  A row buffer is rewritten only after the writer has consumed a row the reader published AFTER
+    // reading it (the two directions alternate), except where noted at the call sites.
+    namespace flow
+    {
+        constexpr int kRowFloat4 = 64;        // one exchanged row: [2][32] float4
+        __device__ __forceinline__ void publish(float4* row, const int lane, const float v0, const float v1, const float v2, const float v3, const int tag)
+        {
+            const unsigned a = (unsigned)__cvta_generic_to_shared(row + lane);
+            const float t = __int_as_float(tag);
+            asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v0), "f"(t), "f"(v1), "f"(t) : "memory");
+            asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 512u), "f"(v2), "f"(t), "f"(v3), "f"(t) : "memory");
+        }
+        __device__ __forceinline__ float4 poll(const float4* row, const int lane, const int tag)
+        {
+            const unsigned a = (unsigned)__cvta_generic_to_shared(row + lane);
+            float4 lo, hi;
+            bool ok;
+            do
+            {
+                asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(a) : "memory");
+                asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(a + 512u) : "memory");
+                ok = ((__float_as_int(lo.y) ^ tag) | (__float_as_int(lo.w) ^ tag) | (__float_as_int(hi.y) ^ tag) | (__float_as_int(hi.w) ^ tag)) == 0;
+            } while (!__all_sync(0xffffffffu, ok));
+            return make_float4(lo.x, lo.z, hi.x, hi.z);
+        }
+    }
+#endif
     // step kernels (pvc_step.cu / pvc_step_fused.cu)
     int launchBaselineSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);
     int launchFusedSteps(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches);

@@ -67,36 +67,20 @@ namespace pvc
         // a quad (128-bit shared / history accesses).  Left to itself the register allocator coalesces the two and pays with ~30
         // moves per time step; copying through an integer op with a run-time zero keeps the mailbox quads temporaries.
         __device__ __forceinline__ float opaqueCopy(float v, int zero) { return __int_as_float(__float_as_int(v) ^ zero); }
-        __device__ __forceinline__ void pairBarrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-        // Synchronisation of the step loop: a warp exchanges halo rows only with the warp above and the warp below.
-        //   kSyncCta   one CTA barrier (every warp waits for the slowest)
-        //   kSyncNamed the named barrier of each shared edge (id = upper warp + 1, 64 threads; even warps take the lower edge first,
-        //              odd warps the upper one: no cycle) -- at most 16 ids, and named barriers are an SM resource
-        // (One shared-memory mbarrier per edge -- any tile height, any number of CTAs per SM -- was measured too: 1.8x slower than
-        // the CTA barrier on every grid, profiles/r02_resident_variants.txt; try_wait costs ~90 cycles even when the phase is over.)
-        //   kSyncTail  tiles taller than 16 warps: named barriers for the edges 1 .. 15 as above, and ONE barrier (id 0) shared by
-        //              the warps 15 .. NW-1 in place of the edges below warp 15 -- 16 ids, and only the last few warps are coupled
-        enum { kSyncCta = 0, kSyncNamed = 1, kSyncTail = 2 };
+        // Row exchange between the warps of a tile in the step loop (a warp needs one row of the warp above and one of the warp below
+        // per time step):
+        //   kSyncCta   rows through shared memory, one CTA barrier per sub-step (the small tiles that run two CTAs per SM: their pass
+        //              is bound by the neighbour hand-over, not by the step loop)
+        //   kSyncFlow  no barrier at all: the exchanged rows carry tags and the reader polls the row itself -- after it has updated the
+        //              rows that do not need it (pvc_internal.h, namespace flow).  1024^2, one listener, 18-warp tiles: 2.13 -> 1.85 ms
+        //              per 1000 steps against named barriers per shared edge (which needed a barrier shared by the warps 15 .. NW-1
+        //              beyond 16 warps; one shared-memory mbarrier per edge was 1.8x slower than the CTA barrier: try_wait costs ~90
+        //              cycles even when the phase is over; profiles/r02_resident_variants.txt)
+        enum { kSyncCta = 0, kSyncFlow = 3 };
         template <int NW, int SYNC>
-        __device__ __forceinline__ void phaseSync(int wp)
+        __device__ __forceinline__ void phaseSync(int)
         {
-            if (SYNC == kSyncNamed)
-            {
-                if (wp & 1) { pairBarrier(wp); if (wp + 1 < NW) pairBarrier(wp + 1); }
-                else { if (wp + 1 < NW) pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
-            }
-            else if (SYNC == kSyncTail)
-            {
-                // warp 15 (odd) meets warp 14 on edge 15 first, then the tail group; warp 14 (even) takes edge 15 first as well: no cycle
-                if (wp >= 15)
-                {
-                    if (wp == 15) pairBarrier(15);
-                    asm volatile("bar.sync 0, %0;" ::"n"((NW - 15) * 32) : "memory");
-                }
-                else if (wp & 1) { pairBarrier(wp); pairBarrier(wp + 1); }
-                else { pairBarrier(wp + 1); if (wp > 0) pairBarrier(wp); }
-            }
-            else __syncthreads();
+            if (SYNC == kSyncCta) __syncthreads();          // (kSyncFlow never gets here: its step loop has no barriers)
         }
         // 1.0f where x < 0 (one FSET): the k of the linear-form velocity rule, folded into the sign of its coefficient
         __device__ __forceinline__ float signFlag(float x)
@@ -159,13 +143,14 @@ namespace pvc
 #endif
 
         // ---- one time step of a warp's R x 128 block; GEN = coefficient path (walls / edges / guard band as data) ----
-        template <int R, bool GEN>
+        // rows J0 .. J1 - 1 of the block (the whole block by default; kSyncFlow updates the row that needs the neighbour's data last)
+        template <int R, bool GEN, int J0 = 0, int J1 = R>
         __device__ __forceinline__ void pressureStep(float (&p)[R][4], const float (&vx)[R][4], const float (&vy)[R][4], const float4 vxBelow,
                                                      const float C, const float4* __restrict__ cP)
         {
             const float vb[4] = { vxBelow.x, vxBelow.y, vxBelow.z, vxBelow.w };
             #pragma unroll
-            for (int j = 0; j < R; ++j)
+            for (int j = J0; j < J1; ++j)
             {
                 const float vyRight = __shfl_down_sync(0xffffffffu, vy[j][0], 1);
                 float ck[4] = { C, C, C, C };
@@ -180,13 +165,13 @@ namespace pvc
                 }
             }
         }
-        template <int R, bool GEN>
+        template <int R, bool GEN, int J0 = 0, int J1 = R>
         __device__ __forceinline__ void velocityStep(const float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4], const float4 pAbove,
                                                      const float C, const float4* __restrict__ sX, const float4* __restrict__ sY)
         {
             const float pa[4] = { pAbove.x, pAbove.y, pAbove.z, pAbove.w };
             #pragma unroll
-            for (int j = 0; j < R; ++j)
+            for (int j = J0; j < J1; ++j)
             {
                 const float pLeft = __shfl_up_sync(0xffffffffu, p[j][3], 1);
                 if (!GEN)
@@ -225,8 +210,8 @@ namespace pvc
         {
             static constexpr int TR = NW * R;
             static constexpr size_t offVxTop = 0;
-            static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 32 * sizeof(float4);
-            static constexpr size_t offCoef = offPBot + (size_t)(NW + 1) * 32 * sizeof(float4);        // [3][TR][32] float4: cP, sX, sY
+            static constexpr size_t offPBot = offVxTop + (size_t)(NW + 1) * 64 * sizeof(float4);       // kSyncFlow: rows of 2 x 32 float4 (value, tag pairs)
+            static constexpr size_t offCoef = offPBot + (size_t)(NW + 1) * 64 * sizeof(float4);        // [3][TR][32] float4: cP, sX, sY
             static constexpr size_t total = offCoef + (size_t)3 * TR * 32 * sizeof(float4);
         };
 
@@ -242,6 +227,7 @@ namespace pvc
             const float* pulse;
             const float4* cP; const float4* sX; const float4* sY;       // this thread's coefficient float4s (row stride 32), shared memory
             int zero;
+            int phase;                // kSyncFlow: number of rows this warp has published (the tag of the row its neighbours expect next)
         };
 
         // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised
@@ -287,9 +273,51 @@ namespace pvc
         // the LAST step are left to the caller, which mails the strips first: the neighbours wait for those, nobody for the history.
         template <int NW, int R, int SYNC, bool GEN, bool TRACK>
         __device__ __forceinline__ void stepLoop(Ctx& X, const int t0, const int nsteps, float (&p)[R][4], float (&vx)[R][4], float (&vy)[R][4],
-                                                 float4 (*sVxTop)[32], float4 (*sPBot)[32], uint32_t& activity)
+                                                 float4* sVxTopRaw, float4* sPBotRaw, uint32_t& activity)
         {
             const int lane = X.lane, wp = X.wp;
+            if (SYNC == kSyncFlow)
+            {
+                // rows of the exchange arrays: [w][2][32] float4
+                const float4* vxFromBelow = sVxTopRaw + (size_t)(wp + 1) * 64;
+                const float4* pFromAbove = sPBotRaw + (size_t)wp * 64;
+                float4* myVxTop = sVxTopRaw + (size_t)wp * 64;
+                float4* myPBot = sPBotRaw + (size_t)(wp + 1) * 64;
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                #pragma unroll 1
+                for (int step = 0; step < nsteps; ++step)
+                {
+                    // ---- pressure sub-step (FDTD.cpp:125-141): the rows that need only this warp's own vx first
+                    pressureStep<R, GEN, 0, R - 1>(p, vx, vy, zero4, X.C, X.cP);
+                    const float4 vxBelow = (wp + 1 < NW) ? flow::poll(vxFromBelow, lane, X.phase) : zero4;
+                    pressureStep<R, GEN, R - 1, R>(p, vx, vy, vxBelow, X.C, X.cP);
+                    X.phase += 1;
+                    flow::publish(myPBot, lane, p[R - 1][0], p[R - 1][1], p[R - 1][2], p[R - 1][3], X.phase);
+                    if (step + 1 < nsteps) recordSample<R>(X, p);
+                    // ---- velocity sub-steps + edge overrides (FDTD.cpp:144-223): row 0 needs the p row of the warp above
+                    velocityStep<R, GEN, 1, R>(p, vx, vy, zero4, X.C, X.sX, X.sY);
+                    const float4 pAbove = (wp > 0) ? flow::poll(pFromAbove, lane, X.phase) : zero4;
+                    velocityStep<R, GEN, 0, 1>(p, vx, vy, pAbove, X.C, X.sX, X.sY);
+                    if (TRACK)
+                    {
+                        #pragma unroll
+                        for (int j = 0; j < R; ++j)
+                        {
+                            activity |= __float_as_uint(p[j][0]) | __float_as_uint(p[j][1]);
+                            activity |= __float_as_uint(p[j][2]) | __float_as_uint(p[j][3]);
+                        }
+                    }
+                    if (step + 1 < nsteps)
+                    {
+                        injectSample<R>(X, p, t0 + step);
+                        X.phase += 1;
+                        flow::publish(myVxTop, lane, vx[0][0], vx[0][1], vx[0][2], vx[0][3], X.phase);
+                    }
+                }
+                return;
+            }
+            float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(sVxTopRaw);
+            float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(sPBotRaw);
             #pragma unroll 1
             for (int step = 0; step < nsteps; ++step)
             {
@@ -328,11 +356,11 @@ namespace pvc
         {
             using SM = Smem<NW, R>;
             constexpr int TR = SM::TR;
-            static_assert(SYNC != kSyncNamed || NW <= 16, "16 named barriers per CTA");
-            static_assert(SYNC != kSyncTail || NW > 16, "the tail group starts at warp 15");
             extern __shared__ __align__(128) unsigned char smemRaw[];
-            float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offVxTop);       // [w]   = vx of warp w's first row
-            float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(smemRaw + SM::offPBot);         // [w+1] = p of warp w's last row
+            float4* sVxTopRaw = reinterpret_cast<float4*>(smemRaw + SM::offVxTop);
+            float4* sPBotRaw = reinterpret_cast<float4*>(smemRaw + SM::offPBot);
+            float4 (*sVxTop)[32] = reinterpret_cast<float4 (*)[32]>(sVxTopRaw);                    // [w]   = vx of warp w's first row
+            float4 (*sPBot)[32] = reinterpret_cast<float4 (*)[32]>(sPBotRaw);                      // [w+1] = p of warp w's last row
             float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);
 
             const int lane = threadIdx.x & 31;
@@ -347,7 +375,13 @@ namespace pvc
             const size_t cell0 = (size_t)(rBase + kGuardRows) * L.pitch + (cBase + kGuardCols);
             const size_t src0 = (size_t)s * L.plane + cell0;
 
-            if (wp == 0)
+            if (SYNC == kSyncFlow)
+            {
+                // tag 0 = nothing published yet (the first published row carries tag 1)
+                sVxTopRaw[(size_t)wp * 64 + lane] = make_float4(0.f, 0.f, 0.f, 0.f); sVxTopRaw[(size_t)wp * 64 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sPBotRaw[(size_t)(wp + 1) * 64 + lane] = make_float4(0.f, 0.f, 0.f, 0.f); sPBotRaw[(size_t)(wp + 1) * 64 + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            else if (wp == 0)
             {
                 sVxTop[NW][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                 sPBot[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -407,7 +441,7 @@ namespace pvc
                 const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
                 X.sj = (hasSrc && !sp.dead) ? sj : -1; X.sk = sk;
             }
-            X.pulse = A.pulse; X.zero = A.zero;
+            X.pulse = A.pulse; X.zero = A.zero; X.phase = 0;
             X.cP = sCoef + (size_t)(wp * R) * 32 + lane;
             X.sX = X.cP + (size_t)TR * 32;
             X.sY = X.cP + (size_t)2 * TR * 32;
@@ -430,9 +464,10 @@ namespace pvc
                     // ---- reload the halo ring from the mailbox: the words the neighbours wrote at the end of pass g - 1 carry tag g
                     const float4* q0 = A.xchg + (size_t)(g & (kSlots - 1)) * A.xchgSlot + src0;
                     const int tag = A.tagBase + g;
-                    // Poll ONE word -- the last one its writer stores -- and fetch the whole ring only when that one has arrived
-                    // (polling all 16 words of every halo thread kept ~50 KB per CTA and iteration moving through the L2 and made
-                    // the hand-over 3 us long); any word that still lags is caught by its own tag and fetched again.
+                    // Poll ONE word -- the last one its writer stores -- and fetch the whole ring only when that one has arrived; any
+                    // word that still lags is caught by its own tag and fetched again.  (Fetching the whole ring in every poll
+                    // iteration shortens the hand-over from 2.7 to 2.2 us but keeps ~25 KB per CTA and iteration moving through the
+                    // L2 while other warps are stepping: 1024^2 1.95 -> 2.07 ms per 1000 steps, profiles/r02_flow_exchange.txt.)
                     int jLast = 0;
                     #pragma unroll
                     for (int j = 0; j < R; ++j) if ((loadRows >> j) & 1u) jLast = j;
@@ -494,22 +529,30 @@ namespace pvc
                 PVC_STAMP_IF(wp == 0 && lane == 1, A, g, 7);
                 __syncwarp();            // the lanes that polled rejoin the others before the (warp-aligned) barriers below
                 PVC_STAMP(A, g, 1);
-                sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
-                phaseSync<NW, SYNC>(wp);
+                if (SYNC == kSyncFlow)
+                {
+                    X.phase += 1;
+                    flow::publish(sVxTopRaw + (size_t)wp * 64, lane, vx[0][0], vx[0][1], vx[0][2], vx[0][3], X.phase);
+                }
+                else
+                {
+                    sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
+                    phaseSync<NW, SYNC>(wp);
+                }
                 PVC_STAMP(A, g, 2);
 
                 uint32_t activity = 0u;
                 if (firstGen == kNeverActive)
                 {
-                    if (general) stepLoop<NW, R, SYNC, true, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
-                    else stepLoop<NW, R, SYNC, false, true>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    if (general) stepLoop<NW, R, SYNC, true, true>(X, t0, nsteps, p, vx, vy, sVxTopRaw, sPBotRaw, activity);
+                    else stepLoop<NW, R, SYNC, false, true>(X, t0, nsteps, p, vx, vy, sVxTopRaw, sPBotRaw, activity);
                     const bool hot = ((activity & 0x7fffffffu) != 0u) && !haloLane;
                     if (__any_sync(0xffffffffu, hot)) firstGen = g;
                 }
                 else
                 {
-                    if (general) stepLoop<NW, R, SYNC, true, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
-                    else stepLoop<NW, R, SYNC, false, false>(X, t0, nsteps, p, vx, vy, sVxTop, sPBot, activity);
+                    if (general) stepLoop<NW, R, SYNC, true, false>(X, t0, nsteps, p, vx, vy, sVxTopRaw, sPBotRaw, activity);
+                    else stepLoop<NW, R, SYNC, false, false>(X, t0, nsteps, p, vx, vy, sVxTopRaw, sPBotRaw, activity);
                 }
 
                 PVC_STAMP(A, g, 3);
@@ -782,22 +825,17 @@ namespace pvc
         }
     }
 
+    // tilings: 60..62 = 8 / 10 / 12 warps x 4 rows, two CTAs per SM; 63, 65, 64 = 16 / 18 / 20 warps x 4 rows, 66 = 16 x 5, one CTA per SM
+    #define PVC_RES_VARIANTS(X) \
+        X(60, 8, 4, 2, res::kSyncCta) X(61, 10, 4, 2, res::kSyncCta) X(62, 12, 4, 2, res::kSyncCta) \
+        X(63, 16, 4, 1, res::kSyncFlow) X(64, 20, 4, 1, res::kSyncFlow) X(65, 18, 4, 1, res::kSyncFlow) X(66, 16, 5, 1, res::kSyncFlow)
     int launchResidentSteps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         switch (variant)
         {
-            case 60: return res::launch<8, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 61: return res::launch<10, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 62: return res::launch<12, 4, 2, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 63: return res::launch<16, 4, 1, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
-            case 64: return res::launch<20, 4, 1, res::kSyncTail>(s, nsrc, t0, t1, hist, launches);
-            case 65: return res::launch<18, 4, 1, res::kSyncTail>(s, nsrc, t0, t1, hist, launches);
-            case 66: return res::launch<16, 5, 1, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
-            case 67: return res::launch<18, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 68: return res::launch<20, 4, 1, res::kSyncCta>(s, nsrc, t0, t1, hist, launches);
-            case 69: return res::launch<8, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
-            case 70: return res::launch<10, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
-            case 71: return res::launch<12, 4, 2, res::kSyncNamed>(s, nsrc, t0, t1, hist, launches);
+    #define X(v, nw, r, minb, sync) case v: return res::launch<nw, r, minb, sync>(s, nsrc, t0, t1, hist, launches);
+            PVC_RES_VARIANTS(X)
+    #undef X
             default: setError("resident step kernel: unknown variant %d", variant); return PVC_ERR_INVALID;
         }
     }
@@ -806,18 +844,9 @@ namespace pvc
     {
         switch (variant)
         {
-            case 60: return res::capacity<8, 4, 2, res::kSyncCta>(device);
-            case 61: return res::capacity<10, 4, 2, res::kSyncCta>(device);
-            case 62: return res::capacity<12, 4, 2, res::kSyncCta>(device);
-            case 63: return res::capacity<16, 4, 1, res::kSyncNamed>(device);
-            case 64: return res::capacity<20, 4, 1, res::kSyncTail>(device);
-            case 65: return res::capacity<18, 4, 1, res::kSyncTail>(device);
-            case 66: return res::capacity<16, 5, 1, res::kSyncNamed>(device);
-            case 67: return res::capacity<18, 4, 1, res::kSyncCta>(device);
-            case 68: return res::capacity<20, 4, 1, res::kSyncCta>(device);
-            case 69: return res::capacity<8, 4, 2, res::kSyncNamed>(device);
-            case 70: return res::capacity<10, 4, 2, res::kSyncNamed>(device);
-            case 71: return res::capacity<12, 4, 2, res::kSyncNamed>(device);
+    #define X(v, nw, r, minb, sync) case v: return res::capacity<nw, r, minb, sync>(device);
+            PVC_RES_VARIANTS(X)
+    #undef X
             default: return 0;
         }
     }

@@ -8,12 +8,12 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref
 # launch list of the same command (every kernel of the process)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-verify --no-extras > gpurun_out/r02_bench_under_ncu.json 2> gpurun_out/r02_ncu_launches.err
-# full captures: the step kernel of the bench workload (--T 400: one launch = 100 generations), the resident kernel on the plugin's
-# case (1024^2, one listener), the analyzer
-ncu --set full --clock-control none --import-source on -k regex:stepKernel -s 4 -c 1 -o gpurun_out/r02_prof_ws2 -f \
-    python bench.py --steps 1 --warmup 3 --T 400 --no-cpu-baseline --no-verify --no-extras > /dev/null 2> gpurun_out/r02_ncu_ws2.err
-ncu --set full --clock-control none --import-source on -k regex:residentKernel -s 2 -c 1 -o gpurun_out/r02_prof_res -f \
-    python tools/gpu_time_one.py BigRoom 1024 400 1 0 3 > /dev/null 2> gpurun_out/r02_ncu_res.err
+# full captures: the resident step kernel of the bench workload (--T 400: one launch = one source, 100 passes; the 13th launch is
+# the first of the timed solve), the generational kernel on config 4's grid (2048^2, two sources), the analyzer
+ncu --set full --clock-control none --import-source on -k regex:residentKernel -s 12 -c 1 -o gpurun_out/r02_prof_res -f \
+    python bench.py --steps 1 --warmup 3 --T 400 --no-cpu-baseline --no-verify --no-extras > /dev/null 2> gpurun_out/r02_ncu_res.err
+ncu --set full --clock-control none --import-source on -k regex:stepKernel -s 2 -c 1 -o gpurun_out/r02_prof_ws2 -f \
+    python tools/gpu_time_one.py HugeRoom 2048 400 2 0 3 > /dev/null 2> gpurun_out/r02_ncu_ws2.err
 ncu --set full --clock-control none --import-source on -k regex:encodeResponseKernel -s 3 -c 1 -o gpurun_out/r02_prof_encode -f \
     python bench.py --steps 1 --warmup 3 --T 400 --no-cpu-baseline --no-verify --no-extras > /dev/null 2> gpurun_out/r02_ncu_encode.err
 ls -la gpurun_out | grep r02_ | tail -12

@@ -44,11 +44,11 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum', 'sm__cycles_elapsed.avg']
-what = {"r02_prof_ws2": "bench.py --T 400 (BigRoom 1024^2, 4 sources; ONE launch = 100 generations x 4 steps)",
-        "r02_prof_res": "tools/gpu_time_one.py BigRoom 1024 400 1 0 (1024^2, one listener, 400 steps in one launch)",
+what = {"r02_prof_res": "bench.py --T 400 (BigRoom 1024^2, 4 sources; ONE launch = one source, 100 passes x 4 steps)",
+        "r02_prof_ws2": "tools/gpu_time_one.py HugeRoom 2048 400 2 0 (config 4's grid: 2048^2, two sources; one launch = 100 generations x 4 steps)",
         "r02_prof_encode": "bench.py --T 400"}
 with open(os.path.join(OUT, f"{tag}_ncu_kernels.txt"), "w") as f:
-    for rep in ("r02_prof_ws2", "r02_prof_res", "r02_prof_encode"):
+    for rep in ("r02_prof_res", "r02_prof_ws2", "r02_prof_encode"):
         path = os.path.join(GO, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue

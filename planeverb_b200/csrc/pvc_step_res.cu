@@ -228,6 +228,7 @@ namespace pvc
             const float4* cP; const float4* sX; const float4* sY;       // this thread's coefficient float4s (row stride 32), shared memory
             int zero;
             int phase;                // kSyncFlow: number of rows this warp has published (the tag of the row its neighbours expect next)
+            bool warpHasSource;       // some lane of this warp holds the pulse cell (warp-uniform: the other 17 warps branch around the injection)
         };
 
         // K (<= 4) time steps; the caller has published this warp's first vx row in sVxTop and synchronised
@@ -309,7 +310,7 @@ namespace pvc
                     }
                     if (step + 1 < nsteps)
                     {
-                        injectSample<R>(X, p, t0 + step);
+                        if (X.warpHasSource) injectSample<R>(X, p, t0 + step);
                         X.phase += 1;
                         flow::publish(myVxTop, lane, vx[0][0], vx[0][1], vx[0][2], vx[0][3], X.phase);
                     }
@@ -343,7 +344,7 @@ namespace pvc
                 if (step + 1 < nsteps)
                 {
                     // ---- inject (FDTD.cpp:234)
-                    injectSample<R>(X, p, t0 + step);
+                    if (X.warpHasSource) injectSample<R>(X, p, t0 + step);
                     sVxTop[wp][lane] = make_float4(vx[0][0], vx[0][1], vx[0][2], vx[0][3]);
                     phaseSync<NW, SYNC>(wp);            // also the write-after-read fence of sPBot
                 }
@@ -440,6 +441,7 @@ namespace pvc
                 const int sj = sp.cell_r - rBase, sk = sp.cell_c - cBase;
                 const bool hasSrc = (sj >= 0) && (sj < R) && (sk >= 0) && (sk < 4);
                 X.sj = (hasSrc && !sp.dead) ? sj : -1; X.sk = sk;
+                X.warpHasSource = __any_sync(0xffffffffu, X.sj >= 0);
             }
             X.pulse = A.pulse; X.zero = A.zero; X.phase = 0;
             X.cP = sCoef + (size_t)(wp * R) * 32 + lane;

@@ -55,7 +55,7 @@ namespace pvc
     // variant 0 = auto: the kernel with the smallest ESTIMATED time per pass (4 time steps of every source of the batch).  The
     // estimates are the measured pass periods of profiles/r02_resident_variants.txt (B200, microseconds):
     //   * resident kernel (pvc_step_res.cu; state in registers for the whole solve, only halo strips through the L2): a launch holds
-    //     as many sources as fit co-resident and advances them one pass per period -- 5.0 (8-warp tiles; x 1.4 when two CTAs share
+    //     as many sources as fit co-resident and advances them one pass per period -- 4.4 (4-warp tiles, grids of the reference's own contract), 5.0 (8-warp tiles; x 1.4 when two CTAs share
     //     an SM), 6.8 / 9.0 (10 / 12 warps), 6.4 / 7.4 / 7.7 (16 / 18 / 20 warps, barrier-free row exchange) -- most of it the
     //     neighbour hand-over, so the period barely depends on how full the GPU is;
     //   * generational kernel (pvc_step_ws2.cu, TMA-staged tiles pulled from a work queue): 5.56 us per work item and SM (variant 47,
@@ -72,7 +72,7 @@ namespace pvc
     }
     static int bestResident(const pvc_config& c, int sms, double* passUs)
     {
-        static const struct { int v; double period; } cand[] = { {60, 5.0}, {61, 6.8}, {62, 9.0}, {63, 6.4}, {65, 7.4}, {64, 7.7} };
+        static const struct { int v; double period; } cand[] = { {67, 4.4}, {60, 5.0}, {61, 6.8}, {62, 9.0}, {63, 6.4}, {65, 7.4}, {64, 7.7} };
         int best = 0;
         double bestUs = 0;
         for (const auto& k : cand)
@@ -80,6 +80,7 @@ namespace pvc
             if (!variantAvailable(k.v)) continue;
             const long tiles = residentTiles(c, k.v), cap = (long)sms * variantMinBlocks(k.v);
             if (tiles > cap) continue;
+            if (k.v == 67 && tiles * c.max_sources > 64) continue;             // measured on 70^2 .. 191^2 only (0.41 / 1.19 ms against 0.46 / 1.45)
             const long perLaunch = cap / tiles < c.max_sources ? cap / tiles : c.max_sources;
             const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
             const double us = (double)launches * k.period * (tiles * perLaunch > sms ? 1.4 : 1.0);

@@ -1121,7 +1121,7 @@ namespace pvc
     // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, kind
     //   kind 0 one launch per 4 steps (fusedStepKernel)      1 persistent        2 TMA persistent   3 generational
     //        4 first warp-specialised generational           5 ws2 (pvc_step_ws2.cu)                6 resident (pvc_step_res.cu)
-    // The default build carries what the product selects -- 47 / 50 (ws2), 60..66 (resident), 18 (fallback without the TMA
+    // The default build carries what the product selects -- 47 / 50 (ws2), 60..67 (resident), 18 (fallback without the TMA
     // driver entry point) -- plus step_kernel = 1 (two-launch baseline, pvc_step.cu).  Everything else documents the
     // search (profiles/r01_variants.txt) and is compiled only with make EXTRA=-DPVC_ALL_VARIANTS.
     struct Variant { int nw, r, minBlocks, persistent, builtin; };
@@ -1138,7 +1138,7 @@ namespace pvc
                                          {12, 4, 1, 5, 0}, {12, 5, 1, 5, 0},                             // 52, 53
                                          {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0},   // 54..59 unused
                                          {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1},    // 60..65: resident (pvc_step_res.cu)
-                                         {16, 5, 1, 6, 1} };                                                                                          // 66: resident, 5 rows per warp
+                                         {16, 5, 1, 6, 1}, {4, 4, 4, 6, 1} };       // 66: resident, 5 rows per warp; 67: resident, 4-warp tiles for tiny grids                                                                                          // 66: resident, 5 rows per warp
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     bool variantAvailable(int variant)
@@ -1484,6 +1484,7 @@ namespace pvc
         {
             case 806: return maskVariant<8, 6, 1>(s);
             case 804: return maskVariant<8, 4, 1>(s);
+            case 404: return maskVariant<4, 4, 1>(s);
             case 1004: return maskVariant<10, 4, 1>(s);
             case 1204: return maskVariant<12, 4, 1>(s);
             case 1404: return maskVariant<14, 4, 1>(s);

@@ -827,10 +827,12 @@ namespace pvc
         }
     }
 
-    // tilings: 60..62 = 8 / 10 / 12 warps x 4 rows, two CTAs per SM; 63, 65, 64 = 16 / 18 / 20 warps x 4 rows, 66 = 16 x 5, one CTA per SM
+    // tilings: 60..62 = 8 / 10 / 12 warps x 4 rows, two CTAs per SM; 63, 65, 64 = 16 / 18 / 20 warps x 4 rows, 66 = 16 x 5, one CTA per SM;
+    // 67 = 4 warps x 4 rows (8 owned rows: the reference's own 70^2 .. 191^2 contract, where a pass is pure latency and more SMs help)
     #define PVC_RES_VARIANTS(X) \
         X(60, 8, 4, 2, res::kSyncCta) X(61, 10, 4, 2, res::kSyncCta) X(62, 12, 4, 2, res::kSyncCta) \
-        X(63, 16, 4, 1, res::kSyncFlow) X(64, 20, 4, 1, res::kSyncFlow) X(65, 18, 4, 1, res::kSyncFlow) X(66, 16, 5, 1, res::kSyncFlow)
+        X(63, 16, 4, 1, res::kSyncFlow) X(64, 20, 4, 1, res::kSyncFlow) X(65, 18, 4, 1, res::kSyncFlow) X(66, 16, 5, 1, res::kSyncFlow) \
+        X(67, 4, 4, 4, res::kSyncCta)
     int launchResidentSteps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         switch (variant)

@@ -381,7 +381,9 @@ namespace pvc
             float4* sCoef = reinterpret_cast<float4*>(smemRaw + SM::offCoef);
 
             const int lane = threadIdx.x & 31;
-            const int wp = threadIdx.x >> 5;
+            // broadcast from lane 0: the compiler then KNOWS the warp index is warp-uniform (uniform registers, plain branches instead of
+            // divergence guards around every shuffle / vote of the step loop)
+            const int wp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
             const int tps = A.tilesPerSource;
             const int sLocal = blockIdx.x / tps;
             const int tile = blockIdx.x - sLocal * tps;

@@ -582,7 +582,7 @@ namespace pvc
             volatile int* pubTotal = pubRing + 17;                                                   // tiles handed out in all (-1: still running)
 
             const int lane = threadIdx.x & 31;
-            const int wp = threadIdx.x >> 5;
+            const int wp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform and known to be (uniform registers, no divergence guards)
             const int total = A.numGen * A.numTiles;
             const int tps = A.tilesPerSource;
 

@@ -55,14 +55,15 @@ namespace pvc
     // variant 0 = auto: the kernel with the smallest ESTIMATED time per pass (4 time steps of every source of the batch).  The
     // estimates are the measured pass periods of profiles/r02_resident_variants.txt (B200, microseconds):
     //   * resident kernel (pvc_step_res.cu; state in registers for the whole solve, only halo strips through the L2): a launch holds
-    //     as many sources as fit co-resident and advances them one pass per period -- 4.4 (4-warp tiles, grids of the reference's own contract), 5.0 (8-warp tiles; x 1.4 when two CTAs share
-    //     an SM), 6.8 / 9.0 (10 / 12 warps), 6.4 / 7.4 / 7.7 (16 / 18 / 20 warps, barrier-free row exchange) -- most of it the
+    //     as many sources as fit co-resident and advances them one pass per period -- 3.0 (4-warp tiles, grids of the reference's own
+    //     contract), 4.2 (8-warp tiles; x 1.4 when two CTAs share an SM), 5.8 / 7.6 (10 / 12 warps), 5.5 / 6.3 / 6.8 (16 / 18 / 20
+    //     warps, barrier-free row exchange) -- a good third of it the
     //     neighbour hand-over, so the period barely depends on how full the GPU is;
     //   * generational kernel (pvc_step_ws2.cu, TMA-staged tiles pulled from a work queue): 5.56 us per work item and SM (variant 47,
     //     56-row tiles), 3.9 (variant 50, 32-row tiles), and never less than the publish -> acquire -> TMA chain between generations
     //     (11.5 / 9.1 us).
     // So: one listener up to 1024^2 and batches of small grids (the plugin's case) run resident; a batch whose sources each fill the GPU
-    // (four 1024^2 sources: 4 x 7.4 against 792 items x 5.56 / 148 = 29.8) runs resident too; batches that leave a resident
+    // (four 1024^2 sources: 4 x 6.3 against 792 items x 5.56 / 148 = 29.8) runs resident too; batches that leave a resident
     // launch half empty (four 768^2 sources) and grids beyond the register files (2048^2) take the work queue.  Without
     // cuTensorMapEncodeTiled in the driver the generational kernels cannot run: resident, else the plain 8 x 6 kernel (18).
     static long residentTiles(const pvc_config& c, int v)
@@ -72,7 +73,7 @@ namespace pvc
     }
     static int bestResident(const pvc_config& c, int sms, double* passUs)
     {
-        static const struct { int v; double period; } cand[] = { {67, 4.4}, {60, 5.0}, {61, 6.8}, {62, 9.0}, {63, 6.4}, {65, 7.4}, {64, 7.7} };
+        static const struct { int v; double period; } cand[] = { {67, 3.0}, {60, 4.2}, {61, 5.8}, {62, 7.6}, {63, 5.5}, {65, 6.3}, {64, 6.8} };
         int best = 0;
         double bestUs = 0;
         for (const auto& k : cand)

@@ -484,28 +484,19 @@ namespace pvc
                     // ---- reload the halo ring from the mailbox: the words the neighbours wrote at the end of pass g - 1 carry tag g
                     const float4* q0 = A.xchg + (size_t)(g & (kSlots - 1)) * A.xchgSlot + src0;
                     const int tag = A.tagBase + g;
-                    // Poll ONE word -- the last one its writer stores -- and fetch the whole ring only when that one has arrived; any
-                    // word that still lags is caught by its own tag and fetched again.  (Fetching the whole ring in every poll
-                    // iteration shortens the hand-over from 2.7 to 2.2 us but keeps ~25 KB per CTA and iteration moving through the
-                    // L2 while other warps are stepping: 1024^2 1.95 -> 2.07 ms per 1000 steps, profiles/r02_flow_exchange.txt.)
-                    int jLast = 0;
-                    #pragma unroll
-                    for (int j = 0; j < R; ++j) if ((loadRows >> j) & 1u) jLast = j;
-                    const float4* qLast = q0 + (size_t)jLast * L.pitch + 3;
+                    // The ring fetch IS the poll: every iteration loads all the words (eight 256-bit loads in flight per thread) and
+                    // checks every tag, so the pass starts one L2 round trip after the last word has landed.  (With 128-bit loads --
+                    // sixteen per thread and iteration -- polling ONE word first and fetching the ring in a second round trip was
+                    // the faster scheme; with 256-bit loads it is the slower one: 1024^2 x 4 7.30 -> 7.10 ms per 1000 steps,
+                    // 512^2 2.28 -> 2.14, profiles/r02_flow_exchange.txt.)
                     unsigned spins = 0;
-                    bool waiting = true;
                     while (true)
                     {
-                        if (waiting)
                         {
-                            if (__float_as_int(loadWord(qLast).w) == tag) { waiting = false; PVC_STAMP_IF(wp == 0 && lane == 1, A, g, 6); }
-                        }
-                        if (!waiting)
-                        {
-                            // The loads are volatile asm statements; a load followed by its use, word after word, made the reload
-                            // sixteen L2 round trips long (4 us of an 8.9 us pass), four words of a row at a time still four.  A thread
-                            // that reloads ALL its rows (halo warps; lanes 0 / 31 of the others) overwrites its whole state, so the
-                            // registers for sixteen words in flight are there: one round trip.  Partial reloads go row by row.
+                            // The loads are volatile asm statements: a load followed by its use, word after word, would make the fetch one
+                            // L2 round trip per word.  A thread that reloads ALL its rows (halo warps; lanes 0 / 31 of the others)
+                            // overwrites its whole state, so the registers for all its words in flight are there: one round trip.
+                            // Partial reloads (the live padding row) go row by row.
                             int bad = 0;
                             if (loadRows == (1u << R) - 1u)
                             {

@@ -10,12 +10,15 @@
 //     others) into a mailbox plane and reads its own halo ring back from it: ~50 KB per tile and pass through the L2
 //     instead of 155 KB (full tile in through TMA, owned cells out), no TMA stage to drain, no store burst, no producer /
 //     publisher warps.  Hand-over WITHOUT fences, flags or CTA barriers: a strip cell travels as ONE 16-byte word
-//     {p, vx, vy, tag} (tag = solve epoch << 16 | pass), written and read with single 128-bit strong accesses, so a
-//     reader that sees the tag it expects has the data that came with it (the low-latency protocol of collective
-//     libraries; it relies on an aligned 16-byte access being performed as one L2 transaction, which
-//     tools/micro/vec16_atomicity.cu stresses on the device and every parity test would expose).  The halo loads ARE the
-//     poll.  Measured against the first version of this kernel (one counter per tile, CTA barrier + st.release, acquire
-//     polls, then reloads): the hand-over chain cost 4.2 us of an 8.3 us pass (profiles/r02_resident_trace.txt).
+//     {p, vx, vy, tag} (tag = solve epoch << 16 | pass), two words per 256-bit strong access, so a reader that sees the
+//     tag it expects in a word has the data that came with it (the low-latency protocol of collective libraries; it
+//     relies on an aligned 16-byte unit being read and written indivisibly, which tools/micro/vec16_atomicity.cu stresses
+//     on the device for 128- and 256-bit accesses and every parity test would expose).  The halo loads ARE the poll:
+//     eight loads in flight per thread, repeated until every tag matches.  Measured against the first version of this
+//     kernel (one counter per tile, CTA barrier + st.release, acquire polls, then reloads: a hand-over chain of 4.2 us in
+//     an 8.3 us pass, profiles/r02_resident_trace.txt): ~1.9 us of a 6.3 us pass (profiles/r02_flow_exchange.txt).
+//   * Inside a tile the warps exchange their boundary rows WITHOUT barriers as well (pvc_internal.h, namespace flow): tagged
+//     rows in shared memory, polled by the reader after it has updated the rows that do not need them.
 //     Eight mailbox slots (pass & 7) keep a writer from overwriting cells a lagging warp of a neighbour still has to read.
 //     All CTAs are co-resident (cooperative launch); a batch of sources that does not fit is solved a few sources per
 //     launch, one launch after the other.
@@ -32,12 +35,13 @@
 //     planes (cP, and k folded into the sign of c: -Courant marks k = 1) are staged once per solve in shared memory.
 //     Admittances must be >= 0 (absorption in [0, 1]); pvc_apply_geometry rejects anything else.
 //
-// Selected automatically when every tile of at least one source fits the GPU at once (grids up to ~1024 x 1024): the
-// reference's own contract (70^2 .. 191^2 cells, one listener) runs as one to four CTAs with no hand-over at all or
-// one per pass instead of a publish -> acquire -> TMA chain per generation.
+// Selected automatically (pvc_api.cu::resolveVariant, by estimated pass time) when every tile of at least one source fits the
+// GPU at once and a launch is reasonably full: one listener up to 1024 x 1024, batches of small grids, batches of 1024^2
+// sources (the headline bench).  The reference's own contract (70^2 .. 191^2 cells, one listener) runs on 4-warp tiles.
 //
 // Roofline: HBM by the 28 B / cell-update accounting of SURVEY.md 8d; physically the kernel
-// moves the 4-byte history record per cell-step and the strips, and is bound by instruction issue.
+// moves the 4-byte history record per cell-step and the strips (4.2 B of DRAM traffic per cell-update), and is bound by
+// instruction issue inside a pass and by the neighbour hand-over between passes.
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>

@@ -103,6 +103,17 @@ PVC_API void pvc_destroy(pvc_solver* s);
 /* bytes of device memory pvc_create would allocate for cfg (pressure history dominates: 4*T*plane per source) */
 PVC_API size_t pvc_memory_requirement(const pvc_config* cfg);
 
+/* Streamed solve for responses whose pressure history (4 bytes x cells x T per source) does not fit the device: the history
+ * holds history_steps samples (rounded down to a multiple of 8) and the response is solved in K = ceil(T / history_steps)
+ * chunks.  Forward sweep: every chunk's time steps followed by the causal part of the analysis (onset, dry energy, flux, wet
+ * energy: Analyzer.cpp:146-247) with the running sums carried per cell; the state is checkpointed at every chunk start.
+ * Backward sweep: the chunks are recomputed from their checkpoints in reverse order for the anti-causal Schroeder integral and
+ * regression (Analyzer.cpp:282-326).  Same results as pvc_create's solver, bit for bit, at (2 - 1/K) x the time steps and 1/K
+ * of the history memory.  Runs on the generational step kernel only (needs cuTensorMapEncodeTiled); pvc_fetch_ir /
+ * pvc_fetch_pressure are not available (there is no full history), pvc_fetch_state only after a run with analyze == 0. */
+PVC_API int  pvc_create_streamed(const pvc_config* cfg, int history_steps, pvc_solver** out);
+PVC_API size_t pvc_memory_requirement_streamed(const pvc_config* cfg, int history_steps);
+
 /* Gaussian source pulse, T floats (Grid.cpp:12-27, evaluated by the host) */
 PVC_API int  pvc_set_pulse(pvc_solver* s, const float* pulse, int n);
 

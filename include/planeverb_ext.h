@@ -30,6 +30,10 @@ typedef struct pvx_scene pvx_scene;
  * simulation on the device (FreeGrid.cpp:71-94). stepKernel/variant: see pvc_config. */
 PVC_API int  pvx_create(float sizeX, float sizeY, int resolution, int responseLength, float efree,
                         int maxSources, int device, int stepKernel, int variant, pvx_scene** out);
+/* the same scene on a streamed solver (pvc_create_streamed): the pressure history holds historySteps samples and the response is
+ * solved in chunks, for grids / response lengths whose full history does not fit the device.  historySteps <= 0: pvx_create. */
+PVC_API int  pvx_create_streamed(float sizeX, float sizeY, int resolution, int responseLength, float efree,
+                                 int maxSources, int device, int stepKernel, int variant, int historySteps, pvx_scene** out);
 PVC_API void pvx_destroy(pvx_scene* sc);
 
 /* ints[10] = gx, gy, T, fs, fluxSamples, drySamples, wetSamples, tailSamples, freeSamples, maxSources

@@ -421,6 +421,264 @@ namespace pvc
         walkDelay[(size_t)s * cells + serial] = (occ > 0.f) ? (float)onset : FLT_MAX;
     }
 
+    // ---- streamed solve: the same analysis over a history that holds one chunk of the response at a time ----------------
+    // EncodeResponse (Analyzer.cpp:139-328) reads a cell's response twice: ascending from sample 0 (onset, Edry, flux, wet
+    // energy) and descending from the last sample (Schroeder integral + regression).  With a bounded history the ascending part
+    // runs chunk by chunk during the forward sweep (forwardChunkKernel) and the descending part chunk by chunk over the
+    // RECOMPUTED chunks in reverse order (backwardChunkKernel; chunk 0 comes last and writes the results).  Every sum is
+    // carried per cell between chunks in fp32 and continues in the reference's order with the reference's operations, so the
+    // outputs are bit-identical to encodeResponseKernel's on the full history (tests/test_gpu_streamed.py).
+    // Carry planes ([kCarryPlanes][sources * cells]): 0 onset (int bits, -1 none), 1 edry, 2 fx, 3 fy, 4 vx, 5 vy, 6 wet,
+    // 7 edc, 8 xysum, 9 ysum.  Sample t of the response is sample t - base of the history; L.T is the history's length.
+    template <int HC>
+    __global__ void __launch_bounds__(128)
+    forwardChunkKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
+                       float* __restrict__ carry, size_t cstride, int base, int len)
+    {
+        const int c = blockIdx.x * HC + threadIdx.x;
+        const int r = blockIdx.y;
+        const int s = blockIdx.z;
+        if ((int)threadIdx.x >= HC || c >= L.gy) return;
+        const size_t cells = (size_t)L.gx * L.gy;
+        const size_t ci = (size_t)s * cells + (size_t)r * L.gy + c;
+        const size_t wi = cellIndex(L, r, c);
+        const float wSelf = w[wi];
+        if (!isAirA(wSelf)) return;                          // a wall cell never has an onset: its carry keeps onset = -1
+        const int T = A.T;
+        const int end = base + len;                          // one past the chunk's last sample
+        int onset = __float_as_int(carry[ci]);
+        if (onset >= 0 && base >= min(onset + A.drySamples + 1 + A.wetSamples, T)) return;      // every causal window is closed
+        const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c) - (ptrdiff_t)base * HC;     // sample t at H[t * HC]
+        constexpr ptrdiff_t hs = HC;
+        constexpr int kBatch = 16;
+        if (onset < 0)
+        {   // Analyzer.cpp:146-154, continued where the previous chunk stopped
+            for (int t0 = base; t0 < end && onset < 0; t0 += kBatch)
+            {
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldg(H + (ptrdiff_t)min(t0 + u, end - 1) * hs);
+                #pragma unroll
+                for (int u = kBatch - 1; u >= 0; --u)
+                    if (t0 + u < end && fabsf(v[u]) > kAudibleThreshold) onset = t0 + u;
+            }
+            if (onset >= 0) carry[ci] = __int_as_float(onset);
+        }
+        // no onset yet: every sample of the chunk precedes it, and so lies inside both dry windows (they start at sample 0)
+        const int directEnd = onset >= 0 ? onset + A.drySamples : T;
+        const int dryEnd = min(min(directEnd, T), end);
+        const int fluxEnd = min(onset >= 0 ? min(onset + A.fluxSamples, T) : T, end);
+        float edry = carry[cstride + ci];
+        if (base < fluxEnd)
+        {
+            float fx = carry[2 * cstride + ci], fy = carry[3 * cstride + ci], vx = carry[4 * cstride + ci], vy = carry[5 * cstride + ci];
+            const float wUp = w[wi - L.pitch], wLeft = w[wi - 1];
+            const bool topEdge = (r == 0), leftEdge = (c == 0);
+            const bool upAir = isAirA(wUp), leftAir = isAirA(wLeft);
+            const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
+            const ptrdiff_t leftOff = leftEdge ? 0 : (((c % HC) != 0) ? -1 : -(ptrdiff_t)L.T * hs + (hs - 1));
+            constexpr int kCausalBatch = 4;
+            for (int t0 = base; t0 < fluxEnd; t0 += kCausalBatch)
+            {
+                float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
+                #pragma unroll
+                for (int u = 0; u < kCausalBatch; ++u)
+                {
+                    const float* q = H + (ptrdiff_t)min(t0 + u, end - 1) * hs;
+                    bp[u] = __ldg(q);
+                    bu[u] = __ldg(q + upOff);
+                    bl[u] = __ldg(q + leftOff);
+                }
+                #pragma unroll
+                for (int u = 0; u < kCausalBatch; ++u)
+                {
+                    if (t0 + u >= fluxEnd) break;
+                    const float p = bp[u];
+                    vx = topEdge ? -p : (upAir ? __fsub_rn(vx, __fmul_rn(A.courant, __fsub_rn(p, bu[u]))) : -__fmul_rn(wUp, p));
+                    vy = leftEdge ? -p : (leftAir ? __fsub_rn(vy, __fmul_rn(A.courant, __fsub_rn(p, bl[u]))) : -__fmul_rn(wLeft, p));
+                    edry = __fadd_rn(edry, __fmul_rn(p, p));
+                    fx = __fadd_rn(fx, __fmul_rn(p, vx));
+                    fy = __fadd_rn(fy, __fmul_rn(p, vy));
+                }
+            }
+            carry[2 * cstride + ci] = fx; carry[3 * cstride + ci] = fy; carry[4 * cstride + ci] = vx; carry[5 * cstride + ci] = vy;
+        }
+        for (int t = max(base, fluxEnd); t < dryEnd; ++t)
+        {
+            const float p = __ldg(H + (ptrdiff_t)t * hs);
+            edry = __fadd_rn(edry, __fmul_rn(p, p));
+        }
+        carry[cstride + ci] = edry;
+        if (onset >= 0)
+        {   // wet energy over [directEnd + 1, min(directEnd + 1 + W, T)) (Analyzer.cpp:235-247)
+            const int wetEnd = min(min(directEnd + 1 + A.wetSamples, T), end);
+            const int wetBegin = max(directEnd + 1, base);
+            if (wetBegin < wetEnd)
+            {
+                float wet = carry[6 * cstride + ci];
+                const float* q = H + (ptrdiff_t)wetBegin * hs;
+                #pragma unroll 4
+                for (int j = wetBegin; j < wetEnd; ++j, q += hs)
+                {
+                    const float p = __ldg(q);
+                    wet = __fadd_rn(wet, __fmul_rn(p, p));
+                }
+                carry[6 * cstride + ci] = wet;
+            }
+        }
+    }
+
+    template <int HC>
+    __global__ void __launch_bounds__(128)
+    backwardChunkKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
+                        const SourceParams* __restrict__ src, float* __restrict__ carry, size_t cstride, int base, int len,
+                        float* __restrict__ results, float* __restrict__ delay, float* __restrict__ walkDelay)
+    {
+        __shared__ LogfEntry sTab[16];
+        __shared__ LogfEntry sTab33[kLogf33];
+        if (threadIdx.x < 16) sTab[threadIdx.x] = kLogfTable[threadIdx.x];
+        if (threadIdx.x < kLogf33) sTab33[threadIdx.x] = buildLogfTable33(threadIdx.x, kLogfTable);
+        __shared__ float4 sTabExp[kExpEntries];
+        for (int E = threadIdx.x; E < kExpEntries; E += blockDim.x) sTabExp[E] = buildExponentEntry(E);
+        __syncthreads();
+
+        const int c = blockIdx.x * HC + threadIdx.x;
+        const int r = blockIdx.y;
+        const int s = blockIdx.z;
+        if ((int)threadIdx.x >= HC || c >= L.gy) return;
+        const size_t cells = (size_t)L.gx * L.gy;
+        const size_t serial = (size_t)r * L.gy + c;
+        const size_t ci = (size_t)s * cells + serial;
+        const bool last = (base == 0);                       // chunk 0 is processed last: finish the regression, write the results
+        const int onset = isAirA(w[cellIndex(L, r, c)]) ? __float_as_int(carry[ci]) : -1;
+        if (onset < 0)
+        {   // wall cell or no onset: results left untouched (Analyzer.cpp:161-165)
+            if (last) { delay[ci] = FLT_MAX; walkDelay[ci] = FLT_MAX; }
+            return;
+        }
+        const int T = A.T;
+        const int end = base + len;
+        const int directEnd = onset + A.drySamples;
+        const int start = directEnd + 1;
+        const int endPoint = T - A.tailSamples;
+        const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c) - (ptrdiff_t)base * HC;
+        constexpr ptrdiff_t hs = HC;
+        constexpr int kBatch = PVC_AN_BATCH;
+        float edc = carry[7 * cstride + ci], xysum = carry[8 * cstride + ci], ysum = carry[9 * cstride + ci];
+        bool touched = false;
+        {   // tail of the curve: energy only (Analyzer.cpp:297-301)
+            int i = end - 1;
+            const int stop = max(max(endPoint, 0), base);
+            if (i >= stop) touched = true;
+            const float* q = H + (ptrdiff_t)i * hs;
+            for (; i - (kBatch - 1) >= stop; i -= kBatch, q -= kBatch * hs)
+            {
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - u * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+            }
+            for (; i >= stop; --i, q -= hs)
+            {
+                const float p = __ldcs(q);
+                edc = __fadd_rn(edc, __fmul_rn(p, p));
+            }
+        }
+        {   // regression part (Analyzer.cpp:303-319)
+            int i = min(endPoint, end) - 1;
+            const int stop = max(start, base);
+            if (i >= stop)
+            {
+                touched = true;
+                float x = (float)(i - start);              // exact; decremented by 1.0f per sample (< 2^24)
+                const float* q = H + (ptrdiff_t)i * hs;
+                for (; i - (kBatch - 1) >= stop; i -= kBatch, q -= kBatch * hs)
+                {
+                    float v[kBatch];
+                    #pragma unroll
+                    for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - u * hs);
+                    float e[kBatch];
+                    #pragma unroll
+                    for (int u = 0; u < kBatch; ++u)
+                    {
+                        edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+                        e[u] = edc;
+                    }
+                    const bool normal = isNormalPositive(e[0]) && isNormalPositive(e[kBatch - 1]);
+                    float y[kBatch];
+                    if (normal)
+                    {
+                        #pragma unroll
+                        for (int u = 0; u < kBatch; ++u) y[u] = decibelsNormal(e[u], sTab33, sTabExp);
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int u = 0; u < kBatch; ++u) y[u] = decibels(e[u], sTab);
+                    }
+                    #pragma unroll
+                    for (int u = 0; u < kBatch; ++u)
+                    {
+                        xysum = __fadd_rn(xysum, __fmul_rn(y[u], x));
+                        ysum = __fadd_rn(ysum, y[u]);
+                        x = __fsub_rn(x, 1.0f);
+                    }
+                }
+                for (; i >= stop; --i, q -= hs)
+                {
+                    const float p = __ldcs(q);
+                    edc = __fadd_rn(edc, __fmul_rn(p, p));
+                    const float y = decibels(edc, sTab);
+                    xysum = __fadd_rn(xysum, __fmul_rn(y, x));
+                    ysum = __fadd_rn(ysum, y);
+                    x = __fsub_rn(x, 1.0f);
+                }
+            }
+        }
+        if (!last)
+        {
+            if (touched) { carry[7 * cstride + ci] = edc; carry[8 * cstride + ci] = xysum; carry[9 * cstride + ci] = ysum; }
+            return;
+        }
+        // ---- the outputs, exactly as encodeResponseKernel forms them (Analyzer.cpp:199-230, 250, 321-326) ----
+        const float edry = carry[cstride + ci], fx = carry[2 * cstride + ci], fy = carry[3 * cstride + ci], wet = carry[6 * cstride + ci];
+        const SourceParams sp = src[s];
+        float efreePr;
+        {
+            const float lX = __fmul_rn((float)sp.efree_r, A.dx), lY = __fmul_rn((float)sp.efree_c, A.dx);
+            const float eX = __fmul_rn((float)r, A.dx), eY = __fmul_rn((float)c, A.dx);
+            const float ddx = __fsub_rn(eX, lX), ddy = __fsub_rn(eY, lY);
+            const float rr = __fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+            efreePr = (rr == 0.f) ? A.efree : __fdiv_rn(A.efree, rr);
+        }
+        const float occ = __fsqrt_rn(__fdiv_rn(edry, efreePr));
+        float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+        norm = __fdiv_rn(-1.0f, (norm > 0.0f ? norm : 1.0f));
+        const float sdx = __fmul_rn(norm, fx), sdy = __fmul_rn(norm, fy);
+        const float rinv = __fdiv_rn(1.0f, fmaxf(0.001f, occ));
+        const float pw = (float)pow((double)__fdiv_rn(rinv, 12.f), (double)0.8f);
+        const float lowpass = __fadd_rn(-147.f, __fdiv_rn(18390.f, __fadd_rn(1.f, pw)));
+        const float wetGain = __fsqrt_rn(__fdiv_rn(wet, A.efree));
+        const int regressN = endPoint - start;
+        const float rn = (float)regressN;
+        const float xmean = __fmul_rn(__fsub_rn(rn, 1.0f), 0.5f);
+        const float xsum = __fmul_rn(rn, xmean);
+        const float denominator = __fmul_rn(__fmul_rn(1.0f / 12.0f, rn), __fsub_rn(__fmul_rn(rn, rn), 1.0f));
+        const float ymean = __fdiv_rn(ysum, rn);
+        float numerator = __fsub_rn(xysum, __fmul_rn(ymean, xsum));
+        numerator = __fsub_rn(numerator, __fmul_rn(xmean, ysum));
+        numerator = __fadd_rn(numerator, __fmul_rn(__fmul_rn(rn, xmean), ymean));
+        const float slopePerSample = __fdiv_rn(numerator, denominator);
+        const float slopePerSec = __fmul_rn(slopePerSample, (float)A.fs);
+        const float rt60 = __fdiv_rn(-60.f, slopePerSec);
+        float* out = results + ci * 8;
+        out[0] = occ; out[1] = wetGain; out[2] = rt60; out[3] = lowpass;
+        out[6] = sdx; out[7] = sdy;
+        delay[ci] = (float)onset;
+        walkDelay[ci] = (occ > 0.f) ? (float)onset : FLT_MAX;
+    }
+
     // ---- Analyzer::EncodeListenerDirection (Analyzer.cpp:340-431) by pointer jumping ----------------------------------
     // walkDelay holds the onset of every cell a walk may step onto (has an onset and occlusion > 0, Analyzer.cpp:372-374)
     // and FLT_MAX elsewhere.  The reference walks, from every cell, to the 8-neighbour with the strictly smallest delay
@@ -655,7 +913,6 @@ namespace pvc
         const Layout& L = s->L;
         const AnalyzeParams A = paramsOf(s);
         dim3 block(128, 1, 1);
-        dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
         dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);     // one block per history strip and row
         if (L.hist_chunk == kHistChunkDefault)
             encodeResponseKernel<kHistChunkDefault><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
@@ -664,10 +921,22 @@ namespace pvc
             encodeResponseKernel<kValidCols><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
                                                                             s->hintsValid ? s->firstActive : nullptr);
         else { setError("analyzer: unsupported history strip width %d", L.hist_chunk); return PVC_ERR_INVALID; }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        *launches += 1;
+        return launchListenerDirection(s, nsrc, launches);
+    }
+
+    int launchListenerDirection(pvc_solver* s, int nsrc, int* launches)
+    {
+        const Layout& L = s->L;
+        const AnalyzeParams A = paramsOf(s);
+        dim3 block(128, 1, 1);
+        dim3 grid((L.gy + 127) / 128, L.gx, nsrc);
         if (s->walkSequential)                              // pvc_set_walk_mode: the reference's walk, the cross-check of the tests
         {
             listenerDirectionKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay);
-            *launches += 2;
+            *launches += 1;
         }
         else
         {
@@ -684,10 +953,46 @@ namespace pvc
             for (int k = 0; k < rounds; ++k)
                 walkJumpKernel<<<dim3((unsigned)((cells + 255) / 256), nsrc), 256, 0, s->stream>>>(cells, kHops, s->walkNext);
             walkResolveKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
-            *launches += 3 + rounds;
+            *launches += 2 + rounds;
         }
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        if (e != cudaSuccess) { setError("listener direction launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    static int streamChecks(const pvc_solver* s)
+    {
+        if (!s->chunkT || !s->carry) { setError("streamed analyzer: the solver was not created with pvc_create_streamed"); return PVC_ERR_INVALID; }
+        if (s->L.hist_chunk != kHistChunkDefault) { setError("streamed analyzer: unsupported history strip width %d", s->L.hist_chunk); return PVC_ERR_INVALID; }
+        return PVC_OK;
+    }
+
+    int launchStreamForward(pvc_solver* s, int nsrc, int base, int len, int* launches)
+    {
+        const int rc = streamChecks(s);
+        if (rc) return rc;
+        const Layout& L = s->L;
+        const AnalyzeParams A = paramsOf(s);
+        const dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);
+        forwardChunkKernel<kHistChunkDefault><<<stripGrid, 128, 0, s->stream>>>(L, A, s->hist, s->w, s->carry, (size_t)s->cfg.max_sources * L.gx * L.gy, base, len);
+        *launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("streamed analyzer (forward) launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+        return PVC_OK;
+    }
+
+    int launchStreamBackward(pvc_solver* s, int nsrc, int base, int len, int* launches)
+    {
+        const int rc = streamChecks(s);
+        if (rc) return rc;
+        const Layout& L = s->L;
+        const AnalyzeParams A = paramsOf(s);
+        const dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);
+        backwardChunkKernel<kHistChunkDefault><<<stripGrid, 128, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->carry, (size_t)s->cfg.max_sources * L.gx * L.gy, base, len,
+                                                                                s->results, s->delay, s->walkDelay);
+        *launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { setError("streamed analyzer (backward) launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
         return PVC_OK;
     }
 

@@ -28,8 +28,9 @@ namespace pvc
 
     static int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 
-    static Layout makeLayout(const pvc_config& c)
+    static Layout makeLayout(const pvc_config& c, int historySteps = 0)        // historySteps: samples the history holds (0: c.T)
     {
+        const int histT = historySteps > 0 ? historySteps : c.T;
         Layout L;
         L.gx = c.gx; L.gy = c.gy;
         L.rows = c.gx + 1; L.cols = c.gy + 1;
@@ -44,10 +45,10 @@ namespace pvc
         L.rows_alloc = L.tiles_y * L.valid_rows + 2 * kGuardRows;
         if (L.rows_alloc < L.rows + kGuardRows + 1) L.rows_alloc = L.rows + kGuardRows + 1;
         L.plane = (size_t)L.rows_alloc * L.pitch;
-        L.T = c.T;
+        L.T = histT;
         L.hist_chunk = fusedHistChunk(c.reserved);
         L.hist_chunks = (L.cols + L.hist_chunk - 1) / L.hist_chunk;
-        L.hist_row = (size_t)L.hist_chunks * c.T * L.hist_chunk;
+        L.hist_row = (size_t)L.hist_chunks * histT * L.hist_chunk;
         L.hist_source = (size_t)L.rows * L.hist_row;
         return L;
     }
@@ -90,7 +91,7 @@ namespace pvc
         *passUs = bestUs;
         return best;
     }
-    static int resolveVariant(const pvc_config& c)
+    static int resolveVariant(const pvc_config& c, bool streamed = false)     // streamed: only the generational kernels start from a given state
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
         int sms = 148;
@@ -101,12 +102,12 @@ namespace pvc
         if (!tma) cudaGetLastError();
         double residentUs = 0;
         const int resident = bestResident(c, sms, &residentUs);
-        if (!tma) return resident ? resident : 18;
+        if (!tma) return streamed ? 0 : (resident ? resident : 18);
         const long cols = (c.gy + 1 + kValidCols - 1) / kValidCols;
         const double items47 = (double)((c.gx + 1 + 47) / 48) * cols * c.max_sources, items50 = (double)((c.gx + 1 + 23) / 24) * cols * c.max_sources;
         const double us47 = items47 * 5.56 / sms > 11.5 ? items47 * 5.56 / sms : 11.5;
         const double us50 = items50 * 3.9 / sms > 9.1 ? items50 * 3.9 / sms : 9.1;
-        if (resident && residentUs <= us47 && residentUs <= us50) return resident;
+        if (!streamed && resident && residentUs <= us47 && residentUs <= us50) return resident;
         return us50 < us47 ? 50 : 47;
     }
 
@@ -272,6 +273,75 @@ namespace pvc
     }
 }
 
+namespace pvc
+{
+    __global__ void initCarryKernel(float* __restrict__ carry, size_t cstride, size_t n)
+    {
+        const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        carry[i] = __int_as_float(-1);                                       // plane 0: onset, none yet
+        #pragma unroll
+        for (int k = 1; k < kCarryPlanes; ++k) carry[k * cstride + i] = 0.f;
+    }
+
+    // Streamed solve (pvc_create_streamed): the response in chunks of s->chunkT samples through a history that holds one chunk.
+    //   forward sweep   chunk 0 .. K-1: [checkpoint the state] -> time steps -> causal analyzer sums (launchStreamForward)
+    //   backward sweep  chunk K-1 (its history is still resident), then K-2 .. 0: restore the checkpoint -> the SAME time steps again
+    //                   -> backward Schroeder sums (launchStreamBackward; chunk 0 finishes the regression and writes the results)
+    // Re-running a chunk from its checkpoint reproduces its history bit for bit (the kernels are deterministic: no atomics or
+    // order-dependent arithmetic in the field update), so the outputs equal the full-history solve's exactly, at (2 - 1/K) x
+    // the time steps and 1/K of the history memory.  Checkpoints: the three state planes at the start of chunks 1 .. K-2 (chunk 0
+    // starts from zero, chunk K-1 is never recomputed).
+    static int runStreamed(pvc_solver* s, int nsrc, int analyze, int* launches)
+    {
+        const Layout& L = s->L;
+        const int T = s->cfg.T, C = s->chunkT, K = (T + C - 1) / C;
+        const size_t S = (size_t)s->cfg.max_sources, cells = (size_t)L.gx * L.gy;
+        if (s->slowMaskDirty) { int rc = rebuildSlowMask(s); if (rc) return rc; }
+        if (analyze)
+        {
+            const size_t n = S * cells;
+            initCarryKernel<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->carry, n, n);
+            *launches += 1;
+        }
+        auto copyState = [&](float* const dst[3], float* const src[3]) -> int {
+            for (int f = 0; f < 3; ++f)
+                PVC_CUDA(cudaMemcpyAsync(dst[f], src[f], sizeof(float) * L.plane * (size_t)nsrc, cudaMemcpyDeviceToDevice, s->stream));
+            return PVC_OK;
+        };
+        auto slot = [&](int k, float* out[3]) { for (int f = 0; f < 3; ++f) out[f] = s->ckpt + ((size_t)(k - 1) * 3 + f) * S * L.plane; };
+        for (int k = 0; k < K; ++k)
+        {
+            const int base = k * C, end = (base + C < T) ? base + C : T;
+            if (s->cur != 0) { setError("streamed solve: chunk %d does not start on ping-pong buffer 0", k); return PVC_ERR_CUDA; }
+            if (analyze && k >= 1 && k <= K - 2) { float* q[3]; slot(k, q); int rc = copyState(q, s->state[0]); if (rc) return rc; }
+            s->finalPass = (k == K - 1);
+            int rc = launchFusedSteps(s, nsrc, base, end, s->hist, launches);
+            if (!rc && analyze) rc = launchStreamForward(s, nsrc, base, end - base, launches);
+            if (rc) return rc;
+        }
+        s->stateStale = 0;
+        s->lastStepLaunches = *launches;
+        if (!analyze) return PVC_OK;
+        // a pipelined fetch of the previous run's grids must finish before the results are overwritten
+        if (s->copyPending) PVC_CUDA(cudaStreamWaitEvent(s->stream, s->evCopied, 0));
+        int rc = launchStreamBackward(s, nsrc, (K - 1) * C, T - (K - 1) * C, launches);
+        if (rc) return rc;
+        for (int k = K - 2; k >= 0; --k)
+        {
+            if (k == 0) { rc = zeroState(s, nsrc); if (rc) return rc; }
+            else { float* q[3]; slot(k, q); rc = copyState(s->state[0], q); if (rc) return rc; s->cur = 0; }
+            s->finalPass = 0;
+            s->stateStale = 1;                      // from here on the state planes hold the end of chunk k, not of the response
+            rc = launchFusedSteps(s, nsrc, k * C, (k + 1) * C, s->hist, launches);
+            if (!rc) rc = launchStreamBackward(s, nsrc, k * C, C, launches);
+            if (rc) return rc;
+        }
+        s->finalPass = 1;
+        return launchListenerDirection(s, nsrc, launches);
+    }
+}
+
 using namespace pvc;
 
 extern "C" {
@@ -294,17 +364,45 @@ int pvc_device_memory(int device, size_t* free_bytes, size_t* total_bytes)
     return PVC_OK;
 }
 
-size_t pvc_memory_requirement(const pvc_config* cfg)
+// chunk length of a streamed solve as the device uses it: a multiple of 8 samples (an even number of 4-step generations, so every
+// chunk starts on ping-pong buffer 0), at least 8, and no chunking at all (0) when the whole response fits
+static int streamChunk(const pvc_config* cfg, int history_steps)
 {
-    if (!validConfig(cfg)) return 0;
-    pvc_config r = *cfg; r.reserved = resolveVariant(*cfg);
-    const Layout L = makeLayout(r);
-    const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
-    return sizeof(float) * (6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 + 32 * S : (variantKind(r.reserved) == 5 ? 7 : 4)) * L.plane + S * L.hist_source + (size_t)cfg->T +
-                            S * cells * 11 + 3 * (size_t)cfg->T) + (size_t)L.tiles_x * L.tiles_y * 64;
+    if (history_steps <= 0) return 0;
+    int c = history_steps / 8 * 8;
+    if (c < 8) c = 8;
+    return c;
 }
 
-int pvc_create(const pvc_config* cfg, pvc_solver** out)
+static size_t memoryRequirement(const pvc_config* cfg, int history_steps)
+{
+    if (!validConfig(cfg)) return 0;
+    const int chunk = streamChunk(cfg, history_steps);
+    pvc_config r = *cfg; r.reserved = resolveVariant(*cfg, chunk > 0);
+    const Layout L = makeLayout(r, chunk);
+    const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
+    size_t floats = 6 * S * L.plane + (variantKind(r.reserved) == 6 ? 7 + 32 * S : (variantKind(r.reserved) == 5 ? 7 : 4)) * L.plane + S * L.hist_source + (size_t)cfg->T +
+                    S * cells * 11 + 3 * (size_t)cfg->T;
+    if (chunk > 0)
+    {
+        const int K = (cfg->T + chunk - 1) / chunk;
+        floats += (size_t)kCarryPlanes * S * cells + (K > 2 ? (size_t)(K - 2) * 3 * S * L.plane : 0);
+    }
+    return sizeof(float) * floats + (size_t)L.tiles_x * L.tiles_y * 64;
+}
+
+size_t pvc_memory_requirement(const pvc_config* cfg) { return memoryRequirement(cfg, 0); }
+size_t pvc_memory_requirement_streamed(const pvc_config* cfg, int history_steps) { return memoryRequirement(cfg, history_steps); }
+
+static int createSolver(const pvc_config* cfg, int history_steps, pvc_solver** out);
+int pvc_create(const pvc_config* cfg, pvc_solver** out) { return createSolver(cfg, 0, out); }
+int pvc_create_streamed(const pvc_config* cfg, int history_steps, pvc_solver** out)
+{
+    if (history_steps < 1) { setError("pvc_create_streamed: history_steps must be positive"); if (out) *out = nullptr; return PVC_ERR_INVALID; }
+    return createSolver(cfg, history_steps, out);
+}
+
+static int createSolver(const pvc_config* cfg, int history_steps, pvc_solver** out)
 {
     if (!out) { setError("pvc_create: null out"); return PVC_ERR_INVALID; }
     *out = nullptr;
@@ -317,7 +415,16 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
     pvc_solver* s = new pvc_solver();
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
-    s->cfg.reserved = resolveVariant(*cfg);
+    s->chunkT = streamChunk(cfg, history_steps);
+    s->finalPass = 1;
+    s->cfg.reserved = resolveVariant(*cfg, s->chunkT > 0);
+    if (s->chunkT && (cfg->step_kernel != 0 || (s->cfg.reserved != 47 && s->cfg.reserved != 50)))
+    {
+        setError("pvc_create_streamed: a streamed solve needs the generational step kernel (variant 47 or 50, TMA driver entry point); got step_kernel %d, variant %d",
+                 cfg->step_kernel, s->cfg.reserved);
+        delete s;
+        return PVC_ERR_INVALID;
+    }
     if (cfg->step_kernel == 0 && !variantAvailable(s->cfg.reserved))
     {
         setError("pvc_create: step-kernel variant %d is not compiled into this build (make EXTRA=-DPVC_ALL_VARIANTS)", s->cfg.reserved);
@@ -325,7 +432,7 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
         return PVC_ERR_INVALID;
     }
     s->device = cfg->device;
-    s->L = makeLayout(s->cfg);
+    s->L = makeLayout(s->cfg, s->chunkT);
     { int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device); s->numSMs = sms > 0 ? sms : 148; }
     const Layout& L = s->L;
     const size_t S = (size_t)cfg->max_sources, cells = (size_t)cfg->gx * cfg->gy;
@@ -364,6 +471,12 @@ int pvc_create(const pvc_config* cfg, pvc_solver** out)
         PVC_TRY(cudaMemsetAsync(s->resXchg, 0, sizeof(float) * 4 * 8 * S * L.plane, s->stream));
     }
     PVC_TRY(cudaMalloc(&s->hist, sizeof(float) * S * L.hist_source));
+    if (s->chunkT)
+    {
+        const int K = (cfg->T + s->chunkT - 1) / s->chunkT;
+        PVC_TRY(cudaMalloc(&s->carry, sizeof(float) * (size_t)kCarryPlanes * S * cells));
+        if (K > 2) PVC_TRY(cudaMalloc(&s->ckpt, sizeof(float) * (size_t)(K - 2) * 3 * S * L.plane));
+    }
     PVC_TRY(cudaMalloc(&s->pulse, sizeof(float) * (size_t)cfg->T));
     PVC_TRY(cudaMemsetAsync(s->pulse, 0, sizeof(float) * (size_t)cfg->T, s->stream));
     PVC_TRY(cudaMalloc(&s->results, sizeof(float) * S * cells * 8));
@@ -394,7 +507,7 @@ void pvc_destroy(pvc_solver* s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->stateBlock);
+    cudaFree(s->stateBlock); cudaFree(s->ckpt); cudaFree(s->carry);
     cudaFree(s->w); for (int f = 0; f < 3; ++f) { cudaFree(s->coef[f]); cudaFree(s->lin[f]); } cudaFree(s->resXchg); cudaFree(s->rects); cudaFree(s->slowMask); cudaFree(s->bpMask); cudaFree(s->tileOrder); cudaFree(s->firstActive); cudaFree(s->tileCounters); cudaFree(s->doneGen); cudaFree(s->hist); cudaFree(s->pulse);
     if (s->copyStream) { cudaStreamSynchronize(s->copyStream); cudaStreamDestroy(s->copyStream); }
     if (s->evAnalyzed) cudaEventDestroy(s->evAnalyzed);
@@ -472,6 +585,7 @@ int pvc_compute_efree(pvc_solver* s, int lr, int lc, int er, int ec, int n, floa
     if (!s || n < 1 || n > s->cfg.T || lr < 0 || lc < 0 || lr > s->cfg.gx || lc > s->cfg.gy ||
         er < 0 || ec < 0 || er > s->cfg.gx || ec > s->cfg.gy)
     { setError("pvc_compute_efree: bad argument (n=%d, T=%d)", n, s ? s->cfg.T : -1); return PVC_ERR_INVALID; }
+    if (s->chunkT && n > s->chunkT) { setError("pvc_compute_efree: the %d-sample probe does not fit the %d-sample history of this streamed solver", n, s->chunkT); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     const Layout& L = s->L;
     // the free field is a second, empty coefficient plane (FreeGrid.cpp:11-18): swap it in for n steps
@@ -536,6 +650,18 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
     s->hintsValid = (s->cfg.step_kernel == 0);
     if (s->hintsValid)
         PVC_CUDA(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * (size_t)n * s->L.tiles_x * s->L.tiles_y * 32, s->stream));
+    if (s->chunkT)
+    {   // streamed solve: time steps and analysis interleave chunk by chunk (the step/analyzer split of pvc_last_timing is not
+        // meaningful: everything is reported as step time)
+        s->hintsValid = 0;
+        rc = runStreamed(s, n, analyze, &launches);
+        if (rc) return rc;
+        PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        PVC_CUDA(cudaEventRecord(s->ev[2], s->stream));
+        s->lastSources = n;
+        s->lastLaunches = launches;
+        return PVC_OK;
+    }
     rc = runSteps(s, n, s->cfg.T, &launches);
     if (rc) return rc;
     s->lastStepLaunches = launches;
@@ -674,6 +800,7 @@ int pvc_fetch_ir(pvc_solver* s, int source, int r, int c, float* out3T)
 {
     if (!s || !out3T || source < 0 || source >= s->cfg.max_sources || r < 0 || c < 0 || r > s->cfg.gx || c > s->cfg.gy)
     { setError("pvc_fetch_ir: bad argument"); return PVC_ERR_INVALID; }
+    if (s->chunkT) { setError("pvc_fetch_ir: a streamed solver keeps no full history"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     int rc = launchIrRebuild(s, source, r, c, s->scratch);
     if (rc) return rc;
@@ -699,6 +826,7 @@ int pvc_fetch_pressure(pvc_solver* s, int source, int t, float* plane)
 {
     if (!s || !plane || source < 0 || source >= s->cfg.max_sources || t < 0 || t >= s->cfg.T)
     { setError("pvc_fetch_pressure: bad argument"); return PVC_ERR_INVALID; }
+    if (s->chunkT) { setError("pvc_fetch_pressure: a streamed solver keeps no full history"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     return fetchPlane(s, s->hist + (size_t)source * s->L.hist_source, t, plane);
 }
@@ -706,6 +834,7 @@ int pvc_fetch_pressure(pvc_solver* s, int source, int t, float* plane)
 int pvc_fetch_state(pvc_solver* s, int source, float* p, float* vx, float* vy)
 {
     if (!s || source < 0 || source >= s->cfg.max_sources) { setError("pvc_fetch_state: bad argument"); return PVC_ERR_INVALID; }
+    if (s->chunkT && s->stateStale) { setError("pvc_fetch_state: after an analyzed streamed solve the state planes hold the end of its first chunk (run with analyze = 0 for the final state)"); return PVC_ERR_INVALID; }
     PVC_CUDA(cudaSetDevice(s->device));
     float* host[3] = { p, vx, vy };
     for (int f = 0; f < 3; ++f)

@@ -62,6 +62,7 @@ namespace pvc
     // sample must be one dense box
     constexpr int kHistChunkDefault = 128;
     constexpr int kNeverActive = 0x7f7f7f7f;     // memset(0x7f) pattern of firstActive
+    constexpr int kCarryPlanes = 10;             // streamed solve: onset, edry, fx, fy, vx, vy, wet, edc, xysum, ysum per cell
 
     // float offset of sample 0 of alloc cell (r, c) inside one source's history; sample t is + t*hist_chunk
     __host__ __device__ inline size_t histCell(const Layout& L, int r, int c)
@@ -150,6 +151,14 @@ struct pvc_solver
     int useGraphs;
     int walkSequential;      // pvc_set_walk_mode: 1 = listener direction by the reference's sequential walk (cross-check)
     pvc::GraphSlot graphs[pvc::kMaxGraphBatch + 1];   // captured step-launch sequences, by batch size
+    // streamed solve (pvc_create_streamed): the history holds chunkT samples only.  Forward sweep chunk by chunk (state checkpointed
+    // at every chunk start, causal analyzer sums carried per cell), then the chunks are RECOMPUTED from their checkpoints in
+    // reverse order for the backward Schroeder pass -- the kernels are deterministic, so every output stays bit-exact.
+    int chunkT;              // samples of history kept (0: the whole response, L.T == cfg.T); L.T == chunkT otherwise
+    int finalPass;           // the chunk being stepped ends the response
+    int stateStale;          // the state planes hold the end of chunk 0, not of the response (after the backward sweep)
+    float* ckpt;             // state at the start of chunks 1 .. K-2: [K-2][3 fields][max_sources * plane]
+    float* carry;            // analyzer state carried across chunks: [pvc::kCarryPlanes][max_sources * gx*gy]
 };
 
 namespace pvc
@@ -246,6 +255,11 @@ namespace pvc
     int fusedHistChunk(int variant);
     // analyzer kernels (pvc_analyze.cu)
     int launchAnalyzer(pvc_solver* s, int nsrc, int* launches);
+    // streamed solve: causal sums over samples base .. base+len-1 (in the history as samples 0 .. len-1), carried in s->carry;
+    // backward Schroeder sums over the same chunk (chunk 0 comes last and writes the results); listener-direction kernels
+    int launchStreamForward(pvc_solver* s, int nsrc, int base, int len, int* launches);
+    int launchStreamBackward(pvc_solver* s, int nsrc, int base, int len, int* launches);
+    int launchListenerDirection(pvc_solver* s, int nsrc, int* launches);
     int launchIrRebuild(pvc_solver* s, int source, int r, int c, float* out_dev);
     // geometry kernels (pvc_geometry.cu)
     int launchClearGeometry(pvc_solver* s);

@@ -174,6 +174,7 @@ namespace pvc
             unsigned long long* debug;             // optional counters (PVC_DEBUG_COUNTERS): tiles, slow-path hand-overs, cycles waiting / total
             int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
             float courant;
+            int finalPass;                         // the launch ends the response (0: a chunk of a streamed solve that another chunk follows)
         };
         // state: loads, [buffer][p,vx,vy], box 128 x tile rows; coef: gx, gy, bp; store: [buffer][p,vx,vy], box 120 x (tile's owned rows), clipped to the
         // alloc grid; hist: 5-D {120 columns, T, strips, rows, sources}, box 120 x 1 x 1 x owned rows x 1 (TS variants only)
@@ -1005,7 +1006,7 @@ namespace pvc
                     X.onlyLast = false;
                     if (hasSrc && (m->srcR >= L.gx || m->srcC >= L.gy || m->srcDead))
                     {
-                        if (TS || t0 + nsteps < A.T) X.sj = -1;
+                        if (TS || t0 + nsteps < A.T || !A.finalPass) X.sj = -1;
                         else X.onlyLast = true;
                     }
                 }
@@ -1236,7 +1237,10 @@ namespace pvc
             using SM = Smem<NW, R, CB, TS, SO>;
             const Layout& L = s->L;
             if (!s->tmaReady || s->tmaTileRows != NW * R) { setError("ws2 step kernel: tensor maps not built for %d-row tiles", NW * R); return PVC_ERR_INVALID; }
-            if (t0 != 0 || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
+            // a chunk of a streamed solve (pvc_create_streamed) is a launch of its own that starts from the state planes as they are:
+            // samples t0 .. t1 - 1 of the response, recorded as samples 0 .. t1 - t0 - 1 of the (chunk-sized) history
+            if ((t0 != 0 && !s->chunkT) || s->cur != 0) { setError("ws2 step kernel: must start at step 0"); return PVC_ERR_INVALID; }
+            if (s->chunkT && (TS || SO)) { setError("ws2 step kernel: variant not usable for a streamed solve"); return PVC_ERR_INVALID; }
             if (!s->bpMask) { setError("ws2 step kernel: descriptor buffer missing"); return PVC_ERR_INVALID; }
             if (L.hist_chunk != (TS ? kValidCols : kHistChunkDefault)) { setError("ws2 step kernel: history strip width %d does not match the variant", L.hist_chunk); return PVC_ERR_INVALID; }
             const size_t smem = SM::total;
@@ -1255,7 +1259,7 @@ namespace pvc
             memset(maps.store, 0, sizeof(maps.store)); memset(&maps.hist, 0, sizeof(maps.hist));
             const int numTiles = L.tiles_x * L.tiles_y * nsrc;
             const int grid = numTiles < s->numSMs ? numTiles : s->numSMs;          // all CTAs must be co-resident (1 CTA per SM)
-            const int gens = (t1 + kTileK - 1) / kTileK;
+            const int gens = (t1 - t0 + kTileK - 1) / kTileK;
             const int perLaunch = 256;                                             // generations per launch (bounds kernel time)
             cudaMemsetAsync(s->doneGen, 0, sizeof(int) * (size_t)numTiles, s->stream);
             cudaMemsetAsync(s->tileCounters, 0, sizeof(int) * (size_t)((gens + perLaunch - 1) / perLaunch + 1), s->stream);
@@ -1267,11 +1271,12 @@ namespace pvc
             { static const char* dbg = getenv("PVC_DEBUG_NOHIST"); if (dbg) A.hist = nullptr; }      // debug: memory-floor probe (results invalid)
 #endif
             if (TS || SO) { rc = buildStoreMaps(s, TS ? A.hist : nullptr, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
-            A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder; A.firstActive = s->firstActive;
-            A.src = s->src; A.pulse = s->pulse;
+            A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder;
+            A.firstActive = s->chunkT ? nullptr : s->firstActive;                   // activity hints count generations from sample 0
+            A.src = s->src; A.pulse = s->pulse + t0; A.finalPass = s->chunkT ? s->finalPass : 1;
             A.doneGen = s->doneGen; A.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
             A.tilesPerSource = L.tiles_x * L.tiles_y; A.nsrc = nsrc; A.numTiles = numTiles;
-            A.T = t1; A.courant = s->cfg.courant;
+            A.T = t1 - t0; A.courant = s->cfg.courant;
             {
                 // sources per group: as many as keep both ping-pong copies of the group's state (2 x 12 B per cell) inside
                 // ~85 MB of the 126 MB L2, groups balanced; the history stream is written evict-first and does not compete

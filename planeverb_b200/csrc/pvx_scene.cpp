@@ -26,6 +26,12 @@ extern "C" {
 int pvx_create(float sizeX, float sizeY, int resolution, int responseLength, float efree,
                int maxSources, int device, int stepKernel, int variant, pvx_scene** out)
 {
+    return pvx_create_streamed(sizeX, sizeY, resolution, responseLength, efree, maxSources, device, stepKernel, variant, 0, out);
+}
+
+int pvx_create_streamed(float sizeX, float sizeY, int resolution, int responseLength, float efree,
+                        int maxSources, int device, int stepKernel, int variant, int historySteps, pvx_scene** out)
+{
     if (!out) return PVC_ERR_INVALID;
     *out = nullptr;
     // Context's validation (PvContext.cpp:101-107)
@@ -37,7 +43,7 @@ int pvx_create(float sizeX, float sizeY, int resolution, int responseLength, flo
     if (g.gx < 2 || g.gy < 2) { delete sc; return PVC_ERR_INVALID; }
     pvc_config cfg = pvhost::configFor(g, maxSources, device, stepKernel);
     cfg.reserved = variant;
-    int rc = pvc_create(&cfg, &sc->solver);
+    int rc = historySteps > 0 ? pvc_create_streamed(&cfg, historySteps, &sc->solver) : pvc_create(&cfg, &sc->solver);
     if (rc) { delete sc; return rc; }
     pvhost::gaussianPulse(resolution, g.fs, sc->pulse, g.T);
     rc = pvc_set_pulse(sc->solver, sc->pulse.data(), g.T);

@@ -23,6 +23,7 @@ _STATUS = {1: "invalid argument/config", 2: "device memory", 3: "CUDA error", 4:
 # every symbol include/planeverb_cuda.h and include/planeverb_ext.h declare
 PVC_SYMBOLS = [
     "pvc_device_count", "pvc_device_memory", "pvc_last_error", "pvc_create", "pvc_destroy", "pvc_memory_requirement",
+    "pvc_create_streamed", "pvc_memory_requirement_streamed",
     "pvc_set_pulse", "pvc_clear_geometry", "pvc_apply_geometry", "pvc_fetch_coefficients",
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_gather_results_async", "pvc_gather_wait", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
@@ -30,7 +31,7 @@ PVC_SYMBOLS = [
     "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_set_walk_mode", "pvc_step_variant",
 ]
 PVX_SYMBOLS = [
-    "pvx_create", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
+    "pvx_create", "pvx_create_streamed", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
     "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup", "pvx_lookup_async", "pvx_lookup_wait",
     "pvx_impulse_response", "pvx_solver",
     "pvx_create_multi", "pvx_destroy_multi", "pvx_multi_devices", "pvx_multi_scene", "pvx_multi_batch", "pvx_multi_add_aabb",
@@ -82,6 +83,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.pvc_last_error.restype = C.c_char_p
         L.pvc_memory_requirement.restype = C.c_size_t
+        L.pvc_memory_requirement_streamed.restype = C.c_size_t
+        L.pvc_memory_requirement_streamed.argtypes = [_vp, _i]
         L.pvc_results_dev.restype = _vp
         L.pvc_stream.restype = _vp
         L.pvx_solver.restype = _vp
@@ -89,6 +92,7 @@ def lib():
         L.pvc_host_alloc.argtypes = [C.c_size_t]
         L.pvc_host_free.argtypes = [_vp]
         L.pvx_create.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _vp]
+        L.pvx_create_streamed.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _i, _vp]
         L.pvx_destroy.argtypes = [_vp]
         L.pvx_info.argtypes = [_vp, _vp, _vp]
         L.pvx_pulse.argtypes = [_vp, _vp, _i]
@@ -174,16 +178,26 @@ def derive_emitter_cell(resolution, size_x, size_y, x, z):
     return None if code else (int(rc[0]), int(rc[1]))
 
 
-def memory_requirement(gx, gy, T, max_sources, variant=0, step_kernel=0):
-    """Device bytes a solver of this size allocates (pvc_memory_requirement: host arithmetic, needs no GPU); 0 = invalid config."""
+def memory_requirement(gx, gy, T, max_sources, variant=0, step_kernel=0, history_steps=0):
+    """Device bytes a solver of this size allocates (pvc_memory_requirement / pvc_memory_requirement_streamed: host arithmetic,
+    needs no GPU); 0 = invalid config.  history_steps > 0: a streamed solver whose history holds that many samples."""
     cfg = PvcConfig(gx=int(gx), gy=int(gy), T=int(T), fs=1443, resolution=275, dx=0.3565818, courant=0.6666667, flux_samples=7, dry_samples=14,
                     wet_samples=115, tail_samples=14, max_sources=int(max_sources), device=0, step_kernel=int(step_kernel),
                     reserved=int(variant))
+    if history_steps > 0:
+        return int(lib().pvc_memory_requirement_streamed(C.byref(cfg), int(history_steps)))
     return int(lib().pvc_memory_requirement(C.byref(cfg)))
 
 
 def device_count():
     return int(lib().pvc_device_count())
+
+
+def device_memory(device=0):
+    """(free, total) bytes of device memory (pvc_device_memory)"""
+    f, t = C.c_size_t(), C.c_size_t()
+    _check(lib().pvc_device_memory(int(device), C.byref(f), C.byref(t)), "pvc_device_memory")
+    return int(f.value), int(t.value)
 
 
 def _check(rc, what):
@@ -224,10 +238,13 @@ class Scene:
     """Grid + FreeGrid + Analyzer on one B200 (batched listeners)."""
 
     def __init__(self, size_x, size_y, resolution, T=0, efree=-1.0, max_sources=1, device=0,
-                 step_kernel=0, variant=0):
+                 step_kernel=0, variant=0, history_steps=0):
+        """history_steps > 0: streamed solver (pvx_create_streamed) -- the pressure history holds that many samples and the
+        response is solved in chunks; same results, for responses whose full history does not fit the device."""
         h = _vp()
-        _check(lib().pvx_create(size_x, size_y, int(resolution), int(T), float(efree), int(max_sources),
-                                int(device), int(step_kernel), int(variant), C.byref(h)), "pvx_create")
+        _check(lib().pvx_create_streamed(size_x, size_y, int(resolution), int(T), float(efree), int(max_sources),
+                                         int(device), int(step_kernel), int(variant), int(history_steps), C.byref(h)), "pvx_create")
+        self.history_steps = int(history_steps)
         self._h = h
         ii = np.zeros(10, np.int32)
         ff = np.zeros(4, np.float32)

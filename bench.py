@@ -25,7 +25,8 @@ Metric: Mcell-updates/s = gx*gy*T*sources / seconds (interior cells x reference-
               and (fast_math) the shipped Release flags
   extras    : the other BASELINE configs through the same library: the Sandbox contract case and configs[1]
               (latency), configs[3] (fixed 8-source 2048^2 job sharded over the N GPUs: strong scaling),
-              configs[4] (dynamic-geometry frame loop, 8 sources over the N GPUs)
+              configs[4] (dynamic-geometry frame loop, 8 sources over the N GPUs); at N = 1 also configs[3] as ONE
+              batch of 8 on the streamed solver (bounded history, chunks recomputed for the backward pass)
 
 The product arm imports nothing from oracle/ or tests/ except inside verify() and the cpu_baseline leg; every
 PVC_* environment variable is removed at start-up (the release library reads none anyway).
@@ -316,6 +317,45 @@ def extra_config4(pvcuda, sharding, device, rank, world, dist, tdev):
             "outputs_checksum": float(np.nan_to_num(allout.astype(np.float64)).sum())}
 
 
+def extra_config4_streamed(pvcuda, device, strong):
+    """BASELINE configs[3] on ONE GPU as ONE batch: the streamed solver (pvc_create_streamed) keeps an 800-sample pressure
+    history instead of 4000 (14 GB per source instead of 71), solves the response in 5 chunks and recomputes 4 of them for the
+    backward Schroeder pass -- all eight sources fit the device at once.  Same job, listeners and emitters as config4_strong:
+    the output checksums must be equal (the two paths are bit-identical, tests/test_gpu_streamed.py)."""
+    cfg = dict(scene="HugeRoom", n=2048, T=4000, sources=8, resolution=275)
+    history = 800
+    need = pvcuda.memory_requirement(cfg["n"], cfg["n"], cfg["T"], cfg["sources"], history_steps=history)
+    free, _ = pvcuda.device_memory(device)
+    if need > 0.95 * free:
+        return {"skipped": f"needs {need / 1e9:.0f} GB of device memory, {free / 1e9:.0f} GB free"}
+    size, scale, boxes = scene_inputs(cfg)
+    listeners = [((5.0 + 1.5 * i) * scale, 0.0, (4.0 + 0.75 * i) * scale) for i in range(cfg["sources"])]
+    emitters = [(x * scale, 0.0, z * scale) for (x, z) in EMITTERS]
+    sc = pvcuda.Scene(size, size, 275, T=cfg["T"], max_sources=cfg["sources"], device=device, efree=EFREE_275, history_steps=history)
+    for b in boxes:
+        sc.add_aabb(*b)
+    sc.flush_geometry()
+    buf = pvcuda.pinned_array((cfg["sources"], len(emitters), 8))
+    best = None
+    for it in range(2):
+        t0 = time.perf_counter()
+        sc.solve_async(listeners)
+        sc.lookup_wait(sc.lookup_async(emitters, buf, n=cfg["sources"]))
+        sc.wait()
+        secs = time.perf_counter() - t0
+        if it:
+            best = secs
+    launches = sc.timing()[3]
+    variant = sc.step_variant()
+    sc.close()
+    units = cfg["n"] * cfg["n"] * cfg["T"] * cfg["sources"]
+    checksum = float(np.nan_to_num(np.array(buf, copy=True).astype(np.float64)).sum())
+    return {"workload": workload_text(cfg, "in all") + f", one GPU, ONE batch of 8 on the streamed solver (history {history} samples, 5 chunks)",
+            "job_ms": best * 1e3, "Mcell_updates_per_s": units / best / 1e6, "kernel_launches": launches, "step_kernel_variant": variant,
+            "device_memory_GB": need / 1e9, "full_history_GB": pvcuda.memory_requirement(cfg["n"], cfg["n"], cfg["T"], cfg["sources"]) / 1e9,
+            "outputs_checksum": checksum, "checksum_equals_config4_strong": bool(checksum == strong.get("outputs_checksum"))}
+
+
 def extra_config5(pvcuda, sharding, device, rank, world, dist, tdev, frames=12):
     """BASELINE configs[4]: FloorPlanScene.pv on 1024 x 1024 with one AABB moved every frame (UpdateGeometry = Remove(old) +
     Add(new), re-voxelised on the device), 8 listener positions sharded over the N GPUs, contract response length (435 steps);
@@ -525,6 +565,8 @@ def main():
         if rank == 0:
             extras.update(extra_latency(pvcuda, device))
         extras["config4_strong"] = extra_config4(pvcuda, sharding, device, rank, world, dist, tdev)
+        if world == 1:
+            extras["config4_streamed"] = extra_config4_streamed(pvcuda, device, extras["config4_strong"])
         extras["config5_dynamic"] = extra_config5(pvcuda, sharding, device, rank, world, dist, tdev)
 
     rc = 0

@@ -31,9 +31,12 @@ typedef struct pvx_scene pvx_scene;
 PVC_API int  pvx_create(float sizeX, float sizeY, int resolution, int responseLength, float efree,
                         int maxSources, int device, int stepKernel, int variant, pvx_scene** out);
 /* the same scene on a streamed solver (pvc_create_streamed): the pressure history holds historySteps samples and the response is
- * solved in chunks, for grids / response lengths whose full history does not fit the device.  historySteps <= 0: pvx_create. */
+ * solved in chunks, for grids / response lengths whose full history does not fit the device.  historySteps == 0: pvx_create;
+ * historySteps < 0: automatic -- the full history if it fits 90 % of the device's free memory, else the longest that does. */
 PVC_API int  pvx_create_streamed(float sizeX, float sizeY, int resolution, int responseLength, float efree,
                                  int maxSources, int device, int stepKernel, int variant, int historySteps, pvx_scene** out);
+/* samples the scene's history holds: 0 = the whole response (full-history solver), > 0 = streamed solver */
+PVC_API int  pvx_history_steps(pvx_scene* sc);
 PVC_API void pvx_destroy(pvx_scene* sc);
 
 /* ints[10] = gx, gy, T, fs, fluxSamples, drySamples, wetSamples, tailSamples, freeSamples, maxSources

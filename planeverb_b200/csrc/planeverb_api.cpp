@@ -221,8 +221,10 @@ namespace Planeverb
         ctx->params = pvhost::derive(config->gridResolution, config->gridSizeInMeters.x, config->gridSizeInMeters.y);
         int device = 0;
         if (const char* env = std::getenv("PLANEVERB_CUDA_DEVICE")) device = std::atoi(env);
-        const int rc = pvx_create(config->gridSizeInMeters.x, config->gridSizeInMeters.y, config->gridResolution,
-                                  0, -1.f, 1, device, 0, 0, &ctx->scene);
+        // history length automatic (-1): a grid whose full pressure history does not fit the device runs on the streamed solver
+        // instead of failing with pv_NotEnoughMemory (only GetImpulseResponse is unavailable then)
+        const int rc = pvx_create_streamed(config->gridSizeInMeters.x, config->gridSizeInMeters.y, config->gridResolution,
+                                           0, -1.f, 1, device, 0, 0, -1, &ctx->scene);
         if (rc != PVC_OK)
         {
             setLastError(std::string("Init: ") + pvc_last_error());

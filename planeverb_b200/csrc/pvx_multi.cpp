@@ -79,7 +79,8 @@ int pvx_create_multi(const int* devices, int n_devices, float sizeX, float sizeY
             }
         }
         pvx_scene* sc = nullptr;
-        rc = pvx_create(sizeX, sizeY, resolution, responseLength, efree, batch, devices[k], 0, 0, &sc);
+        // history length automatic: a batch of one whose full history does not fit the device still runs, streamed
+        rc = pvx_create_streamed(sizeX, sizeY, resolution, responseLength, efree, batch, devices[k], 0, 0, -1, &sc);
         if (rc) break;
         m->scenes.push_back(sc);
         m->batch.push_back(batch);

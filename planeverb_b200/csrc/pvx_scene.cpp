@@ -3,6 +3,7 @@
 // index/scalar derivation done here on the host (pv_params.h) and all field work done on the device.
 // Entry points are declared in include/planeverb_ext.h.  There is no CPU solve path in this file: if
 // the device layer fails, the error is returned to the caller.
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -19,7 +20,32 @@ struct pvx_scene
     float efree = 0.f;
     int maxSources = 1;
     int lastSources = 0;
+    int historySteps = 0;              // > 0: streamed solver with a history of this many samples
 };
+
+namespace
+{
+    // historySteps < 0: the full history if it fits 90 % of the device's free memory, else the longest history (a multiple of 8
+    // samples) that does -- a streamed solver, same results at up to twice the time steps (pvc_create_streamed)
+    int autoHistory(const pvc_config& cfg, int freeSamples)
+    {
+        size_t freeB = 0, totalB = 0;
+        if (pvc_device_memory(cfg.device, &freeB, &totalB) != PVC_OK) return 0;
+        const size_t budget = (size_t)(0.9 * (double)freeB);
+        const size_t full = pvc_memory_requirement(&cfg);
+        if (full && full <= budget) return 0;
+        const int floor8 = std::max(64, (freeSamples + 7) / 8 * 8);
+        int lo = floor8, hi = cfg.T / 8 * 8;                    // the requirement grows with the history length: bisect
+        if (hi <= lo) return lo;
+        if (pvc_memory_requirement_streamed(&cfg, lo) > budget) return lo;      // will fail with PVC_ERR_MEMORY, as it should
+        while (hi - lo > 8)
+        {
+            const int mid = (lo + (hi - lo) / 2) / 8 * 8;
+            if (pvc_memory_requirement_streamed(&cfg, mid) <= budget) lo = mid; else hi = mid;
+        }
+        return lo;
+    }
+}
 
 extern "C" {
 
@@ -43,6 +69,8 @@ int pvx_create_streamed(float sizeX, float sizeY, int resolution, int responseLe
     if (g.gx < 2 || g.gy < 2) { delete sc; return PVC_ERR_INVALID; }
     pvc_config cfg = pvhost::configFor(g, maxSources, device, stepKernel);
     cfg.reserved = variant;
+    if (historySteps < 0) historySteps = autoHistory(cfg, g.freeSamples);
+    sc->historySteps = historySteps;
     int rc = historySteps > 0 ? pvc_create_streamed(&cfg, historySteps, &sc->solver) : pvc_create(&cfg, &sc->solver);
     if (rc) { delete sc; return rc; }
     pvhost::gaussianPulse(resolution, g.fs, sc->pulse, g.T);
@@ -61,6 +89,8 @@ int pvx_create_streamed(float sizeX, float sizeY, int resolution, int responseLe
     *out = sc;
     return PVC_OK;
 }
+
+int pvx_history_steps(pvx_scene* sc) { return sc ? sc->historySteps : -1; }
 
 void pvx_destroy(pvx_scene* sc)
 {

@@ -31,7 +31,7 @@ PVC_SYMBOLS = [
     "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_set_walk_mode", "pvc_step_variant",
 ]
 PVX_SYMBOLS = [
-    "pvx_create", "pvx_create_streamed", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
+    "pvx_create", "pvx_create_streamed", "pvx_history_steps", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",
     "pvx_flush_geometry", "pvx_solve", "pvx_solve_async", "pvx_wait", "pvx_solve_pipelined", "pvx_fetch_wait", "pvx_lookup", "pvx_lookup_async", "pvx_lookup_wait",
     "pvx_impulse_response", "pvx_solver",
     "pvx_create_multi", "pvx_destroy_multi", "pvx_multi_devices", "pvx_multi_scene", "pvx_multi_batch", "pvx_multi_add_aabb",
@@ -94,6 +94,7 @@ def lib():
         L.pvx_create.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _vp]
         L.pvx_create_streamed.argtypes = [_f, _f, _i, _i, _f, _i, _i, _i, _i, _i, _vp]
         L.pvx_destroy.argtypes = [_vp]
+        L.pvx_history_steps.argtypes = [_vp]
         L.pvx_info.argtypes = [_vp, _vp, _vp]
         L.pvx_pulse.argtypes = [_vp, _vp, _i]
         L.pvx_add_aabb.argtypes = [_vp] + [_f] * 5
@@ -244,7 +245,6 @@ class Scene:
         h = _vp()
         _check(lib().pvx_create_streamed(size_x, size_y, int(resolution), int(T), float(efree), int(max_sources),
                                          int(device), int(step_kernel), int(variant), int(history_steps), C.byref(h)), "pvx_create")
-        self.history_steps = int(history_steps)
         self._h = h
         ii = np.zeros(10, np.int32)
         ff = np.zeros(4, np.float32)
@@ -255,6 +255,7 @@ class Scene:
         self.resolution = int(resolution)
         self.size_x, self.size_y = float(size_x), float(size_y)
         self._solver = lib().pvx_solver(self._h)
+        self.history_steps = int(lib().pvx_history_steps(self._h))      # 0: full history; > 0: streamed solver
 
     def close(self):
         if getattr(self, "_h", None):

@@ -147,3 +147,31 @@ def test_config4_eight_sources_as_one_streamed_batch(pv, scenes):
         assert (df < 3e38).sum() > 1000000
     full.close()
     print(f"config 4 on one GPU: streamed batch of 8 (history 800) {tot:.1f} ms, {launches} launches; four full-history batches of 2: {ms_full:.1f} ms")
+
+
+def test_automatic_history_length_falls_back_to_a_streamed_solver(pv, scenes):
+    """history_steps = -1 (what Planeverb::Init and pvx_create_multi pass): the full history when it fits 90 % of the device's free
+    memory, else the longest history that does.  Three 2048 x 2048 x 4000 sources need 214 GB of history: a streamed solver."""
+    size, scale = common.scaled_config(2048)
+    boxes = common.boxes_of(scenes, "HugeRoom", scale)
+    listeners = common.listeners_for(3, scale)
+    small = pv.Scene(25.0, 25.0, 275, history_steps=-1)
+    assert small.history_steps == 0                          # fits: the ordinary solver
+    small.close()
+    free, _ = pv.device_memory(0)
+    if pv.memory_requirement(2048, 2048, 4000, 3) <= 0.9 * free:
+        pytest.skip("three full 2048^2 histories fit this device")
+    auto = pv.Scene(size, size, 275, T=4000, max_sources=3, history_steps=-1)
+    assert 0 < auto.history_steps < 4000 and auto.history_steps % 8 == 0
+    assert pv.memory_requirement(2048, 2048, 4000, 3, history_steps=auto.history_steps) <= 0.9 * free
+    for b in boxes:
+        auto.add_aabb(*b)
+    ra, da = auto.solve(listeners)
+    efree = float(auto.efree)
+    auto.close()
+    full = pv.Scene(size, size, 275, T=4000, max_sources=1, efree=efree)
+    for b in boxes:
+        full.add_aabb(*b)
+    rf, df = full.solve(listeners[2:3])
+    assert np.array_equal(df[0], da[2]) and same_bits(rf[0], ra[2])
+    full.close()

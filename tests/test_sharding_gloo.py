@@ -116,6 +116,22 @@ def test_batch_size_from_the_memory_requirement():
     assert pvcuda.memory_requirement(1, 1, 10, 1) == 0                      # invalid config
 
 
+def test_streamed_solver_memory_requirement():
+    """pvc_memory_requirement_streamed (host arithmetic): the history shrinks with history_steps, the carry planes and the K - 2
+    state checkpoints are small beside it -- all eight 2048^2 x 4000-step sources of BASELINE configs[3] fit ONE B200 with an
+    800-sample history, and a 4096^2 source (268 GB of full history) fits with 1600."""
+    from planeverb_b200 import pvcuda
+    full = pvcuda.memory_requirement(2048, 2048, 4000, 8)
+    assert full > 560e9
+    need = [pvcuda.memory_requirement(2048, 2048, 4000, 8, history_steps=h) for h in (400, 800, 1000, 2000, 4000)]
+    assert all(a < b for a, b in zip(need, need[1:]))
+    assert need[1] < 0.9 * 178e9 < need[3]
+    assert need[4] > full                                               # one chunk: the full history plus the carry planes
+    assert pvcuda.memory_requirement(2048, 2048, 4000, 8, history_steps=803) == need[1]      # rounded down to a multiple of 8
+    assert pvcuda.memory_requirement(4096, 4096, 4000, 1) > 250e9
+    assert pvcuda.memory_requirement(4096, 4096, 4000, 1, history_steps=1600) < 0.9 * 178e9
+
+
 def _batched_worker(rank, world, port, listeners, max_batch, q):
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)

@@ -105,9 +105,11 @@ namespace pvc
     //   * a 33-entry table indexed by (bits(m) - 0x3f330000) >> 19 (arithmetic, -7..25) that holds, per logf interval AND
     //     exponent k in {-1, 0, 1}, { invc * 2^-k, logc + k*ln2 } (buildLogfTable33: the reference's own y0 = logc + k*ln2,
     //     one rounding, and an exact power-of-two scaling), so neither the reduced mantissa z = m * 2^-k nor k is formed;
-    //   * r = fma(m, invc', -1) and the polynomial in FMA form: 6 double-precision instructions instead of 11.  The fused
-    //     roundings differ from e_logf.c's separate ones only far below the final rounding to float -- on no input at all
-    //     (glibc's own __logf_fma variant, which FMA-capable x86-64 hosts run, contracts the same expressions);
+    //   * r = fma(m, invc', -1) and the whole of logc + r + r^2 (A2 + A1 r + A0 r^2) as ONE Horner chain in r,
+    //     y = fma(fma(fma(fma(A0, r, A1), r, A2), r, 1), r, logc'): 5 double-precision instructions instead of e_logf.c's 11 (the
+    //     Estrin-like form of e_logf.c in FMAs, which glibc's own __logf_fma variant runs on FMA-capable x86-64 hosts, needs 6).
+    //     The roundings differ from e_logf.c's only far below the final rounding to float -- on no input at all, which is not
+    //     argued but checked on every one of the 2^24 inputs;
     //   * float -> double of m by integer ops (exact for normal floats).
     __device__ __forceinline__ bool isNormalPositive(float e)
     {
@@ -147,10 +149,10 @@ namespace pvc
         const LogfEntry en = tab33[idx];
         const double md = __hiloint2double((int)((hm >> 3) + 0x38000000u), (int)(hm << 29));
         const double r = __fma_rn(md, en.invc, -1.0);
-        const double r2 = __dmul_rn(r, r);
-        double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
-        y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
-        y = __fma_rn(y, r2, __dadd_rn(en.logc, r));
+        double q = __fma_rn(-0x1.00ea348b88334p-2, r, 0x1.5575b0be00b6ap-2);
+        q = __fma_rn(q, r, -0x1.ffffef20a4123p-2);
+        q = __fma_rn(q, r, 1.0);
+        const double y = __fma_rn(q, r, en.logc);
         const float lf = (float)y;
         const float zz = __fadd_rn(ex.x, __fmul_rn(4.3429449201e-01f, lf));
         return __fmul_rn(10.f, __fadd_rn(zz, ex.y));

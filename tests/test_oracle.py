@@ -222,13 +222,18 @@ def test_device_logf_fma_form_is_exhaustively_exact(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, csrc, "-lm"])
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "inputs 16777216  a!=b 0  a!=libm 0  b!=libm 0  device!=libm 0" in p.stdout
+    assert "inputs 16777216  a!=b 0  a!=libm 0  b!=libm 0  device!=libm 0  horner!=libm 0" in p.stdout
     # the C restatement and the CUDA source use the same constants and the same table indexing
     cu = open(os.path.join(common.ROOT, "planeverb_b200", "csrc", "pvc_analyze.cu")).read()
     c = open(csrc).read()
     for const in re.findall(r"-?0x1\.[0-9a-f]+p[+-]\d+", c):
         assert const in cu, const
     assert "0x3f330000u) >> 19) + kLogf33Bias" in cu and "kLogf33Bias = 7" in cu and ">> 19) + 7" in c
+    # ... and the device evaluates the Horner chain the harness calls (d): A0, A1, A2, 1, logc in that order
+    body = cu[cu.index("decibelsNormal(float e"):]
+    body = body[:body.index("#endif")]
+    order = [body.index(t) for t in ("-0x1.00ea348b88334p-2, r, 0x1.5575b0be00b6ap-2", "q, r, -0x1.ffffef20a4123p-2", "q, r, 1.0", "q, r, en.logc")]
+    assert order == sorted(order)
 
 
 def test_reference_dsp_consumer_accepts_the_golden_outputs():

@@ -3,8 +3,10 @@
  * m * 2^k with m in [0.5, 2)).  Three forms are compared on all 2^24 inputs:
  *   (a) glibc 2.39 e_logf.c as written, separate multiply / add roundings (what an x86-64 build without FMA executes)
  *   (b) the same with every a*b+c contracted to fma (what glibc's __logf_fma ifunc variant executes on FMA-capable CPUs)
- *   (c) the device form: 33-entry table indexed by (ix - OFF) >> 19 holding { invc * 2^-k, logc + k*ln2 }, so that
- *       r = fma(m, invc', -1) needs neither the reduced mantissa z nor the k*ln2 term; polynomial in Horner/FMA form
+ *   (c) the device form of round 1: 33-entry table indexed by (ix - OFF) >> 19 holding { invc * 2^-k, logc + k*ln2 }, so that
+ *       r = fma(m, invc', -1) needs neither the reduced mantissa z nor the k*ln2 term; e_logf.c's polynomial in FMA form (6 DP ops)
+ *   (d) the device form now: the same table and r, and y = logc' + r + r^2 (A2 + A1 r + A0 r^2) as one Horner chain in r,
+ *       fma(fma(fma(fma(A0, r, A1), r, A2), r, 1), r, logc') (5 DP ops)
  * Build + run:  gcc -O2 -ffp-contract=off -o logf_fma_recipe logf_fma_recipe.c -lm && ./logf_fma_recipe
  * (tests/test_oracle.py::test_device_logf_fma_form_is_exhaustively_exact runs it.)                                            */
 #include <math.h>
@@ -65,16 +67,28 @@ static float logf_device(float m)
     return (float)y;
 }
 
+static float logf_device_horner(float m)
+{
+    uint32_t ix = f2u(m);
+    int idx = ((int32_t)(ix - 0x3f330000u) >> 19) + 7;
+    double md = (double)m, r = fma(md, tab33[idx].invc, -1.0);
+    double q = fma(A0, r, A1);
+    q = fma(q, r, A2);
+    q = fma(q, r, 1.0);
+    return (float)fma(q, r, tab33[idx].logc);
+}
+
 int main(void)
 {
-    long ab = 0, a_l = 0, b_l = 0, c_l = 0, n = 0;
+    long ab = 0, a_l = 0, b_l = 0, c_l = 0, d_l = 0, n = 0;
     build33();
     for (uint32_t u = 0x3f000000u; u < 0x40000000u; ++u, ++n)
     {
-        const float x = u2f(u), a = logf_glibc(x, 0), b = logf_glibc(x, 1), c = logf_device(x), ref = logf(x);
+        const float x = u2f(u), a = logf_glibc(x, 0), b = logf_glibc(x, 1), c = logf_device(x), d = logf_device_horner(x), ref = logf(x);
         ab += f2u(a) != f2u(b); a_l += f2u(a) != f2u(ref); b_l += f2u(b) != f2u(ref);
         c_l += f2u(c) != f2u(ref) && !(u == 0x3f800000u && c == 0.f && ref == 0.f);
+        d_l += f2u(d) != f2u(ref) && !(u == 0x3f800000u && d == 0.f && ref == 0.f);
     }
-    printf("inputs %ld  a!=b %ld  a!=libm %ld  b!=libm %ld  device!=libm %ld\n", n, ab, a_l, b_l, c_l);
-    return (ab | a_l | b_l | c_l) ? 1 : 0;
+    printf("inputs %ld  a!=b %ld  a!=libm %ld  b!=libm %ld  device!=libm %ld  horner!=libm %ld\n", n, ab, a_l, b_l, c_l, d_l);
+    return (ab | a_l | b_l | c_l | d_l) ? 1 : 0;
 }

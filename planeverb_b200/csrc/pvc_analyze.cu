@@ -435,7 +435,7 @@ namespace pvc
     template <int HC>
     __global__ void __launch_bounds__(128)
     forwardChunkKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
-                       float* __restrict__ carry, size_t cstride, int base, int len)
+                       float* __restrict__ carry, size_t cstride, int base, int len, const int* __restrict__ firstActive)
     {
         const int c = blockIdx.x * HC + threadIdx.x;
         const int r = blockIdx.y;
@@ -453,9 +453,28 @@ namespace pvc
         const float* H = hist + (size_t)s * L.hist_source + histCell(L, r, c) - (ptrdiff_t)base * HC;     // sample t at H[t * HC]
         constexpr ptrdiff_t hs = HC;
         constexpr int kBatch = 16;
+        // activity hints of THIS chunk's step launch (generations counted from the chunk's first sample): everything this cell,
+        // its up and its left neighbour recorded before them is exactly zero -- no onset there, every sum unchanged, the rebuilt
+        // velocities unchanged up to the sign of a zero that only ever multiplies those zero pressures
+        int onsetBegin = base, causalBegin = base;
+        if (firstActive)
+        {
+            const int* fa = firstActive + (size_t)s * L.tiles_x * L.tiles_y * 32;
+            auto blockFirst = [&](int rr, int cc) {
+                const int ty = rr / L.valid_rows, tx = cc / kValidCols;
+                const int wIdx = (rr - ty * L.valid_rows + kTileK) / L.warp_rows;
+                const int g = fa[((size_t)ty * L.tiles_x + tx) * 32 + wIdx];
+                return g >= kNeverActive ? len : min(g * kTileK, len);
+            };
+            const int mine = blockFirst(r, c);
+            const int up = (r > 0) ? blockFirst(r - 1, c) : mine, left = (c > 0) ? blockFirst(r, c - 1) : mine;
+            onsetBegin = base + mine;
+            causalBegin = base + min(mine, min(up, left));
+            if (causalBegin >= end) return;                  // nothing but zeros in this chunk (then there is no onset behind it either)
+        }
         if (onset < 0)
         {   // Analyzer.cpp:146-154, continued where the previous chunk stopped
-            for (int t0 = base; t0 < end && onset < 0; t0 += kBatch)
+            for (int t0 = onsetBegin; t0 < end && onset < 0; t0 += kBatch)
             {
                 float v[kBatch];
                 #pragma unroll
@@ -480,7 +499,7 @@ namespace pvc
             const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
             const ptrdiff_t leftOff = leftEdge ? 0 : (((c % HC) != 0) ? -1 : -(ptrdiff_t)L.T * hs + (hs - 1));
             constexpr int kCausalBatch = 4;
-            for (int t0 = base; t0 < fluxEnd; t0 += kCausalBatch)
+            for (int t0 = causalBegin; t0 < fluxEnd; t0 += kCausalBatch)
             {
                 float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
                 #pragma unroll
@@ -976,7 +995,8 @@ namespace pvc
         const Layout& L = s->L;
         const AnalyzeParams A = paramsOf(s);
         const dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);
-        forwardChunkKernel<kHistChunkDefault><<<stripGrid, 128, 0, s->stream>>>(L, A, s->hist, s->w, s->carry, (size_t)s->cfg.max_sources * L.gx * L.gy, base, len);
+        forwardChunkKernel<kHistChunkDefault><<<stripGrid, 128, 0, s->stream>>>(L, A, s->hist, s->w, s->carry, (size_t)s->cfg.max_sources * L.gx * L.gy, base, len,
+                                                                               s->hintsValid ? s->firstActive : nullptr);
         *launches += 1;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("streamed analyzer (forward) launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }

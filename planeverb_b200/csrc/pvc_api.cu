@@ -316,13 +316,20 @@ namespace pvc
             if (s->cur != 0) { setError("streamed solve: chunk %d does not start on ping-pong buffer 0", k); return PVC_ERR_CUDA; }
             if (analyze && k >= 1 && k <= K - 2) { float* q[3]; slot(k, q); int rc = copyState(q, s->state[0]); if (rc) return rc; }
             s->finalPass = (k == K - 1);
+            s->abortSticky = (k > 0);
+            // activity hints of this chunk (first generation, counted from the chunk's start, in which a warp's block recorded
+            // anything but zeros): the forward analysis skips the exact zeros in front of the wave
+            s->hintsValid = analyze ? 1 : 0;
+            if (s->hintsValid)
+                PVC_CUDA(cudaMemsetAsync(s->firstActive, 0x7f, sizeof(int) * (size_t)nsrc * L.tiles_x * L.tiles_y * 32, s->stream));
             int rc = launchFusedSteps(s, nsrc, base, end, s->hist, launches);
             if (!rc && analyze) rc = launchStreamForward(s, nsrc, base, end - base, launches);
+            s->hintsValid = 0;
             if (rc) return rc;
         }
         s->stateStale = 0;
         s->lastStepLaunches = *launches;
-        if (!analyze) return PVC_OK;
+        if (!analyze) { s->abortSticky = 0; return PVC_OK; }
         // a pipelined fetch of the previous run's grids must finish before the results are overwritten
         if (s->copyPending) PVC_CUDA(cudaStreamWaitEvent(s->stream, s->evCopied, 0));
         int rc = launchStreamBackward(s, nsrc, (K - 1) * C, T - (K - 1) * C, launches);
@@ -338,6 +345,7 @@ namespace pvc
             if (rc) return rc;
         }
         s->finalPass = 1;
+        s->abortSticky = 0;
         return launchListenerDirection(s, nsrc, launches);
     }
 }
@@ -655,6 +663,7 @@ int pvc_run(pvc_solver* s, const pvc_listener* listeners, int n, int analyze)
         // meaningful: everything is reported as step time)
         s->hintsValid = 0;
         rc = runStreamed(s, n, analyze, &launches);
+        s->abortSticky = 0; s->finalPass = 1;          // also after a failed sweep
         if (rc) return rc;
         PVC_CUDA(cudaEventRecord(s->ev[1], s->stream));
         PVC_CUDA(cudaEventRecord(s->ev[2], s->stream));

@@ -157,6 +157,7 @@ struct pvc_solver
     int chunkT;              // samples of history kept (0: the whole response, L.T == cfg.T); L.T == chunkT otherwise
     int finalPass;           // the chunk being stepped ends the response
     int stateStale;          // the state planes hold the end of chunk 0, not of the response (after the backward sweep)
+    int abortSticky;         // step launches leave the abort flag alone (every chunk of a streamed solve but the first)
     float* ckpt;             // state at the start of chunks 1 .. K-2: [K-2][3 fields][max_sources * plane]
     float* carry;            // analyzer state carried across chunks: [pvc::kCarryPlanes][max_sources * gx*gy]
 };

@@ -1262,7 +1262,11 @@ namespace pvc
             const int gens = (t1 - t0 + kTileK - 1) / kTileK;
             const int perLaunch = 256;                                             // generations per launch (bounds kernel time)
             cudaMemsetAsync(s->doneGen, 0, sizeof(int) * (size_t)numTiles, s->stream);
-            cudaMemsetAsync(s->tileCounters, 0, sizeof(int) * (size_t)((gens + perLaunch - 1) / perLaunch + 1), s->stream);
+            {   // slot 0 is the abort flag: a streamed solve clears it with its first chunk only, so that a time-out in any chunk is still there
+                // when the host looks (after the last one)
+                const int keep = s->abortSticky ? 1 : 0;
+                cudaMemsetAsync(s->tileCounters + keep, 0, sizeof(int) * (size_t)((gens + perLaunch - 1) / perLaunch + 1 - keep), s->stream);
+            }
             Args A;
             A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
@@ -1272,7 +1276,7 @@ namespace pvc
 #endif
             if (TS || SO) { rc = buildStoreMaps(s, TS ? A.hist : nullptr, (NW - 2) * R, maps.store, &maps.hist); if (rc) return rc; }
             A.mode = s->slowMask; A.bpMask = s->bpMask; A.tileOrder = s->tileOrderNatural ? nullptr : s->tileOrder;
-            A.firstActive = s->chunkT ? nullptr : s->firstActive;                   // activity hints count generations from sample 0
+            A.firstActive = (s->chunkT && !s->hintsValid) ? nullptr : s->firstActive;   // streamed solve: hints per chunk, forward sweep only
             A.src = s->src; A.pulse = s->pulse + t0; A.finalPass = s->chunkT ? s->finalPass : 1;
             A.doneGen = s->doneGen; A.abortFlag = s->tileCounters;                  // slot 0 of the pool is the abort flag
             A.tilesPerSource = L.tiles_x * L.tiles_y; A.nsrc = nsrc; A.numTiles = numTiles;

@@ -126,8 +126,8 @@ namespace pvc
         return o;
     }
     // Per-exponent part of fdlibm's log10f for a normal float with exponent field E = 1..254: k = E - 127, i = (k < 0),
-    // K = k + i, and the two products that depend on K alone, y*log10_2lo and y*log10_2hi with y = (float)K; z holds K << 23,
-    // so that the mantissa re-biased to [0.5, 2) is bits(e) - z.  One 16-byte shared-memory load (neighbouring cells have
+    // K = k + i, and the two products that depend on K alone, y*log10_2lo and y*log10_2hi with y = (float)K; z and w hold the integer
+    // offsets that turn bits(e) into the logf table index and into the double of the mantissa re-biased to [0.5, 2).  One 16-byte shared-memory load (neighbouring cells have
     // neighbouring energies: mostly a broadcast) replaces 10 integer / conversion / multiply instructions per sample.
     constexpr int kExpEntries = 256;
     __device__ __forceinline__ float4 buildExponentEntry(int E)
@@ -135,7 +135,10 @@ namespace pvc
         const int k = E - 127;
         const int i = (int)((unsigned)k >> 31);
         const float yk = (float)(k + i);
-        return make_float4(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(yk, 3.0102920532e-01f), __int_as_float((k + i) << 23), 0.f);
+        // .z: bits(e) - z = the logf table index << 19 (re-bias by K << 23, the table's origin 0x3f330000 and its bias folded in);
+        // .w: (bits(e) >> 3) + w = high word of the re-biased mantissa m as a double (0x38000000 = the exponent re-bias of float -> double)
+        return make_float4(__fmul_rn(yk, 7.9034151668e-07f), __fmul_rn(yk, 3.0102920532e-01f),
+                           __int_as_float(((k + i) << 23) + 0x3f330000 - (kLogf33Bias << 19)), __int_as_float(0x38000000 - ((k + i) << 20)));
     }
     __device__ __forceinline__ float decibelsNormal(float e, const LogfEntry* __restrict__ tab33, const float4* __restrict__ tabExp)
     {
@@ -144,10 +147,10 @@ namespace pvc
     #else
         const int hx = __float_as_int(e);
         const float4 ex = tabExp[(unsigned)hx >> 23];
-        const uint32_t hm = (uint32_t)(hx - __float_as_int(ex.z));                  // m in [1,2) (e >= 1) or [0.5,1)
-        const int idx = ((int)(hm - 0x3f330000u) >> 19) + kLogf33Bias;
+        // m = e * 2^-K in [1,2) (e >= 1) or [0.5,1) is never formed as a float: its table index and its double come straight from bits(e)
+        const int idx = (hx - __float_as_int(ex.z)) >> 19;                           // == ((bits(m) - 0x3f330000u) >> 19) + kLogf33Bias
         const LogfEntry en = tab33[idx];
-        const double md = __hiloint2double((int)((hm >> 3) + 0x38000000u), (int)(hm << 29));
+        const double md = __hiloint2double((int)(((uint32_t)hx >> 3) + (uint32_t)__float_as_int(ex.w)), (int)((uint32_t)hx << 29));
         const double r = __fma_rn(md, en.invc, -1.0);
         double q = __fma_rn(-0x1.00ea348b88334p-2, r, 0x1.5575b0be00b6ap-2);
         q = __fma_rn(q, r, -0x1.ffffef20a4123p-2);
@@ -965,12 +968,11 @@ namespace pvc
             walkNextKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
             // A pass follows up to kHops further links from every cell, so it multiplies the length every link spans by at
             // least kHops + 1 (in place: a link read here may already be longer); delays are integral sample indices that
-            // strictly decrease along a walk, so no walk is longer than T hops: ceil(log_(kHops+1) T) passes resolve them all,
-            // one more for good measure.  walkResolveKernel still follows whatever is left.
+            // strictly decrease along a walk, so no walk is longer than T hops: ceil(log_(kHops+1) T) passes resolve them all
+            // (walkResolveKernel follows whatever could be left, so the count is a matter of speed, not of correctness).
             constexpr int kHops = 3;
             int rounds = 1;
             for (long span = kHops + 1; span < (long)A.T; span *= kHops + 1) ++rounds;
-            rounds += 1;
             for (int k = 0; k < rounds; ++k)
                 walkJumpKernel<<<dim3((unsigned)((cells + 255) / 256), nsrc), 256, 0, s->stream>>>(cells, kHops, s->walkNext);
             walkResolveKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);

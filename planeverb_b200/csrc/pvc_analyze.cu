@@ -290,10 +290,13 @@ namespace pvc
                 }
             }
             const float* q = H + (ptrdiff_t)fluxEnd * hs;
-            for (int t = fluxEnd; t < dryEnd; ++t, q += hs)
+            for (int t = fluxEnd; t < dryEnd; t += kBatch, q += kBatch * hs)
             {
-                const float p = __ldg(q);
-                edry = __fadd_rn(edry, __fmul_rn(p, p));
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldg(q + min(u, dryEnd - 1 - t) * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) if (t + u < dryEnd) edry = __fadd_rn(edry, __fmul_rn(v[u], v[u]));
             }
         }
 
@@ -323,11 +326,22 @@ namespace pvc
         {
             const int end = min(directEnd + 1 + A.wetSamples, T);
             const float* q = H + (ptrdiff_t)(directEnd + 1) * hs;
-            #pragma unroll 4
-            for (int j = directEnd + 1; j < end; ++j, q += hs)
+            int j = directEnd + 1;
+            for (; j + kBatch <= end; j += kBatch, q += kBatch * hs)        // kBatch loads in flight: on small grids a dependent load per few samples IS the frame time
             {
-                const float p = __ldg(q);
-                wet = __fadd_rn(wet, __fmul_rn(p, p));
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldg(q + u * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) wet = __fadd_rn(wet, __fmul_rn(v[u], v[u]));
+            }
+            if (j < end)
+            {
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldg(q + min(u, end - 1 - j) * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) if (j + u < end) wet = __fadd_rn(wet, __fmul_rn(v[u], v[u]));
             }
         }
         const float wetGain = __fsqrt_rn(__fdiv_rn(wet, A.efree));
@@ -355,10 +369,13 @@ namespace pvc
                 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
             }
-            for (; i >= stop; --i, q -= hs)
-            {
-                const float p = __ldcs(q);
-                edc = __fadd_rn(edc, __fmul_rn(p, p));
+            if (i >= stop)
+            {   // the last, partial batch: its loads in flight together as well (clamped into the range, extra ones unused)
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - min(u, i - stop) * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) if (i - u >= stop) edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
             }
         }
         if (endPoint - 1 >= start)
@@ -402,14 +419,21 @@ namespace pvc
                     x = __fsub_rn(x, 1.0f);
                 }
             }
-            for (; i >= start; --i, q -= hs)
-            {
-                const float p = __ldcs(q);
-                edc = __fadd_rn(edc, __fmul_rn(p, p));
-                const float y = decibels(edc, sTab);
-                xysum = __fadd_rn(xysum, __fmul_rn(y, x));
-                ysum = __fadd_rn(ysum, y);
-                x = __fsub_rn(x, 1.0f);
+            if (i >= start)
+            {   // the last, partial batch
+                float v[kBatch];
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u) v[u] = __ldcs(q - min(u, i - start) * hs);
+                #pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if (i - u >= start)
+                    {
+                        edc = __fadd_rn(edc, __fmul_rn(v[u], v[u]));
+                        const float y = decibels(edc, sTab);
+                        xysum = __fadd_rn(xysum, __fmul_rn(y, x));
+                        ysum = __fadd_rn(ysum, y);
+                        x = __fsub_rn(x, 1.0f);
+                    }
             }
         }
         const float ymean = __fdiv_rn(ysum, rn);
@@ -757,6 +781,28 @@ namespace pvc
         return fabsf(__fsub_rn(geodesic, eu)) < K.thresholdDist;
     }
 
+    // link of cell u = (r, c): the cell a walk standing on u ends on without another move (kWalkDone set) or moves to
+    __device__ __forceinline__ int walkLink(const AnalyzeParams& A, const SourceParams& sp, const float* __restrict__ res, const float* __restrict__ wd,
+                                            int r, int c, int gx, int gy)
+    {
+        const int u = r * gy + c;
+        const float d = wd[u];
+        int out = u | kWalkDone;
+        if (d != FLT_MAX)                    // cells no walk can stand on keep a harmless self link
+        {
+            const WalkConsts K = walkConsts(A);
+            const float loud = res[(size_t)u * 8];
+            const bool goOn = (d > kDelayClose && loud < kGainThreshold) && !walkLineOfSight(A, K, sp, r, c, d);
+            if (goOn)
+            {
+                float best;
+                const int v = walkArgmin(wd, r, c, gx, gy, best);
+                if (v >= 0) out = (best >= d) ? (v | kWalkDone) : v;
+            }
+        }
+        return out;
+    }
+
     __global__ void __launch_bounds__(128)
     walkNextKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, const float* __restrict__ results,
                    const float* __restrict__ walkDelay, int* __restrict__ next)
@@ -765,25 +811,8 @@ namespace pvc
         const int r = blockIdx.y;
         const int s = blockIdx.z;
         if (c >= L.gy) return;
-        const int gx = L.gx, gy = L.gy;
-        const size_t cells = (size_t)gx * gy;
-        const float* wd = walkDelay + (size_t)s * cells;
-        const int u = r * gy + c;
-        const float d = wd[u];
-        int out = u | kWalkDone;
-        if (d != FLT_MAX)                    // cells no walk can stand on keep a harmless self link
-        {
-            const WalkConsts K = walkConsts(A);
-            const float loud = results[((size_t)s * cells + u) * 8];
-            const bool goOn = (d > kDelayClose && loud < kGainThreshold) && !walkLineOfSight(A, K, src[s], r, c, d);
-            if (goOn)
-            {
-                float best;
-                const int v = walkArgmin(wd, r, c, gx, gy, best);
-                if (v >= 0) out = (best >= d) ? (v | kWalkDone) : v;
-            }
-        }
-        next[(size_t)s * cells + u] = out;
+        const size_t cells = (size_t)L.gx * L.gy;
+        next[(size_t)s * cells + (size_t)r * L.gy + c] = walkLink(A, src[s], results + (size_t)s * cells * 8, walkDelay + (size_t)s * cells, r, c, L.gx, L.gy);
     }
 
     __global__ void __launch_bounds__(256)
@@ -800,20 +829,10 @@ namespace pvc
         next[u] = n;
     }
 
-    __global__ void __launch_bounds__(128)
-    walkResolveKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, float* __restrict__ results,
-                      const float* __restrict__ walkDelay, const int* __restrict__ nextAll)
+    // the walk from start cell (r0, c0) through the shortened links, and the direction it yields (Analyzer.cpp:357-386, 409-431)
+    __device__ __forceinline__ void walkResolve(const AnalyzeParams& A, const SourceParams& sp, float* __restrict__ res, const float* __restrict__ wd,
+                                                const int* next, int r0, int c0, int gx, int gy)
     {
-        const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
-        const int r0 = blockIdx.y;
-        const int s = blockIdx.z;
-        if (c0 >= L.gy) return;
-        const int gx = L.gx, gy = L.gy;
-        const size_t cells = (size_t)gx * gy;
-        float* res = results + (size_t)s * cells * 8;
-        const float* wd = walkDelay + (size_t)s * cells;
-        const int* next = nextAll + (size_t)s * cells;
-        const SourceParams sp = src[s];
         int target = r0 * gy + c0;
         // first hop: delay = FLT_MAX, so only the start's loudness can stop the walk before it moves, and any selectable
         // neighbour is an improvement (Analyzer.cpp:357-386)
@@ -824,7 +843,7 @@ namespace pvc
             if (v >= 0)
             {
                 int n = next[v];
-                while (n >= 0) n = next[n];            // the jump rounds have resolved every link (see launchAnalyzer); this follows whatever a pathological case left
+                while (n >= 0) n = next[n];            // whatever the jump rounds left (see launchListenerDirection)
                 target = n & 0x7fffffff;
             }
         }
@@ -840,6 +859,47 @@ namespace pvc
         }
         float* out = res + ((size_t)r0 * gy + c0) * 8;
         out[4] = ox; out[5] = oy;
+    }
+
+    __global__ void __launch_bounds__(128)
+    walkResolveKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, float* __restrict__ results,
+                      const float* __restrict__ walkDelay, const int* __restrict__ nextAll)
+    {
+        const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const int r0 = blockIdx.y;
+        const int s = blockIdx.z;
+        if (c0 >= L.gy) return;
+        const size_t cells = (size_t)L.gx * L.gy;
+        walkResolve(A, src[s], results + (size_t)s * cells * 8, walkDelay + (size_t)s * cells, nextAll + (size_t)s * cells, r0, c0, L.gx, L.gy);
+    }
+
+    // Small grids (the reference's own contract: 70 x 70 .. 127 x 127 cells): links, every jump round and the resolve in ONE launch,
+    // one CTA per source, block barriers between the phases -- eight dependent launches cost more than the work they carry there.
+    constexpr int kWalkSmallCells = 128 * 128;
+    __global__ void __launch_bounds__(1024)
+    walkSmallKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, float* __restrict__ results,
+                    const float* __restrict__ walkDelay, int* __restrict__ nextAll, int rounds, int hops)
+    {
+        const int s = blockIdx.x;
+        const int gx = L.gx, gy = L.gy, cells = gx * gy;
+        float* res = results + (size_t)s * cells * 8;
+        const float* wd = walkDelay + (size_t)s * cells;
+        int* next = nextAll + (size_t)s * cells;
+        const SourceParams sp = src[s];
+        for (int u = threadIdx.x; u < cells; u += blockDim.x) next[u] = walkLink(A, sp, res, wd, u / gy, u % gy, gx, gy);
+        __syncthreads();
+        for (int k = 0; k < rounds; ++k)
+        {
+            for (int u = threadIdx.x; u < cells; u += blockDim.x)
+            {
+                int n = *((volatile int*)next + u);
+                if (n < 0) continue;
+                for (int h = 0; h < hops && n >= 0; ++h) n = *((volatile int*)next + n);
+                *((volatile int*)next + u) = n;
+            }
+            __syncthreads();
+        }
+        for (int u = threadIdx.x; u < cells; u += blockDim.x) walkResolve(A, sp, res, wd, next, u / gy, u % gy, gx, gy);
     }
 
     // The reference's walk, one thread per start cell (cross-check of the pointer-jumping kernels: PVC_WALK=sequential)
@@ -965,6 +1025,16 @@ namespace pvc
         else
         {
             const size_t cells = (size_t)L.gx * L.gy;
+            if (cells <= (size_t)kWalkSmallCells)
+            {
+                int rounds = 1;
+                for (long span = 4; span < (long)A.T; span *= 4) ++rounds;
+                walkSmallKernel<<<nsrc, 1024, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext, rounds, 3);
+                *launches += 1;
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) { setError("listener direction launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
+                return PVC_OK;
+            }
             walkNextKernel<<<grid, block, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext);
             // A pass follows up to kHops further links from every cell, so it multiplies the length every link spans by at
             // least kHops + 1 (in place: a link read here may already be longer); delays are integral sample indices that

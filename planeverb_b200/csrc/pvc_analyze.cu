@@ -878,13 +878,13 @@ namespace pvc
     constexpr int kWalkSmallCells = 128 * 128;
     __global__ void __launch_bounds__(1024)
     walkSmallKernel(Layout L, AnalyzeParams A, const SourceParams* __restrict__ src, float* __restrict__ results,
-                    const float* __restrict__ walkDelay, int* __restrict__ nextAll, int rounds, int hops)
+                    const float* __restrict__ walkDelay, int rounds, int hops)
     {
+        extern __shared__ int next[];                        // the links live in shared memory: a hop costs 30 cycles instead of an L2 round trip
         const int s = blockIdx.x;
         const int gx = L.gx, gy = L.gy, cells = gx * gy;
         float* res = results + (size_t)s * cells * 8;
         const float* wd = walkDelay + (size_t)s * cells;
-        int* next = nextAll + (size_t)s * cells;
         const SourceParams sp = src[s];
         for (int u = threadIdx.x; u < cells; u += blockDim.x) next[u] = walkLink(A, sp, res, wd, u / gy, u % gy, gx, gy);
         __syncthreads();
@@ -1029,7 +1029,14 @@ namespace pvc
             {
                 int rounds = 1;
                 for (long span = 4; span < (long)A.T; span *= 4) ++rounds;
-                walkSmallKernel<<<nsrc, 1024, 0, s->stream>>>(L, A, s->src, s->results, s->walkDelay, s->walkNext, rounds, 3);
+                static bool configured[64] = {};
+                if (!configured[s->device & 63])
+                {
+                    if (cudaFuncSetAttribute(walkSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmallCells * (int)sizeof(int)) != cudaSuccess)
+                    { setError("listener direction: shared-memory opt-in failed: %s", cudaGetErrorString(cudaGetLastError())); return PVC_ERR_CUDA; }
+                    configured[s->device & 63] = true;
+                }
+                walkSmallKernel<<<nsrc, 1024, cells * sizeof(int), s->stream>>>(L, A, s->src, s->results, s->walkDelay, rounds, 3);
                 *launches += 1;
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) { setError("listener direction launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }

@@ -175,3 +175,29 @@ def test_automatic_history_length_falls_back_to_a_streamed_solver(pv, scenes):
     rf, df = full.solve(listeners[2:3])
     assert np.array_equal(df[0], da[2]) and same_bits(rf[0], ra[2])
     full.close()
+
+
+@pytest.mark.parametrize("scene,n,T,history,nsrc", [
+    ("BigRoom", 1024, 16000, 2000, 1),      # a response four times config 3's length: K = 8
+    ("HugeRoom", 4096, 1000, 248, 1),       # a grid four times config 4's area: K = 5 (its full 4000-step history would be 268 GB)
+])
+def test_streamed_long_responses_and_huge_grids(pv, scenes, scene, n, T, history, nsrc):
+    """Sizes the streamed solver exists for, chosen so that the full history still fits the device once and the two solvers can be
+    compared bit for bit."""
+    size, scale = common.scaled_config(n)
+    boxes = common.boxes_of(scenes, scene, scale)
+    listeners = common.listeners_for(nsrc, scale)
+    free, _ = pv.device_memory(0)
+    need = pv.memory_requirement(n, n, T, nsrc) + pv.memory_requirement(n, n, T, nsrc, history_steps=history)
+    if need > 0.95 * free:
+        pytest.skip(f"needs {need / 1e9:.0f} GB of device memory, {free / 1e9:.0f} GB free")
+    full = pv.Scene(size, size, 275, T=T, max_sources=nsrc, efree=0.0447895788)
+    strm = pv.Scene(size, size, 275, T=T, max_sources=nsrc, efree=0.0447895788, history_steps=history)
+    for b in boxes:
+        full.add_aabb(*b); strm.add_aabb(*b)
+    rf, df = full.solve(listeners)
+    rs, ds = strm.solve(listeners)
+    assert (df < 3e38).sum() > 100000
+    assert np.array_equal(df, ds) and same_bits(rf, rs)
+    print(f"{scene} {n}^2 x{nsrc} T={T}: full history {full.timing()[2]:.1f} ms (variant {full.step_variant()}), streamed (history {history}) {strm.timing()[2]:.1f} ms")
+    full.close(); strm.close()

@@ -16,4 +16,8 @@ ncu --set full --clock-control none --import-source on -k regex:stepKernel -s 2 
     python tools/gpu_time_one.py HugeRoom 2048 400 2 0 3 > /dev/null 2> gpurun_out/r02_ncu_ws2.err
 ncu --set full --clock-control none --import-source on -k regex:encodeResponseKernel -s 3 -c 1 -o gpurun_out/r02_prof_encode -f \
     python bench.py --steps 1 --warmup 3 --T 400 --no-cpu-baseline --no-verify --no-extras > /dev/null 2> gpurun_out/r02_ncu_encode.err
-ls -la gpurun_out | grep r02_ | tail -12
+# streamed solver: config 4's eight 2048^2 sources as one batch (history 800 samples, 5 chunks): timing and the launch list of one solve
+python tools/gpu_time_one.py HugeRoom 2048 4000 8 0 3 800 > gpurun_out/r02_streamed_time.txt 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_streamed_launches.csv \
+    python tools/gpu_time_one.py HugeRoom 2048 4000 8 0 2 800 > /dev/null 2> gpurun_out/r02_ncu_streamed.err
+ls -la gpurun_out | grep r02_ | tail -14

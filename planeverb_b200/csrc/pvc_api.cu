@@ -54,12 +54,13 @@ namespace pvc
     }
 
     // variant 0 = auto: the kernel with the smallest ESTIMATED time per pass (4 time steps of every source of the batch).  The
-    // estimates are the measured pass periods of profiles/r02_resident_variants.txt (B200, microseconds):
+    // estimates are the measured pass periods of profiles/r02_resident_variants.txt and r02_small_tilings.txt (B200, microseconds):
     //   * resident kernel (pvc_step_res.cu; state in registers for the whole solve, only halo strips through the L2): a launch holds
     //     as many sources as fit co-resident and advances them one pass per period -- 3.0 (4-warp tiles, grids of the reference's own
-    //     contract), 4.2 (8-warp tiles; x 1.4 when two CTAs share an SM), 5.8 / 7.6 (10 / 12 warps), 5.5 / 6.3 / 6.8 (16 / 18 / 20
-    //     warps, barrier-free row exchange) -- a good third of it the
-    //     neighbour hand-over, so the period barely depends on how full the GPU is;
+    //     contract), 3.95 (8-warp tiles; x 1.45 when two CTAs share an SM), 4.3 / 4.7 / 5.15 / 5.5 / 6.3 / 6.8 (10 / 12 / 14 / 16 / 18 /
+    //     20 warps, one CTA per SM), all but the 4-warp tiles with the barrier-free row exchange -- a good third of it the
+    //     neighbour hand-over, so the period barely depends on how full the GPU is, and the smallest tiling whose tiles all fit
+    //     co-resident wins;
     //   * generational kernel (pvc_step_ws2.cu, TMA-staged tiles pulled from a work queue): 5.56 us per work item and SM (variant 47,
     //     56-row tiles), 3.9 (variant 50, 32-row tiles), and never less than the publish -> acquire -> TMA chain between generations
     //     (11.5 / 9.1 us).
@@ -74,7 +75,9 @@ namespace pvc
     }
     static int bestResident(const pvc_config& c, int sms, double* passUs)
     {
-        static const struct { int v; double period; } cand[] = { {67, 3.0}, {60, 4.2}, {61, 5.8}, {62, 7.6}, {63, 5.5}, {65, 6.3}, {64, 6.8} };
+        // measured pass periods (profiles/r02_small_tilings.txt); `shared` = the factor when two CTAs sit on one SM
+        static const struct { int v; double period, shared; } cand[] = { {67, 3.0, 1.4}, {69, 3.95, 1.45}, {72, 4.3, 1.0}, {70, 4.7, 1.0}, {71, 5.15, 1.0},
+                                                                         {63, 5.5, 1.0}, {65, 6.3, 1.0}, {64, 6.8, 1.0} };
         int best = 0;
         double bestUs = 0;
         for (const auto& k : cand)
@@ -85,7 +88,7 @@ namespace pvc
             if (k.v == 67 && tiles * c.max_sources > 64) continue;             // measured on 70^2 .. 191^2 only (0.41 / 1.19 ms against 0.46 / 1.45)
             const long perLaunch = cap / tiles < c.max_sources ? cap / tiles : c.max_sources;
             const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
-            const double us = (double)launches * k.period * (tiles * perLaunch > sms ? 1.4 : 1.0);
+            const double us = (double)launches * k.period * (tiles * perLaunch > sms ? k.shared : 1.0);
             if (!best || us < bestUs) { best = k.v; bestUs = us; }
         }
         *passUs = bestUs;

@@ -1121,7 +1121,7 @@ namespace pvc
     // tile variants (pvc_config::reserved): warps per CTA, rows per thread, min CTAs per SM, kind
     //   kind 0 one launch per 4 steps (fusedStepKernel)      1 persistent        2 TMA persistent   3 generational
     //        4 first warp-specialised generational           5 ws2 (pvc_step_ws2.cu)                6 resident (pvc_step_res.cu)
-    // The default build carries what the product selects -- 47 / 50 (ws2), 60..67 (resident), 18 (fallback without the TMA
+    // The default build carries what the product selects -- 47 / 50 (ws2), 63..67 and 69..72 (resident), 18 (fallback without the TMA
     // driver entry point) -- plus step_kernel = 1 (two-launch baseline, pvc_step.cu).  Everything else documents the
     // search (profiles/r01_variants.txt) and is compiled only with make EXTRA=-DPVC_ALL_VARIANTS.
     struct Variant { int nw, r, minBlocks, persistent, builtin; };
@@ -1137,8 +1137,10 @@ namespace pvc
                                          {8, 4, 1, 5, 1}, {10, 4, 1, 5, 0},                              // 50 (default when few work items), 51
                                          {12, 4, 1, 5, 0}, {12, 5, 1, 5, 0},                             // 52, 53
                                          {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0}, {8, 6, 2, 0, 0},   // 54..59 unused
-                                         {8, 4, 2, 6, 1}, {10, 4, 2, 6, 1}, {12, 4, 2, 6, 1}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1},    // 60..65: resident (pvc_step_res.cu)
-                                         {16, 5, 1, 6, 1}, {4, 4, 4, 6, 1} };       // 66: resident, 5 rows per warp; 67: resident, 4-warp tiles for tiny grids                                                                                          // 66: resident, 5 rows per warp
+                                         {8, 4, 2, 6, 0}, {10, 4, 2, 6, 0}, {12, 4, 2, 6, 0}, {16, 4, 1, 6, 1}, {20, 4, 1, 6, 1}, {18, 4, 1, 6, 1},    // 60..65: resident (pvc_step_res.cu); 60..62 (CTA barrier per sub-step, two CTAs per SM) superseded by 69 / 72 / 70
+                                         {16, 5, 1, 6, 1}, {4, 4, 4, 6, 1},         // 66: resident, 5 rows per warp; 67: resident, 4-warp tiles for tiny grids
+                                         {10, 4, 2, 6, 0}, {8, 4, 2, 6, 1},         // 68 / 69: resident, 10 / 8 warps, two CTAs per SM, barrier-free row exchange (68 superseded by 72)
+                                         {12, 4, 1, 6, 1}, {14, 4, 1, 6, 1}, {10, 4, 1, 6, 1} };      // 70 / 71 / 72: resident, 12 / 14 / 10 warps, one CTA per SM, barrier-free row exchange
     static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
     bool variantAvailable(int variant)

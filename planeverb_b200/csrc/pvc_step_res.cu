@@ -846,12 +846,20 @@ namespace pvc
         }
     }
 
-    // tilings: 60..62 = 8 / 10 / 12 warps x 4 rows, two CTAs per SM; 63, 65, 64 = 16 / 18 / 20 warps x 4 rows, 66 = 16 x 5, one CTA per SM;
-    // 67 = 4 warps x 4 rows (8 owned rows: the reference's own 70^2 .. 191^2 contract, where a pass is pure latency and more SMs help)
+    // tilings, all 4 rows per warp unless noted.  Barrier-free row exchange, one CTA per SM: 72 / 70 / 71 / 63 / 65 / 64 = 10 / 12 / 14 / 16 /
+    // 18 / 20 warps, 66 = 16 warps x 5 rows; two CTAs per SM: 69 = 8 warps.  CTA barrier per sub-step: 67 = 4 warps (8 owned rows: the
+    // reference's own 70^2 .. 191^2 contract, where a pass is pure latency and more SMs help).  Superseded, -DPVC_ALL_VARIANTS only:
+    // 60..62 = 8 / 10 / 12 warps with the CTA barrier, 68 = 10 warps, two CTAs per SM.
+#ifdef PVC_ALL_VARIANTS
+    #define PVC_RES_OLD_VARIANTS(X) X(60, 8, 4, 2, res::kSyncCta) X(61, 10, 4, 2, res::kSyncCta) X(62, 12, 4, 2, res::kSyncCta) X(68, 10, 4, 2, res::kSyncFlow)
+#else
+    #define PVC_RES_OLD_VARIANTS(X)
+#endif
     #define PVC_RES_VARIANTS(X) \
-        X(60, 8, 4, 2, res::kSyncCta) X(61, 10, 4, 2, res::kSyncCta) X(62, 12, 4, 2, res::kSyncCta) \
+        PVC_RES_OLD_VARIANTS(X) \
         X(63, 16, 4, 1, res::kSyncFlow) X(64, 20, 4, 1, res::kSyncFlow) X(65, 18, 4, 1, res::kSyncFlow) X(66, 16, 5, 1, res::kSyncFlow) \
-        X(67, 4, 4, 4, res::kSyncCta)
+        X(67, 4, 4, 4, res::kSyncCta) X(69, 8, 4, 2, res::kSyncFlow) \
+        X(70, 12, 4, 1, res::kSyncFlow) X(71, 14, 4, 1, res::kSyncFlow) X(72, 10, 4, 1, res::kSyncFlow)
     int launchResidentSteps(pvc_solver* s, int variant, int nsrc, int t0, int t1, float* hist, int* launches)
     {
         switch (variant)

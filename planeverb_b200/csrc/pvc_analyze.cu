@@ -170,8 +170,12 @@ namespace pvc
         int resolution;
     };
 
-    template <int HC>          // history strip width (Layout::hist_chunk) as a compile-time stride
-    __global__ void __launch_bounds__(128)
+    // MINB: blocks per SM the register allocation aims at.  0 = the compiler's own choice (64 registers, no spills) is
+    // best where the kernel is a chain of dependent loads (small grids: 70^2 0.077 ms against 0.083); 10 (48 registers, 16 bytes of
+    // spill) trades instruction-level for thread-level parallelism and is 4-6 % faster once the grid fills the GPU (HugeRoom
+    // 2 x 2048^2: 26.1 -> 24.9 ms; 12 blocks: 24.8 but slower on everything smaller; 6 / 4 blocks = 80 / 124 registers: 29.2 / 32.1 ms).
+    template <int HC, int MINB>          // HC: history strip width (Layout::hist_chunk) as a compile-time stride
+    __global__ void __launch_bounds__(128, MINB)
     encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
                          const SourceParams* __restrict__ src, float* __restrict__ results,
                          float* __restrict__ delay, float* __restrict__ walkDelay, const int* __restrict__ firstActive)
@@ -998,12 +1002,14 @@ namespace pvc
         const AnalyzeParams A = paramsOf(s);
         dim3 block(128, 1, 1);
         dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);     // one block per history strip and row
-        if (L.hist_chunk == kHistChunkDefault)
-            encodeResponseKernel<kHistChunkDefault><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
-                                                                                   s->hintsValid ? s->firstActive : nullptr);
+        const int* hints = s->hintsValid ? s->firstActive : nullptr;
+        const bool dense = (size_t)L.gx * L.gy * nsrc >= (size_t)1 << 20;          // enough threads to fill the GPU several times over
+        if (L.hist_chunk == kHistChunkDefault && dense)
+            encodeResponseKernel<kHistChunkDefault, 10><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+        else if (L.hist_chunk == kHistChunkDefault)
+            encodeResponseKernel<kHistChunkDefault, 0><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else if (L.hist_chunk == kValidCols)
-            encodeResponseKernel<kValidCols><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay,
-                                                                            s->hintsValid ? s->firstActive : nullptr);
+            encodeResponseKernel<kValidCols, 0><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else { setError("analyzer: unsupported history strip width %d", L.hist_chunk); return PVC_ERR_INVALID; }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }

@@ -174,6 +174,9 @@ namespace pvc
     // best where the kernel is a chain of dependent loads (small grids: 70^2 0.077 ms against 0.083); 10 (48 registers, 16 bytes of
     // spill) trades instruction-level for thread-level parallelism and is 4-6 % faster once the grid fills the GPU (HugeRoom
     // 2 x 2048^2: 26.1 -> 24.9 ms; 12 blocks: 24.8 but slower on everything smaller; 6 / 4 blocks = 80 / 124 registers: 29.2 / 32.1 ms).
+#ifndef PVC_AN_DENSE_MINB
+#define PVC_AN_DENSE_MINB 10
+#endif
     template <int HC, int MINB>          // HC: history strip width (Layout::hist_chunk) as a compile-time stride
     __global__ void __launch_bounds__(128, MINB)
     encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
@@ -1005,7 +1008,7 @@ namespace pvc
         const int* hints = s->hintsValid ? s->firstActive : nullptr;
         const bool dense = (size_t)L.gx * L.gy * nsrc >= (size_t)1 << 20;          // enough threads to fill the GPU several times over
         if (L.hist_chunk == kHistChunkDefault && dense)
-            encodeResponseKernel<kHistChunkDefault, 10><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+            encodeResponseKernel<kHistChunkDefault, PVC_AN_DENSE_MINB><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else if (L.hist_chunk == kHistChunkDefault)
             encodeResponseKernel<kHistChunkDefault, 0><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else if (L.hist_chunk == kValidCols)

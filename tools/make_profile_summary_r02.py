@@ -46,9 +46,10 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum', 'sm__cycles_elapsed.avg']
 what = {"r02_prof_res": "bench.py --T 400 (BigRoom 1024^2, 4 sources; ONE launch = one source, 100 passes x 4 steps)",
         "r02_prof_ws2": "tools/gpu_time_one.py HugeRoom 2048 400 2 0 (config 4's grid: 2048^2, two sources; one launch = 100 generations x 4 steps)",
-        "r02_prof_encode": "bench.py --T 400"}
+        "r02_prof_encode": "bench.py --T 400",
+        "r02_prof_encode_huge": "tools/gpu_time_one.py HugeRoom 2048 4000 2 0 (an all-onset scene at full length: two 2048^2 sources x 4000 steps, 134 GB of history)"}
 with open(os.path.join(OUT, f"{tag}_ncu_kernels.txt"), "w") as f:
-    for rep in ("r02_prof_res", "r02_prof_ws2", "r02_prof_encode"):
+    for rep in ("r02_prof_res", "r02_prof_ws2", "r02_prof_encode", "r02_prof_encode_huge"):
         path = os.path.join(GO, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue

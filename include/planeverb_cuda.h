@@ -182,6 +182,9 @@ PVC_API int  pvc_debug_timeline(pvc_solver* s, int nsrc, unsigned long long* out
  * order }.  Host arithmetic, needs no GPU; tests/test_abi.py checks that the order is a bijection in which every dependency of
  * an item (same source, previous generation) precedes it -- the kernel's deadlock-freedom argument.  PVC_ERR_INVALID if out of range. */
 PVC_API int  pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_per_source, int* out3);
+/* the same with the tile rows of a chunk split into bands of `band` rows (the order used on grids whose state exceeds the L2,
+ * pvc_internal.h::Ws2Order); out3[2] = tile_row * tiles_x + tile_column */
+PVC_API int  pvc_debug_ws2_item_banded(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_x, int tiles_y, int band, int* out3);
 /* Listener-direction algorithm of the analyzer (Analyzer::EncodeListenerDirection, Analyzer.cpp:340-431): 0 (default) = pointer
  * jumping over a link array, 1 = the reference's walk, one thread per start cell.  Bit-identical results; the second exists as the
  * cross-check of the first (tests/test_gpu_parity.py). */

@@ -929,7 +929,17 @@ int pvc_debug_ws2_item(int w, int gen_chunk, int src_group, int num_gen, int nsr
 {
     if (!out3 || gen_chunk < 1 || src_group < 1 || src_group > nsrc || num_gen < 1 || nsrc < 1 || tiles_per_source < 1 ||
         w < 0 || (long long)w >= (long long)num_gen * tiles_per_source * nsrc) { setError("pvc_debug_ws2_item: bad argument"); return PVC_ERR_INVALID; }
-    const pvc::Ws2Order ord = { gen_chunk, src_group, num_gen, nsrc, tiles_per_source, tiles_per_source * nsrc };
+    const pvc::Ws2Order ord = { gen_chunk, src_group, num_gen, nsrc, tiles_per_source, tiles_per_source * nsrc, 0, 0 };
+    const pvc::Ws2Item it = pvc::ws2DecodeItem(w, ord);
+    out3[0] = it.s; out3[1] = it.gen; out3[2] = it.o;
+    return PVC_OK;
+}
+
+int pvc_debug_ws2_item_banded(int w, int gen_chunk, int src_group, int num_gen, int nsrc, int tiles_x, int tiles_y, int band, int* out3)
+{
+    if (!out3 || gen_chunk < 1 || src_group < 1 || src_group > nsrc || num_gen < 1 || nsrc < 1 || tiles_x < 1 || tiles_y < 1 || band < 1 ||
+        w < 0 || (long long)w >= (long long)num_gen * tiles_x * tiles_y * nsrc) { setError("pvc_debug_ws2_item_banded: bad argument"); return PVC_ERR_INVALID; }
+    const pvc::Ws2Order ord = { gen_chunk, src_group, num_gen, nsrc, tiles_x * tiles_y, tiles_x * tiles_y * nsrc, band, tiles_x };
     const pvc::Ws2Item it = pvc::ws2DecodeItem(w, ord);
     out3[0] = it.s; out3[1] = it.gen; out3[2] = it.o;
     return PVC_OK;

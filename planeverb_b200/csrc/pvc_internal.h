@@ -171,7 +171,13 @@ namespace pvc
     // an item -- same source, the tile and its up-to-8 neighbours, previous generation -- precedes it in this order, which
     // is what makes the kernel's "pull the next item, wait for its dependencies" loop deadlock-free with co-resident CTAs.
     // Shared by the kernel and the host (pvc_debug_ws2_item -> tests/test_abi.py checks the invariant on the CPU).
-    struct Ws2Order { int genChunk, srcGroup, numGen, nsrc, tps, numTiles; };      // numTiles = tps * nsrc
+    // Grids whose ping-pong state does not fit the L2 even for one source (2048^2: 100 MB) add a level: inside a chunk the tile rows
+    // are split into BANDS of `band` rows that shift up by one tile row per generation (band k, generation g of the chunk: rows
+    // k*band - g .. (k+1)*band - g - 1, clipped to the grid, the last band reaching its end), and a band runs ALL the chunk's
+    // generations before the next band starts -- a band's state then stays in the L2 for the whole chunk instead of streaming
+    // through HBM every generation.  The skew is what keeps it a dependency-respecting order: item (g, row r) needs (g-1, r-1 .. r+1),
+    // which lie in the same band one generation earlier or in an earlier band.  band == 0: no bands (tx unused).
+    struct Ws2Order { int genChunk, srcGroup, numGen, nsrc, tps, numTiles, band, tx; };      // numTiles = tps * nsrc; tx = tiles per tile row
     struct Ws2Item { int s, gen, o; };                  // source, generation relative to the launch, position in the tile order
 #if defined(__CUDACC__)
     __host__ __device__
@@ -188,6 +194,30 @@ namespace pvc
         rem -= q * groupItems;
         const int rest = P.nsrc - q * P.srcGroup;
         const int sq = P.srcGroup < rest ? P.srcGroup : rest;
+        if (P.band > 0)
+        {
+            const int ty = P.tps / P.tx, nb = (ty + P.band - 1) / P.band, per = P.tx * sq;      // per: items of one tile row
+            int k = 0, g = 0, lo = 0;
+            bool found = false;
+            for (k = 0; k < nb && !found; ++k)
+                for (g = 0; g < gc; ++g)
+                {
+                    int a = k * P.band - g, b = (k == nb - 1) ? ty : (k + 1) * P.band - g;
+                    a = a < 0 ? 0 : (a > ty ? ty : a);
+                    b = b < 0 ? 0 : (b > ty ? ty : b);
+                    const int n = (b - a) * per;
+                    if (rem < n) { lo = a; found = true; break; }
+                    rem -= n;
+                }
+            const int r = lo + rem / per;
+            rem -= (rem / per) * per;
+            const int col = rem / sq;
+            Ws2Item bi;
+            bi.s = q * P.srcGroup + (rem - col * sq);
+            bi.gen = c * P.genChunk + g;
+            bi.o = r * P.tx + col;
+            return bi;
+        }
         const int g = rem / (sq * P.tps);
         rem -= g * (sq * P.tps);
         const int o = rem / sq;

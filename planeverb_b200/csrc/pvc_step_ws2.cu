@@ -175,6 +175,7 @@ namespace pvc
             int srcGroup, genChunk;                // item order: sources per L2-resident group, generations per chunk
             float courant;
             int finalPass;                         // the launch ends the response (0: a chunk of a streamed solve that another chunk follows)
+            int band;                              // tile rows per L2-resident band of the item order (0: none; pvc_internal.h::Ws2Order)
         };
         // state: loads, [buffer][p,vx,vy], box 128 x tile rows; coef: gx, gy, bp; store: [buffer][p,vx,vy], box 120 x (tile's owned rows), clipped to the
         // alloc grid; hist: 5-D {120 columns, T, strips, rows, sources}, box 120 x 1 x 1 x owned rows x 1 (TS variants only)
@@ -751,7 +752,7 @@ namespace pvc
                     nx.valid = w < total;
                     if (!nx.valid) return;
                     // item order (pvc_internal.h::ws2DecodeItem): every dependency of an item precedes it
-                    const Ws2Order ord = { A.genChunk, A.srcGroup, A.numGen, A.nsrc, tps, A.numTiles };
+                    const Ws2Order ord = { A.genChunk, A.srcGroup, A.numGen, A.nsrc, tps, A.numTiles, A.band, L.tiles_x };
                     const Ws2Item wi = ws2DecodeItem(w, ord);
                     const int o = wi.o;
                     nx.s = wi.s;
@@ -1285,10 +1286,16 @@ namespace pvc
                 // sources per group: as many as keep both ping-pong copies of the group's state (2 x 12 B per cell) inside
                 // ~85 MB of the 126 MB L2, groups balanced; the history stream is written evict-first and does not compete
                 const double perSource = 24.0 * (double)L.plane;
-                int maxSg = (int)(85.0e6 / perSource); if (maxSg < 1) maxSg = 1;
+                int maxSg = (int)(85.0e6 / perSource);
+                A.band = 0;
+                A.genChunk = 16;
+                // (Bands of tile rows for grids whose state exceeds the L2 even for one source -- pvc_internal.h::Ws2Order -- were built and
+                // measured on config 4's grid: a band small enough to stay in the L2 (15 tile rows at 2048^2) leaves an item only 270 items
+                // away from its dependencies, fewer than the CTAs in flight, and the polling costs 14 %; a band that keeps the distance
+                // (22 rows) no longer fits and changes nothing.  profiles/r02_l2_bands.txt.  A.band stays 0 outside tuning builds.)
+                if (maxSg < 1) maxSg = 1;
                 const int groups = (nsrc + maxSg - 1) / maxSg;
                 A.srcGroup = (nsrc + groups - 1) / groups;
-                A.genChunk = 16;
                 // protocol knobs, fixed in the release build (the measured optimum, profiles/r01_variants.txt); a tuning build
                 // (make EXTRA=-DPVC_TUNING) reads them from the environment
                 A.earlyFetch = 2; A.slowPathPoll = 1; A.lateRelease = 0; A.fenceMode = 0; A.tsDebug = 0;
@@ -1302,6 +1309,7 @@ namespace pvc
                 { static const char* td = getenv("PVC_TS_DEBUG"); if (td) A.tsDebug = atoi(td); }
                 if (eg && atoi(eg) > 0) A.srcGroup = atoi(eg);
                 if (ec && atoi(ec) > 0) A.genChunk = atoi(ec);
+                { static const char* eb = getenv("PVC_BAND_ROWS"); if (eb) A.band = (atoi(eb) > 0 && s->tileOrderNatural) ? atoi(eb) : 0; }
 #endif
 #ifdef PVC_WS2_TRACE
                 {

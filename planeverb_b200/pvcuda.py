@@ -28,7 +28,7 @@ PVC_SYMBOLS = [
     "pvc_compute_efree", "pvc_set_efree", "pvc_run", "pvc_synchronize", "pvc_clear_results",
     "pvc_fetch_results", "pvc_fetch_results_async", "pvc_fetch_wait", "pvc_fetch_result_at", "pvc_gather_results_async", "pvc_gather_wait", "pvc_fetch_ir", "pvc_fetch_pressure", "pvc_fetch_state",
     "pvc_last_timing", "pvc_last_launch_counts", "pvc_results_dev", "pvc_stream", "pvc_host_alloc", "pvc_host_free",
-    "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_set_walk_mode", "pvc_step_variant",
+    "pvc_mark", "pvc_mark_elapsed", "pvc_debug_timeline", "pvc_debug_ws2_item", "pvc_debug_ws2_item_banded", "pvc_set_walk_mode", "pvc_step_variant",
 ]
 PVX_SYMBOLS = [
     "pvx_create", "pvx_create_streamed", "pvx_history_steps", "pvx_destroy", "pvx_info", "pvx_pulse", "pvx_add_aabb", "pvx_remove_aabb",

@@ -144,6 +144,46 @@ def test_ws2_work_item_order_is_a_dependency_respecting_bijection(gen_chunk, src
     assert L.pvc_debug_ws2_item(0, gen_chunk, nsrc + 1, num_gen, nsrc, tps, out) == pvcuda.PVC_ERR_INVALID
 
 
+@pytest.mark.parametrize("gen_chunk,src_group,num_gen,nsrc,tx,ty,band", [
+    (8, 1, 20, 2, 3, 11, 4),       # config 4's shape in small: single-source groups, three bands, a partial last chunk
+    (8, 1, 8, 1, 2, 7, 7),         # one band = the whole grid: plain generation-major order
+    (4, 2, 9, 3, 2, 9, 2),         # bands shorter than a chunk (a band is empty in late generations), uneven last group
+    (16, 1, 5, 1, 4, 5, 3),        # fewer generations than a chunk
+])
+def test_ws2_banded_item_order_respects_the_tile_dependencies(gen_chunk, src_group, num_gen, nsrc, tx, ty, band):
+    """The banded order of the generational kernel (pvc_internal.h::Ws2Order: bands of tile rows that shift up one row per
+    generation and run a whole chunk of generations before the next band starts) gives up "generation g-1 entirely before
+    generation g" -- what must still hold is the kernel's actual wait condition: every (source, generation, tile) is exactly
+    one item, and the tile and its up-to-8 neighbours of the previous generation precede it."""
+    import ctypes as C
+    L = pvcuda.lib()
+    out = (C.c_int * 3)()
+    total = num_gen * nsrc * tx * ty
+    at = {}
+    for w in range(total):
+        assert L.pvc_debug_ws2_item_banded(w, gen_chunk, src_group, num_gen, nsrc, tx, ty, band, out) == 0
+        key = (out[0], out[1], out[2])
+        assert 0 <= key[0] < nsrc and 0 <= key[1] < num_gen and 0 <= key[2] < tx * ty and key not in at
+        at[key] = w
+    assert len(at) == total
+    for (s, g, o), w in at.items():
+        if g == 0:
+            continue
+        r, c = divmod(o, tx)
+        for dr in (-1, 0, 1):
+            for dc in (-1, 0, 1):
+                rr, cc = r + dr, c + dc
+                if 0 <= rr < ty and 0 <= cc < tx:
+                    assert at[(s, g - 1, rr * tx + cc)] < w, (s, g, r, c, rr, cc)
+    # a band really runs several generations before the next band starts: the order is not generation-major
+    if band < ty and num_gen > 1:
+        first_gen1 = min(w for (s, g, o), w in at.items() if g == 1 and s == 0)
+        last_gen0 = max(w for (s, g, o), w in at.items() if g == 0 and s == 0)
+        assert first_gen1 < last_gen0
+    assert L.pvc_debug_ws2_item_banded(total, gen_chunk, src_group, num_gen, nsrc, tx, ty, band, out) == pvcuda.PVC_ERR_INVALID
+    assert L.pvc_debug_ws2_item_banded(0, gen_chunk, src_group, num_gen, nsrc, tx, ty, 0, out) == pvcuda.PVC_ERR_INVALID
+
+
 def test_product_scene_scaling_matches_the_oracle():
     """bench.py sizes its scenes with the product's own helper (planeverb_b200.scenes, through pvx_derive); it must agree with
     the oracle's derivation to the bit for every BASELINE grid size."""

@@ -108,6 +108,24 @@ def test_every_step_kernel_variant_matches_oracle(pv, scenes, step_kernel, varia
     gpu.close()
 
 
+@pytest.mark.parametrize("scene,res", [("FloorPlanScene", 750), ("BigRoom", 600)])
+def test_contract_mode_at_high_resolutions(pv, scenes, scene, res):
+    """The reference's own contract -- the Sandbox's 25 m world with everything derived from the resolution (cfg 1) -- at
+    resolutions the golden set does not hold: 750 -> 191 x 191 cells, T = 1187 (the largest the Sandbox offers), and 600.  Grid
+    parameters, the free-field normaliser computed on the device, planes and every analyzer output against the oracle."""
+    gpu, ora, Ls = run_pair(pv, scenes, scene, res=res)
+    if res == 750:
+        assert (gpu.gx, gpu.gy, gpu.T) == (191, 191, 1187)
+    res_, dly = gpu.solve(Ls)
+    ora.generate(Ls[0])
+    ora.analyze(Ls[0])
+    for t in (0, 5, gpu.T // 2, gpu.T - 1):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(gpu.gx + 1, gpu.gy + 1)).all(), f"t={t}"
+    assert (ora.delay < 3e38).sum() > 1000
+    assert_results(res_[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    gpu.close()
+
+
 def test_config1_smallroom_128_500(pv, scenes):
     """BASELINE.json configs[0]: SmallRoom.pv, 128x128, 1 source, 500 steps."""
     gpu, ora, Ls = run_pair(pv, scenes, "SmallRoom", n=128, T=500)

@@ -50,8 +50,11 @@ PVU_EXPORT void PVU_CC PlaneverbSetListenerPosition(float x, float y, float z);
  *   PlaneverbWorkerState      0 no context, 1 the acoustics thread is running, 2 stopped by Exit, -1 stopped by a device
  *                             failure (GetOutput then keeps serving the last good frame);
  *   PlaneverbLastError        process-wide text of the last failure, including the acoustics thread's (empty if none); the
- *                             pointer stays valid until the calling thread asks again. */
+ *                             pointer stays valid until the calling thread asks again;
+ *   PlaneverbHistorySteps     samples of pressure history the context's solver keeps: 0 = the whole response, > 0 = the streamed
+ *                             solver (a grid whose full history does not fit the device, or PLANEVERB_HISTORY_STEPS), -1 no context. */
 PVU_EXPORT unsigned long long PVU_CC PlaneverbFramesCompleted(void);
+PVU_EXPORT int PVU_CC PlaneverbHistorySteps(void);
 PVU_EXPORT int PVU_CC PlaneverbWorkerState(void);
 PVU_EXPORT const char* PVU_CC PlaneverbLastError(void);
 

@@ -222,9 +222,12 @@ namespace Planeverb
         int device = 0;
         if (const char* env = std::getenv("PLANEVERB_CUDA_DEVICE")) device = std::atoi(env);
         // history length automatic (-1): a grid whose full pressure history does not fit the device runs on the streamed solver
-        // instead of failing with pv_NotEnoughMemory (only GetImpulseResponse is unavailable then)
+        // instead of failing with pv_NotEnoughMemory (only GetImpulseResponse is unavailable then).  PLANEVERB_HISTORY_STEPS forces
+        // a history length (operators of memory-shared devices; the plugin test of the streamed path).
+        int historySteps = -1;
+        if (const char* env = std::getenv("PLANEVERB_HISTORY_STEPS")) historySteps = std::atoi(env);
         const int rc = pvx_create_streamed(config->gridSizeInMeters.x, config->gridSizeInMeters.y, config->gridResolution,
-                                           0, -1.f, 1, device, 0, 0, -1, &ctx->scene);
+                                           0, -1.f, 1, device, 0, 0, historySteps, &ctx->scene);
         if (rc != PVC_OK)
         {
             setLastError(std::string("Init: ") + pvc_last_error());
@@ -483,6 +486,12 @@ unsigned long long PVU_CC PlaneverbFramesCompleted(void)
 {
     const std::shared_ptr<Planeverb::Context> ctx = Planeverb::current();
     return ctx ? ctx->frames.load(std::memory_order_acquire) : 0ull;
+}
+
+int PVU_CC PlaneverbHistorySteps(void)
+{
+    const std::shared_ptr<Planeverb::Context> ctx = Planeverb::current();
+    return (ctx && ctx->scene) ? pvx_history_steps(ctx->scene) : -1;
 }
 
 int PVU_CC PlaneverbWorkerState(void)

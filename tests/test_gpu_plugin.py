@@ -42,6 +42,7 @@ def plugin():
     L.PlaneverbFramesCompleted.restype = C.c_ulonglong
     L.PlaneverbLastError.restype = C.c_char_p
     L.PlaneverbWorkerState.restype = C.c_int
+    L.PlaneverbHistorySteps.restype = C.c_int
     yield L
     L.PlaneverbExit()
 
@@ -74,7 +75,25 @@ def test_invalid_config_leaves_no_context(plugin):
 
 @pytest.mark.parametrize("name", ["smallroom_70", "floorplan_70", "hugeroom_70"])
 def test_unity_session_matches_reference_outputs(plugin, name):
-    L = plugin
+    _unity_session(plugin, name)
+
+
+def test_unity_session_on_the_streamed_solver(plugin, monkeypatch):
+    """The same session with the context's solver forced onto a 104-sample pressure history (PLANEVERB_HISTORY_STEPS; what
+    Planeverb::Init falls back to by itself when the full history does not fit the device): T = 435 in five chunks per frame,
+    the same outputs bit for bit."""
+    monkeypatch.setenv("PLANEVERB_HISTORY_STEPS", "104")
+    _unity_session(plugin, "floorplan_70")
+    assert plugin.PlaneverbHistorySteps() == 104
+    plugin.PlaneverbExit()
+    monkeypatch.delenv("PLANEVERB_HISTORY_STEPS")
+    plugin.PlaneverbInit(25.0, 25.0, 275, 0, b".", 0, 1)
+    assert plugin.PlaneverbHistorySteps() == 0                     # the whole response fits: the ordinary solver
+    plugin.PlaneverbExit()
+    assert plugin.PlaneverbHistorySteps() == -1
+
+
+def _unity_session(L, name):
     meta, z = common.load_golden(name)
     L.PlaneverbInit(meta["size"], meta["size"], meta["resolution"], 0, b".", 0, 1)
     assert L.PlaneverbLastError() in (b"", None) or True

@@ -213,6 +213,33 @@ def test_edge_case_grids_and_listeners(pv, n, T, listener_cell):
     gpu.close()
 
 
+@pytest.mark.parametrize("variant,n", [(69, 96), (72, 128), (70, 120), (71, 96), (63, 112), (65, 128), (67, 96)])
+def test_resident_tilings_when_the_grid_is_a_multiple_of_the_owned_rows(pv, variant, n):
+    """gx a multiple of a tiling's owned rows (24 / 32 / 40 / 48 / 56 / 64 / 8): the padding row is then the first halo row of the
+    last tile row and is live state there (pvc_step_res.cu, liveRow).  Listener in the last interior cell, walls on the padding
+    row and column, T not a multiple of 4; planes, final state and every output against the oracle, for each tiling explicitly
+    (the automatic selection only ever picks one of them per grid size)."""
+    T = 97
+    size, _ = common.scaled_config(n)
+    ora = pvoracle.OracleSim(size, size, 275, T=T, efree=0.0447895788)
+    gpu = pv.Scene(size, size, 275, T=T, efree=0.0447895788, variant=variant)
+    assert gpu.step_variant() == variant
+    dx = float(ora.dx)
+    L = ((n - 0.5) * dx, 0.0, (n - 0.5) * dx)
+    assert ora.listener_cell(L) == (n - 1, n - 1)
+    for b in [(n * dx, 0.5 * n * dx, 4 * dx, 6 * dx, 0.5), (0.4 * n * dx, n * dx, 5 * dx, 2.5 * dx, 0.97), (0.5 * n * dx, 0.5 * n * dx, 7 * dx, 3 * dx, 0.8)]:
+        ora.add_aabb(*b); gpu.add_aabb(*b)
+    res, dly = gpu.solve([L])
+    ora.generate(L, keep_velocity=True); ora.analyze(L)
+    for t in (0, 1, 4, 5, T // 2, T - 1):
+        assert common.bit_equal(gpu.pressure(t), ora.hist[t].reshape(n + 1, n + 1)).all(), f"t={t}"
+    p, vx, vy = gpu.state()
+    assert common.bit_equal(vx, ora.hvx[-1].reshape(n + 1, n + 1)).all()
+    assert common.bit_equal(vy, ora.hvy[-1].reshape(n + 1, n + 1)).all()
+    assert_results(res[0], dly[0], ora.results, ora.delay, exclude=ora.clamped.astype(bool))
+    gpu.close()
+
+
 def test_listener_inside_a_wall_produces_no_onsets(pv):
     gpu = pv.Scene(25.0, 25.0, 275)
     ora = pvoracle.OracleSim(25.0, 25.0, 275)

@@ -109,7 +109,7 @@ PVC_API size_t pvc_memory_requirement(const pvc_config* cfg);
  * energy: Analyzer.cpp:146-247) with the running sums carried per cell; the state is checkpointed at every chunk start.
  * Backward sweep: the chunks are recomputed from their checkpoints in reverse order for the anti-causal Schroeder integral and
  * regression (Analyzer.cpp:282-326).  Same results as pvc_create's solver, bit for bit, at (2 - 1/K) x the time steps and 1/K
- * of the history memory.  Runs on the generational step kernel only (needs cuTensorMapEncodeTiled); pvc_fetch_ir /
+ * of the history memory.  Runs on the resident and the generational step kernels (not on the plain fallback 18); pvc_fetch_ir /
  * pvc_fetch_pressure are not available (there is no full history), pvc_fetch_state only after a run with analyze == 0. */
 PVC_API int  pvc_create_streamed(const pvc_config* cfg, int history_steps, pvc_solver** out);
 PVC_API size_t pvc_memory_requirement_streamed(const pvc_config* cfg, int history_steps);

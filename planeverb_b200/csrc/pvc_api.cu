@@ -94,7 +94,7 @@ namespace pvc
         *passUs = bestUs;
         return best;
     }
-    static int resolveVariant(const pvc_config& c, bool streamed = false)     // streamed: only the generational kernels start from a given state
+    static int resolveVariant(const pvc_config& c, bool streamed = false)     // streamed: the plain fallback kernel (18) has no chunked form
     {
         if (c.reserved != 0 || c.step_kernel != 0) return c.reserved;
         int sms = 148;
@@ -105,12 +105,12 @@ namespace pvc
         if (!tma) cudaGetLastError();
         double residentUs = 0;
         const int resident = bestResident(c, sms, &residentUs);
-        if (!tma) return streamed ? 0 : (resident ? resident : 18);
+        if (!tma) return resident ? resident : (streamed ? 0 : 18);
         const long cols = (c.gy + 1 + kValidCols - 1) / kValidCols;
         const double items47 = (double)((c.gx + 1 + 47) / 48) * cols * c.max_sources, items50 = (double)((c.gx + 1 + 23) / 24) * cols * c.max_sources;
         const double us47 = items47 * 5.56 / sms > 11.5 ? items47 * 5.56 / sms : 11.5;
         const double us50 = items50 * 3.9 / sms > 9.1 ? items50 * 3.9 / sms : 9.1;
-        if (!streamed && resident && residentUs <= us47 && residentUs <= us50) return resident;
+        if (resident && residentUs <= us47 && residentUs <= us50) return resident;
         return us50 < us47 ? 50 : 47;
     }
 
@@ -434,9 +434,9 @@ static int createSolver(const pvc_config* cfg, int history_steps, pvc_solver** o
     s->chunkT = streamChunk(cfg, history_steps);
     s->finalPass = 1;
     s->cfg.reserved = resolveVariant(*cfg, s->chunkT > 0);
-    if (s->chunkT && (cfg->step_kernel != 0 || (s->cfg.reserved != 47 && s->cfg.reserved != 50)))
+    if (s->chunkT && (cfg->step_kernel != 0 || !((s->cfg.reserved == 47 || s->cfg.reserved == 50 || variantKind(s->cfg.reserved) == 6) && variantAvailable(s->cfg.reserved))))
     {
-        setError("pvc_create_streamed: a streamed solve needs the generational step kernel (variant 47 or 50, TMA driver entry point); got step_kernel %d, variant %d",
+        setError("pvc_create_streamed: a streamed solve needs a step kernel that can continue from a stored state (the generational variants 47 / 50 or a resident tiling); got step_kernel %d, variant %d",
                  cfg->step_kernel, s->cfg.reserved);
         delete s;
         return PVC_ERR_INVALID;

@@ -128,6 +128,8 @@ namespace pvc
             int tilesPerSource, s0, nsrc;          // this launch solves sources s0 .. s0 + nsrc - 1
             int numGen, T;
             float courant;
+            int loadState;                         // start from the state planes (buffer 0) instead of from zero: a later chunk of a streamed solve
+            int finalPass;                         // the launch ends the response (0: a chunk of a streamed solve that another chunk follows)
 #ifdef PVC_TUNING
             int dbg;                               // tuning builds only: bit 0 no history stores, bit 1 no neighbour wait / halo reload (both: results invalid), bit 2 no nanosleep in the poll
             unsigned long long* trace;             // per CTA x traced pass x 8 %globaltimer stamps (null: off)
@@ -475,6 +477,23 @@ namespace pvc
             for (int j = 0; j < R; ++j)
                 #pragma unroll
                 for (int k = 0; k < 4; ++k) { p[j][k] = 0.f; vx[j][k] = 0.f; vy[j][k] = 0.f; }
+            if (A.loadState)
+            {
+                // A later chunk of a streamed solve (pvc_create_streamed) continues from what the previous chunk's final store -- or the
+                // restored checkpoint -- holds in buffer 0: the owned cells of every tile, i.e. this tile's own cells AND its halo (the
+                // neighbours' owned cells: what the mailbox would have delivered); whatever no tile owns is guard band or inert padding
+                // and zero in the planes as it is in the registers of an unbroken solve.
+                #pragma unroll
+                for (int j = 0; j < R; ++j)
+                {
+                    const float4 a = __ldcg(reinterpret_cast<const float4*>(A.p0 + src0 + (size_t)j * L.pitch));
+                    const float4 b = __ldcg(reinterpret_cast<const float4*>(A.vx0 + src0 + (size_t)j * L.pitch));
+                    const float4 c = __ldcg(reinterpret_cast<const float4*>(A.vy0 + src0 + (size_t)j * L.pitch));
+                    p[j][0] = a.x; p[j][1] = a.y; p[j][2] = a.z; p[j][3] = a.w;
+                    vx[j][0] = b.x; vx[j][1] = b.y; vx[j][2] = b.z; vx[j][3] = b.w;
+                    vy[j][0] = c.x; vy[j][1] = c.y; vy[j][2] = c.z; vy[j][3] = c.w;
+                }
+            }
 
             int firstGen = kNeverActive;          // first pass in which this warp's block recorded anything but zeros
             #pragma unroll 1
@@ -602,7 +621,7 @@ namespace pvc
                 else if (ownRows)
                 {
                     // ---- the final state of every owned cell into the state planes (Grid's m_grid after the last step)
-                    if (sp.dead && A.T == t0 + nsteps)
+                    if (sp.dead && A.T == t0 + nsteps && A.finalPass)
                     {
                         // the reference injects the last pulse sample even into a wall / padding cell, where nothing ever reads it
                         // again (FDTD.cpp:234): it only shows in the final state
@@ -701,14 +720,16 @@ namespace pvc
         static int launch(pvc_solver* s, int nsrc, int t0, int t1, float* hist, int* launches)
         {
             const Layout& L = s->L;
-            if (t0 != 0 || s->cur != 0) { setError("resident step kernel: must start at step 0"); return PVC_ERR_INVALID; }
+            // a chunk of a streamed solve (pvc_create_streamed): samples t0 .. t1 - 1 of the response, recorded as samples 0 .. t1 - t0 - 1
+            // of the chunk-sized history, continued from the state planes when t0 > 0
+            if ((t0 != 0 && !s->chunkT) || s->cur != 0) { setError("resident step kernel: must start at step 0"); return PVC_ERR_INVALID; }
             if (!hist || !s->lin[0] || !s->resXchg) { setError("resident step kernel: history / coefficient planes / mailbox missing"); return PVC_ERR_INVALID; }
             if (L.hist_chunk != kHistChunkDefault || L.tile_rows != NW * R) { setError("resident step kernel: layout does not match the variant"); return PVC_ERR_INVALID; }
             const int tps = L.tiles_x * L.tiles_y;
             const int cap = capacity<NW, R, MINB, SYNC>(s->device);
             if (cap < tps) { setError("resident step kernel: %d tiles per source exceed the %d co-resident CTAs of this device", tps, cap); return PVC_ERR_INVALID; }
             const int perLaunch = cap / tps;
-            const int gens = (t1 + kTileK - 1) / kTileK;
+            const int gens = (t1 - t0 + kTileK - 1) / kTileK;
             if (gens >= 65536) { setError("resident step kernel: %d passes exceed the 16-bit pass field of the mailbox tag", gens); return PVC_ERR_INVALID; }
             // every solve gets its own tag epoch, so words left in the mailbox by earlier solves can never match; when the 15-bit
             // epoch wraps the mailbox is cleared once
@@ -723,10 +744,12 @@ namespace pvc
             A.p0 = s->state[0][0]; A.vx0 = s->state[0][1]; A.vy0 = s->state[0][2];
             A.p1 = s->state[1][0]; A.vx1 = s->state[1][1]; A.vy1 = s->state[1][2];
             A.hist = hist; A.mode = s->slowMask; A.cP = s->lin[0]; A.sX = s->lin[1]; A.sY = s->lin[2];
-            A.firstActive = s->firstActive; A.src = s->src; A.pulse = s->pulse;
+            A.firstActive = (s->chunkT && !s->hintsValid) ? nullptr : s->firstActive;      // streamed solve: hints per chunk, forward sweep only
+            A.src = s->src; A.pulse = s->pulse + t0;
+            A.loadState = (s->chunkT && t0 > 0) ? 1 : 0; A.finalPass = s->chunkT ? s->finalPass : 1;
             A.xchg = reinterpret_cast<float4*>(s->resXchg); A.xchgSlot = (size_t)s->cfg.max_sources * L.plane; A.tagBase = s->resEpoch << 16;
             A.abortFlag = s->tileCounters; A.zero = 0;
-            A.tilesPerSource = tps; A.numGen = gens; A.T = t1; A.courant = s->cfg.courant;
+            A.tilesPerSource = tps; A.numGen = gens; A.T = t1 - t0; A.courant = s->cfg.courant;
 #ifdef PVC_TUNING
             { static const char* d = getenv("PVC_RES_DEBUG"); A.dbg = d ? atoi(d) : 0; }
             A.trace = nullptr;

@@ -26,15 +26,20 @@ def same_bits(a, b):
     return np.array_equal(np.ascontiguousarray(a, np.float32).view(np.uint32), np.ascontiguousarray(b, np.float32).view(np.uint32))
 
 
-@pytest.mark.parametrize("scene,n,T,history,nsrc", [
-    ("SmallRoom", None, 0, 104, 1),        # Sandbox default 70 x 70, T = 435: K = 5 chunks, the last one 19 samples
-    ("SmallRoom", None, 0, 8, 1),          # the shortest chunk there is: K = 55, every analysis window straddles chunk borders
-    ("SmallRoom", None, 0, 1000, 1),       # history longer than the response: one chunk, the chunk kernels against the full ones
-    ("FloorPlanScene", 250, 600, 304, 3),  # K = 2 (no checkpoint at all), three batched listeners, walls in most tiles
-    ("FloorPlanScene", 250, 601, 200, 3),  # K = 4 with a one-sample last chunk
-    ("BigRoom", 512, 1203, 400, 2),        # K = 4, T not a multiple of 4
+@pytest.mark.parametrize("scene,n,T,history,nsrc,variant", [
+    ("SmallRoom", None, 0, 104, 1, 0),        # Sandbox default 70 x 70, T = 435: K = 5 chunks, the last one 19 samples (resident 4-warp tiling)
+    ("SmallRoom", None, 0, 104, 1, 47),       # ... on the generational kernel
+    ("SmallRoom", None, 0, 8, 1, 0),          # the shortest chunk there is: K = 55, every analysis window straddles chunk borders
+    ("SmallRoom", None, 0, 8, 1, 50),
+    ("SmallRoom", None, 0, 1000, 1, 0),       # history longer than the response: one chunk, the chunk kernels against the full ones
+    ("FloorPlanScene", 250, 600, 304, 3, 0),  # K = 2 (no checkpoint at all), three batched listeners, walls in most tiles
+    ("FloorPlanScene", 250, 601, 200, 3, 47), # K = 4 with a one-sample last chunk
+    ("FloorPlanScene", 250, 601, 200, 3, 65), # ... on 18-warp resident tiles (96 registers, the config-3 kernel)
+    ("FloorPlanScene", 240, 601, 200, 2, 69), # ... on two-CTA 8-warp tiles, gx a multiple of the owned rows (live padding row across chunks)
+    ("BigRoom", 512, 1203, 400, 2, 0),        # K = 4, T not a multiple of 4 (resident 12-warp tiling)
+    ("BigRoom", 512, 1203, 400, 2, 47),
 ])
-def test_streamed_solve_equals_the_full_history_solve_and_the_oracle(pv, scenes, scene, n, T, history, nsrc):
+def test_streamed_solve_equals_the_full_history_solve_and_the_oracle(pv, scenes, scene, n, T, history, nsrc, variant):
     if n is None:
         size, scale = 25.0, 1.0
     else:
@@ -42,8 +47,8 @@ def test_streamed_solve_equals_the_full_history_solve_and_the_oracle(pv, scenes,
     boxes = common.boxes_of(scenes, scene, scale)
     listeners = common.listeners_for(nsrc, scale)
     full = pv.Scene(size, size, 275, T=T, max_sources=nsrc)
-    strm = pv.Scene(size, size, 275, T=T, max_sources=nsrc, history_steps=history, efree=float(full.efree))
-    assert strm.step_variant() in (47, 50) and (strm.gx, strm.gy, strm.T) == (full.gx, full.gy, full.T)
+    strm = pv.Scene(size, size, 275, T=T, max_sources=nsrc, history_steps=history, efree=float(full.efree), variant=variant)
+    assert (strm.gx, strm.gy, strm.T) == (full.gx, full.gy, full.T) and strm.step_variant() == (variant or full.step_variant())
     for b in boxes:
         full.add_aabb(*b); strm.add_aabb(*b)
     rf, df = full.solve(listeners)
@@ -108,7 +113,7 @@ def test_streamed_solver_rejects_what_it_cannot_run(pv):
     with pytest.raises(pv.PlaneverbCudaError):
         pv.Scene(25.0, 25.0, 275, history_steps=104, step_kernel=1)          # two-launch baseline: no chunked form
     with pytest.raises(pv.PlaneverbCudaError):
-        pv.Scene(25.0, 25.0, 275, history_steps=104, variant=63)             # resident kernel: starts from zero state only
+        pv.Scene(25.0, 25.0, 275, history_steps=104, variant=18)             # the plain one-launch-per-4-steps fallback: no chunked form
     # the free-field probe must fit the history
     with pytest.raises(pv.PlaneverbCudaError):
         pv.Scene(25.0, 25.0, 275, history_steps=8)

@@ -1,3 +1,4 @@
+"""Print the headline fields of a bench.py JSON line:  python tools/bench_show.py FILE   (value, e2e, verified, phases, launches, ms/step, extras)"""
 import json,sys
 d=json.loads([x for x in open(sys.argv[1]) if x.startswith("{")][-1])
 print(d["value"], d["e2e"]["value"], d.get("verified"), d.get("phases_ms_per_step"), d["gpu_launches"], d["ms_per_step"])

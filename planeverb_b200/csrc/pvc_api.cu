@@ -56,8 +56,8 @@ namespace pvc
     // variant 0 = auto: the kernel with the smallest ESTIMATED time per pass (4 time steps of every source of the batch).  The
     // estimates are the measured pass periods of profiles/r02_resident_variants.txt and r02_small_tilings.txt (B200, microseconds):
     //   * resident kernel (pvc_step_res.cu; state in registers for the whole solve, only halo strips through the L2): a launch holds
-    //     as many sources as fit co-resident and advances them one pass per period -- 3.0 (4-warp tiles, grids of the reference's own
-    //     contract), 3.95 (8-warp tiles; x 1.45 when two CTAs share an SM), 4.3 / 4.7 / 5.15 / 5.5 / 6.3 / 6.8 (10 / 12 / 14 / 16 / 18 /
+    //     as many sources as fit co-resident and advances them one pass per period -- 3.0 (4-warp tiles, x 1.3 when two CTAs share an SM),
+    //     3.95 (8-warp tiles; x 1.45 when two CTAs share an SM), 4.3 / 4.7 / 5.15 / 5.5 / 6.3 / 6.8 (10 / 12 / 14 / 16 / 18 /
     //     20 warps, one CTA per SM), all but the 4-warp tiles with the barrier-free row exchange -- a good third of it the
     //     neighbour hand-over, so the period barely depends on how full the GPU is, and the smallest tiling whose tiles all fit
     //     co-resident wins;
@@ -76,7 +76,7 @@ namespace pvc
     static int bestResident(const pvc_config& c, int sms, double* passUs)
     {
         // measured pass periods (profiles/r02_small_tilings.txt); `shared` = the factor when two CTAs sit on one SM
-        static const struct { int v; double period, shared; } cand[] = { {67, 3.0, 1.4}, {69, 3.95, 1.45}, {72, 4.3, 1.0}, {70, 4.7, 1.0}, {71, 5.15, 1.0},
+        static const struct { int v; double period, shared; } cand[] = { {67, 3.0, 1.3}, {69, 3.95, 1.45}, {72, 4.3, 1.0}, {70, 4.7, 1.0}, {71, 5.15, 1.0},
                                                                          {63, 5.5, 1.0}, {65, 6.3, 1.0}, {64, 6.8, 1.0} };
         int best = 0;
         double bestUs = 0;
@@ -85,7 +85,7 @@ namespace pvc
             if (!variantAvailable(k.v)) continue;
             const long tiles = residentTiles(c, k.v), cap = (long)sms * variantMinBlocks(k.v);
             if (tiles > cap) continue;
-            if (k.v == 67 && tiles * c.max_sources > 64) continue;             // measured on 70^2 .. 191^2 only (0.41 / 1.19 ms against 0.46 / 1.45)
+            if (k.v == 67 && tiles * c.max_sources > 2L * sms) continue;       // measured up to two CTAs per SM (256^2 .. 384^2, batches of 128^2)
             const long perLaunch = cap / tiles < c.max_sources ? cap / tiles : c.max_sources;
             const long launches = (c.max_sources + perLaunch - 1) / perLaunch;
             const double us = (double)launches * k.period * (tiles * perLaunch > sms ? k.shared : 1.0);

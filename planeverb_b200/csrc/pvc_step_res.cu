@@ -871,7 +871,8 @@ namespace pvc
 
     // tilings, all 4 rows per warp unless noted.  Barrier-free row exchange, one CTA per SM: 72 / 70 / 71 / 63 / 65 / 64 = 10 / 12 / 14 / 16 /
     // 18 / 20 warps, 66 = 16 warps x 5 rows; two CTAs per SM: 69 = 8 warps.  CTA barrier per sub-step: 67 = 4 warps (8 owned rows: the
-    // reference's own 70^2 .. 191^2 contract, where a pass is pure latency and more SMs help).  Superseded, -DPVC_ALL_VARIANTS only:
+    // reference's own 70^2 .. 191^2 contract and everything else whose 8-row tiles fit the GPU at most two to an SM -- a pass there
+    // is pure latency and more SMs help; with the barrier-free exchange these tiles are 7 % SLOWER, profiles/r02_small_tilings.txt).  Superseded, -DPVC_ALL_VARIANTS only:
     // 60..62 = 8 / 10 / 12 warps with the CTA barrier, 68 = 10 warps, two CTAs per SM.
 #ifdef PVC_ALL_VARIANTS
     #define PVC_RES_OLD_VARIANTS(X) X(60, 8, 4, 2, res::kSyncCta) X(61, 10, 4, 2, res::kSyncCta) X(62, 12, 4, 2, res::kSyncCta) X(68, 10, 4, 2, res::kSyncFlow)

@@ -177,7 +177,7 @@ namespace pvc
 #ifndef PVC_AN_DENSE_MINB
 #define PVC_AN_DENSE_MINB 10
 #endif
-    template <int HC, int MINB>          // HC: history strip width (Layout::hist_chunk) as a compile-time stride
+    template <int HC, int MINB, int BATCH>          // HC: history strip width (Layout::hist_chunk) as a compile-time stride
     __global__ void __launch_bounds__(128, MINB)
     encodeResponseKernel(Layout L, AnalyzeParams A, const float* __restrict__ hist, const float* __restrict__ w,
                          const SourceParams* __restrict__ src, float* __restrict__ results,
@@ -241,7 +241,9 @@ namespace pvc
     #ifndef PVC_AN_BATCH
     #define PVC_AN_BATCH 16
     #endif
-        constexpr int kBatch = PVC_AN_BATCH;          // streaming loads in flight per thread (A/B: make EXTRA=-DPVC_AN_BATCH=8)
+        // streaming loads in flight per thread: 16 (A/B 8 / 16 / 32 on grids that fill the GPU), 32 in the instantiation for tiny grids --
+        // there a thread's chain of dependent load rounds IS the kernel's run time, and registers are no concern
+        constexpr int kBatch = BATCH;
         int onset = -1;
         for (int t0 = onsetBegin; t0 < T && onset < 0; t0 += kBatch)
         {
@@ -272,7 +274,7 @@ namespace pvc
             const ptrdiff_t upOff = topEdge ? 0 : -(ptrdiff_t)L.hist_row;
             const ptrdiff_t leftOff = leftEdge ? 0 : (((c % HC) != 0) ? -1 : -(ptrdiff_t)T * hs + (hs - 1));
             float vx = 0.f, vy = 0.f;
-            constexpr int kCausalBatch = 4;
+            constexpr int kCausalBatch = BATCH / 4;
             for (int t0 = causalBegin; t0 < fluxEnd; t0 += kCausalBatch)
             {
                 float bp[kCausalBatch], bu[kCausalBatch], bl[kCausalBatch];
@@ -1006,13 +1008,17 @@ namespace pvc
         dim3 block(128, 1, 1);
         dim3 stripGrid((L.gy + L.hist_chunk - 1) / L.hist_chunk, L.gx, nsrc);     // one block per history strip and row
         const int* hints = s->hintsValid ? s->firstActive : nullptr;
-        const bool dense = (size_t)L.gx * L.gy * nsrc >= (size_t)1 << 20;          // enough threads to fill the GPU several times over
+        const size_t threads = (size_t)L.gx * L.gy * nsrc;
+        const bool dense = threads >= (size_t)1 << 20;          // enough threads to fill the GPU several times over
+        const bool tiny = threads <= (size_t)96 << 10;          // fewer than the GPU holds at once: latency-bound (70^2 .. 256^2: 5-13 % faster with 32 loads in flight; 512^2: 33 % slower)
         if (L.hist_chunk == kHistChunkDefault && dense)
-            encodeResponseKernel<kHistChunkDefault, PVC_AN_DENSE_MINB><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+            encodeResponseKernel<kHistChunkDefault, PVC_AN_DENSE_MINB, PVC_AN_BATCH><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+        else if (L.hist_chunk == kHistChunkDefault && tiny)
+            encodeResponseKernel<kHistChunkDefault, 0, 2 * PVC_AN_BATCH><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else if (L.hist_chunk == kHistChunkDefault)
-            encodeResponseKernel<kHistChunkDefault, 0><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+            encodeResponseKernel<kHistChunkDefault, 0, PVC_AN_BATCH><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else if (L.hist_chunk == kValidCols)
-            encodeResponseKernel<kValidCols, 0><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
+            encodeResponseKernel<kValidCols, 0, PVC_AN_BATCH><<<stripGrid, block, 0, s->stream>>>(L, A, s->hist, s->w, s->src, s->results, s->delay, s->walkDelay, hints);
         else { setError("analyzer: unsupported history strip width %d", L.hist_chunk); return PVC_ERR_INVALID; }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { setError("analyzer launch: %s", cudaGetErrorString(e)); return PVC_ERR_CUDA; }
